@@ -1,0 +1,252 @@
+/*
+ * pttspp_b200.h -- C ABI of the B200-native (sm_100a) PromptTTS++ inference hot path.
+ *
+ * The reference (line/promptttspp) has no FFI of its own: its "plugin" boundary is the
+ * Python object protocol that Hydra `instantiate` + app.py / egs/proposed/bin/synthesize.py
+ * rely on.  This header is the C boundary *beneath* that protocol:
+ * every entry point takes plain pointers, sizes and a cudaStream_t (as void*), returns an
+ * int status (0 = ok) and leaves a message for pttspp_last_error() otherwise.  The Python
+ * shims in promptttspp_b200/ bind it with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Activation layout ("cl" = channels-last): x[b][t][c], c contiguous, fp32.
+ * Reference-facing tensors keep the reference layout ([B, C, T]) and are transposed inside.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference repository root).
+ */
+#ifndef PTTSPP_B200_H_
+#define PTTSPP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTTSPP_ABI_VERSION 1
+
+typedef void* pttspp_stream_t; /* cudaStream_t */
+
+/* ---- status / introspection ------------------------------------------------------- */
+const char* pttspp_last_error(void);
+int pttspp_abi_version(void);
+/* 0 when the current CUDA device is compute capability 10.x (the only supported target). */
+int pttspp_device_check(void);
+/* Number of kernel launches issued by this library on the calling thread since the last
+ * reset (bench.py's `gpu_launches`). */
+int64_t pttspp_launch_count(void);
+void pttspp_reset_launch_count(void);
+
+/* ---- op level -------------------------------------------------------------------- */
+
+enum {
+  PTTSPP_ACT_NONE = 0,
+  PTTSPP_ACT_RELU = 1,
+  PTTSPP_ACT_GELU = 2,  /* exact erf GELU (torch.nn.GELU(), frame_prior.py:64) */
+  PTTSPP_ACT_SWISH = 3, /* x*sigmoid(x) (esp/conformer/swish.py:18) */
+  PTTSPP_ACT_GATE = 4,  /* sigmoid(v[2j])*tanh(v[2j+1]) -> Cout/2 outputs (denoiser.py:76-77,
+                           weights packed gate/filter interleaved) */
+  PTTSPP_ACT_TANH = 5
+};
+
+/* Conv1d / Linear / polyphase ConvTranspose1d on channels-last activations with a fused
+ * prologue (input length mask, per-channel input add) and epilogue:
+ *     v   = act(acc_scale * conv(in)[row, co] + bias[co] + addend[row, co])
+ *     out = (res_scale * res[row, co] + alpha * mask(row) * v + beta * out[row, co]) / out_div
+ * for output index m in [m_begin, m_begin + M): row = m * out_mul + out_off, the input row of
+ * tap k is m * in_stride + k * dil - pad; rows outside [0, T_in) (or >= in_len[b]) read as 0,
+ * rows outside [0, T_out) are not written.
+ * Replaces torch.nn.Conv1d / Linear / ConvTranspose1d call sites of the hot path, e.g.
+ * promptttspp/modules/denoiser.py:69-83, esp/transformer/multi_layer_conv.py:65-67,
+ * promptttspp/vocoders/bigvgan.py:42-47,90-102. */
+typedef struct {
+  const float* in;
+  int64_t in_bs; /* batch stride, elements */
+  int32_t in_ld; /* row stride, elements (multiple of 4) */
+  int32_t T_in;
+  int32_t Cin; /* multiple of 16 */
+  const float* w; /* packed [K][Cin][w_ld] (pttspp_pack_conv_weight) */
+  int32_t w_ld;   /* multiple of 4, >= Cout */
+  const float* bias; /* [Cout] or NULL */
+  int32_t K, dil, pad, in_stride;
+  float* out;
+  int64_t out_bs;
+  int32_t out_ld;
+  int32_t T_out;
+  int32_t Cout; /* pre-activation columns */
+  int32_t m_begin, M;
+  int32_t out_mul, out_off;
+  const int64_t* in_len;  /* optional [B] */
+  const int64_t* out_len; /* optional [B]: mask(row) = row < out_len[b] */
+  const float* in_add;    /* optional [Cin], added to rows inside [0, min(T_in, in_len)) */
+  const float* addend;    /* optional, indexed like out but with Cout columns */
+  int64_t addend_bs;
+  int32_t addend_ld;
+  int32_t act;
+  float acc_scale;
+  const float* res; /* optional, indexed like out */
+  int64_t res_bs;
+  int32_t res_ld;
+  float res_scale;
+  float alpha, beta;
+  float out_div; /* 0 = no division */
+  int32_t B;
+  int32_t impl; /* 0 = auto, 1 = force SIMT fp32, 2 = force tcgen05 split-fp16 */
+} pttspp_conv1d_desc;
+
+int pttspp_conv1d_cl(const pttspp_conv1d_desc* d, pttspp_stream_t stream);
+
+/* Weight packing runs once at load time on the HOST (v, g, packed are host pointers).
+ * Repack a torch Conv1d weight [Cout][Cin][K] into [K][Cin][w_ld];
+ * if g != NULL the weight-norm reparametrisation w = g * v / ||v|| (norm over dims 1,2;
+ * torch.nn.utils.weight_norm dim=0, bigvgan.py:24-36) is folded in.  `interleave_halves`
+ * packs output channel c of the first half to column 2c and of the second half to 2c+1. */
+int pttspp_pack_conv_weight(const float* v, const float* g, int Cout, int Cin, int K, float* packed,
+                            int w_ld, int interleave_halves, pttspp_stream_t stream);
+/* Repack a ConvTranspose1d weight [Cin][Cout][Kt] (+ optional weight-norm g[Cin]) into `stride`
+ * polyphase 2-D conv weights [stride][Kt/stride][Cin][w_ld] (bigvgan.py:90-102). */
+int pttspp_pack_convtr_weight(const float* v, const float* g, int Cin, int Cout, int Kt, int stride,
+                              float* packed, int w_ld, pttspp_stream_t stream);
+
+/* LayerNorm over the channel dim of x[b][t][c]:
+ *   x = in_scale * (in * mask_in) + in2 + row_add[t];  y = LN(x) * gamma + beta;  out = y * mask_out
+ * Replaces esp/transformer/layer_norm.py:21 (eps 1e-12), layers/norm.py:26-32, frame_prior.py:31-34
+ * and the `x*16 + pe` of modules/embedding.py:90-92. */
+typedef struct {
+  const float* in;
+  const float* in2;     /* optional, same indexing as in */
+  const float* row_add; /* optional [T][C] */
+  const float* gamma;
+  const float* beta;
+  float* out;
+  int64_t bs; /* batch stride (elements) of in/in2/out */
+  int32_t ld;
+  int32_t B, T, C; /* C multiple of 4, <= 1024 */
+  float eps, in_scale;
+  const int64_t* in_len;
+  const int64_t* out_len;
+} pttspp_layernorm_desc;
+int pttspp_layernorm_cl(const pttspp_layernorm_desc* d, pttspp_stream_t stream);
+
+/* Fused anti-aliased Snake: 2x polyphase up-sample (replicate pad) -> x + sin^2(a x)/(a + 1e-9)
+ * -> 2x low-pass down-sample, never materialising the 2x signal.  x, y: [B][L][C] channels-last.
+ * Replaces promptttspp/layers/activations.py:22-33 (UpSample1d :74-96, Snake :36-44,
+ * DownSample1d :99-138).  up_filter / down_filter: 12 taps each (device pointers, the
+ * checkpoint's `up.filter` / `down.lowpass.filter` buffers); log_alpha: [C]. */
+int pttspp_aa_snake_cl(const float* x, float* y, int B, int L, int C, const float* log_alpha,
+                       const float* up_filter, const float* down_filter, pttspp_stream_t stream);
+
+/* Duration quantisation + length regulator.
+ *   dur[b][i] = (i < len[b]) ? max(rint(exp(log_d[b][i])), 1) : 0    (variance_adaptor.py:179-181)
+ *   frame_len[b] = sum_i dur[b][i]                                   (variance_adaptor.py:183)
+ * then out[b][t][:] = x[b][idx(b,t)][:] for t < frame_len[b] else 0, idx = searchsorted(cumsum(dur), t,
+ * right) -- the gather that `x @ generate_path(...)` (utils/model.py:37-47,
+ * variance_adaptor.py:185-187) computes with a dense one-hot matmul. */
+int pttspp_duration_quantize(const float* log_d, const int64_t* phone_len, int B, int Tx, int64_t* dur,
+                             int64_t* frame_len, pttspp_stream_t stream);
+int pttspp_length_regulate(const float* x, const int64_t* dur, int B, int Tx, int C, int Ty, float* out,
+                           int32_t* idx_out /* optional [B][Ty], -1 on padding */, pttspp_stream_t stream);
+
+/* Relative-position multi-head self-attention (Transformer-XL style), both ESPnet variants.
+ *   scores = ((q+u) k^T + rel_shift((q+v) p^T)) / sqrt(d_k); masked softmax; . v
+ * q,k,v,out: [B][T][H*d_k]; p: [Tp][H*d_k] with Tp = T (legacy) or 2T-1 (new);
+ * bias_u, bias_v: [H][d_k]; lens: [B].  Replaces esp/transformer/attention.py:164-206 (legacy,
+ * incl. the wrapped upper triangle of its rel_shift :142-162), :262-305 (new) and :63-93.
+ * scratch: B*H*T*Tp floats. */
+int pttspp_relpos_attention(const float* q, const float* k, const float* v, const float* p,
+                            const float* bias_u, const float* bias_v, const int64_t* lens, int B, int T,
+                            int H, int dk, int legacy, float* scratch, float* out, pttspp_stream_t stream);
+
+/* ---- model level: BigVGAN ---------------------------------------------------------- */
+
+typedef struct pttspp_bigvgan pttspp_bigvgan_t;
+typedef struct {
+  int32_t in_channel;               /* 80 */
+  int32_t upsample_initial_channel; /* 512 */
+  int32_t num_upsamples;            /* <= 8 */
+  int32_t upsample_rates[8];
+  int32_t upsample_kernel_sizes[8];
+  int32_t num_kernels; /* <= 8 */
+  int32_t resblock_kernel_sizes[8];
+  int32_t num_dilations; /* layers per AMPBlock, <= 8 */
+  int32_t resblock_dilations[8][8];
+} pttspp_bigvgan_config;
+
+/* promptttspp/vocoders/bigvgan.py:71-118 (constructor), conf/vocoder/bigvgan.yaml. */
+int pttspp_bigvgan_create(const pttspp_bigvgan_config* cfg, pttspp_bigvgan_t** out);
+void pttspp_bigvgan_destroy(pttspp_bigvgan_t* h);
+/* One call per state_dict entry (reference key names: conv_pre.weight_g, mrfs.0.1.layers.2.act1.act.alpha,
+ * ...; `weight` instead of weight_g/weight_v after remove_weight_norm_).  `data` may be a host or a
+ * device pointer; the library keeps its own copy.  Replaces load_state_dict (app.py:35-37). */
+int pttspp_bigvgan_set_tensor(pttspp_bigvgan_t* h, const char* name, const float* data, const int64_t* shape,
+                              int ndim, pttspp_stream_t stream);
+/* Folds weight-norm, repacks all weights.  Fails naming the first missing key. */
+int pttspp_bigvgan_finalize(pttspp_bigvgan_t* h, pttspp_stream_t stream);
+size_t pttspp_bigvgan_workspace_bytes(const pttspp_bigvgan_t* h, int B, int T);
+/* mel: [B][in_channel][T] (reference layout), wav: [B][1][T*prod(rates)].
+ * Replaces BigVGAN.forward (bigvgan.py:120-131). */
+int pttspp_bigvgan_forward(pttspp_bigvgan_t* h, const float* mel, int B, int T, float* wav, void* workspace,
+                           size_t workspace_bytes, pttspp_stream_t stream);
+
+/* ---- model level: acoustic model (PromptTTSMDNDurCFG inference) --------------------- */
+
+typedef struct pttspp_acoustic pttspp_acoustic_t;
+typedef struct {
+  int32_t num_vocab;  /* 90 */
+  int32_t channels;   /* 256 */
+  int32_t emb_do_scale;
+  /* Conformer encoder (conf/model/prompttts_mdn_v2_wo_erg_final.yaml:13-30) */
+  int32_t enc_heads, enc_linear_units, enc_blocks, enc_ff_kernel, enc_cnn_kernel;
+  int32_t rel_pos_legacy; /* 1 = legacy, 0 = new */
+  /* variance adaptor (:32-64) */
+  int32_t dur_layers, dur_kernel, dur_gaussians;
+  int32_t pitch_layers, pitch_kernel;
+  int32_t fp_layers, fp_kernel;
+  /* prompt adaptor + style MDN (:79-91) */
+  int32_t prompt_in, prompt_mid, style_gaussians;
+  int32_t norm_style_emb;
+  /* diffusion decoder (:93-105) */
+  int32_t mel_dim, K_step, diff_layers, diff_channels, diff_kernel, diff_dilation_cycle;
+  float diff_scale; /* SinusoidalPosEmb scale */
+  float norm_scale; /* <= 0: use a_min/a_max */
+  float a_min, a_max;
+} pttspp_acoustic_config;
+
+int pttspp_acoustic_create(const pttspp_acoustic_config* cfg, pttspp_acoustic_t** out);
+void pttspp_acoustic_destroy(pttspp_acoustic_t* h);
+int pttspp_acoustic_set_tensor(pttspp_acoustic_t* h, const char* name, const float* data,
+                               const int64_t* shape, int ndim, pttspp_stream_t stream);
+int pttspp_acoustic_finalize(pttspp_acoustic_t* h, pttspp_stream_t stream);
+
+size_t pttspp_acoustic_encode_workspace_bytes(const pttspp_acoustic_t* h, int B, int Tx);
+/* Text side of PromptTTSMDNDurCFG.infer_batch (models/prompttts_mdn_v2_final/model.py:261-303 and
+ * variance_adaptor.py:178-183): embedding -> Conformer -> prompt adaptor + style MDN sample ->
+ * x + style -> MDN duration predictor -> integer durations.
+ *   phoneme [B][Tx] int64, phone_len [B] int64, pos_emb [Tp][C] (Tp = Tx legacy / 2Tx-1 new),
+ *   cls_emb [B][prompt_in] (BERT CLS), z_style [B][C] (the randn_like draw of model.py:191),
+ * outputs: enc_state [B][Tx][C] (x + style), dur [B][Tx] int64, frame_len [B] int64,
+ *   log_dur [B][Tx] (optional), style_emb [B][C] (optional). */
+int pttspp_acoustic_encode(pttspp_acoustic_t* h, const int64_t* phoneme, const int64_t* phone_len, int B,
+                           int Tx, const float* pos_emb, int Tp, const float* cls_emb, const float* z_style,
+                           float noise_scale, int use_max, float* enc_state, int64_t* dur,
+                           int64_t* frame_len, float* log_dur, float* style_emb, void* workspace,
+                           size_t workspace_bytes, pttspp_stream_t stream);
+
+size_t pttspp_acoustic_decode_workspace_bytes(const pttspp_acoustic_t* h, int B, int Tx, int Ty);
+/* Frame side (variance_adaptor.py:185-206, model.py:311-325, diffusion.py:320-356): length regulator ->
+ * frame prior -> pitch predictor -> + pitch embedding -> K_step DDPM ancestral sampling with the DiffNet
+ * denoiser -> mel.
+ *   pe_abs [Ty][C] sinusoidal table (modules/embedding.py:57-78), x_T [B][mel][Ty] and
+ *   z [K_step][B][mel][Ty] the Gaussian draws of diffusion.py:332 / :218 (z[0] is used at step K-1),
+ * outputs (reference layouts): mel [B][mel][Ty], log_cf0 [B][1][Ty], vuv [B][1][Ty];
+ *   cond_out [B][Ty][C] optional (decoder conditioning, for tests). */
+int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_state, const int64_t* dur,
+                           const int64_t* frame_len, int B, int Tx, int Ty, const float* pe_abs,
+                           const float* x_T, const float* z, float* mel, float* log_cf0, float* vuv,
+                           float* cond_out, void* workspace, size_t workspace_bytes, pttspp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTTSPP_B200_H_ */

@@ -1,0 +1,106 @@
+// Fused anti-aliased Snake activation on channels-last activations x[b][l][c]:
+//   u = 2x polyphase up-sample of x (replicate pad 5, 12-tap Kaiser sinc, gain 2, crop 15/15)
+//   s = u + sin^2(alpha*u) / (alpha + 1e-9),  alpha = exp(log_alpha[c])
+//   y = 2x low-pass down-sample of s (replicate pad 5 left / 6 right, 12 taps, stride 2)
+// Closed forms (derived from promptttspp/layers/activations.py:74-138, checked by the oracle):
+//   u[2j]   = 2 * sum_{d<6} x[clamp(j-3+d)] * f[11-2d]
+//   u[2j+1] = 2 * sum_{d<6} x[clamp(j-2+d)] * f[10-2d]
+//   y[t]    = sum_{k<12} s[clamp(2t+k-5, 0, 2L-1)] * g[k]
+// A thread owns one channel and a strip of TT consecutive outputs: 2*TT+10 up-sampled values are
+// produced in registers and never touch memory.  A warp spans 32 consecutive channels, so every
+// row access is one coalesced 128-byte line.  HBM-bound: 2*4 bytes per element.
+#include "common.h"
+
+namespace pttspp {
+namespace {
+
+constexpr int TT = 8;           // outputs per thread
+constexpr int NX = TT + 10;     // input samples per strip
+constexpr int NS = 2 * TT + 10; // up-sampled samples per strip
+
+__global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__ x, float* __restrict__ y, int L,
+                                                       int C, const float* __restrict__ log_alpha,
+                                                       const float* __restrict__ up_f,
+                                                       const float* __restrict__ down_f) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int t0 = (blockIdx.y * blockDim.y + threadIdx.y) * TT;
+  const int b = blockIdx.z;
+  if (c >= C || t0 >= L) return;
+  float f[12], g[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    f[i] = up_f[i];
+    g[i] = down_f[i];
+  }
+  const float alpha = expf(log_alpha[c]);
+  const float inv_alpha = 1.f / (alpha + 1e-9f);
+  const float* xb = x + (int64_t)b * L * C + c;
+
+  float xs[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    int l = t0 - 5 + i;
+    l = l < 0 ? 0 : (l > L - 1 ? L - 1 : l);
+    xs[i] = xb[(int64_t)l * C];
+  }
+  // up-sample + snake.  s[i] <-> up-sampled index m = 2*t0 - 5 + i:
+  //   i even -> m odd,  j = t0 - 3 + i/2, taps x[j-2+d] = xs[i/2 + d],      filter f[10-2d]
+  //   i odd  -> m even, j = t0 - 2 + (i-1)/2, taps x[j-3+d] = xs[(i-1)/2+d], filter f[11-2d]
+  float sv[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    float u = 0.f;
+    if ((i & 1) == 0) {
+#pragma unroll
+      for (int dd = 0; dd < 6; ++dd) u = fmaf(xs[i / 2 + dd], f[10 - 2 * dd], u);
+    } else {
+#pragma unroll
+      for (int dd = 0; dd < 6; ++dd) u = fmaf(xs[(i - 1) / 2 + dd], f[11 - 2 * dd], u);
+    }
+    u *= 2.f;
+    const float sn = sinf(u * alpha);
+    sv[i] = u + inv_alpha * (sn * sn);
+  }
+  // replicate padding of the up-sampled signal: indices below 0 / above 2L-1 repeat the edge value
+#pragma unroll
+  for (int i = 4; i >= 0; --i)
+    if (2 * t0 - 5 + i < 0) sv[i] = sv[i + 1];
+  const int imax = 2 * (L - t0) + 4;  // strip index of up-sampled sample 2L-1
+#pragma unroll
+  for (int i = 1; i < NS; ++i)
+    if (i > imax) sv[i] = sv[i - 1];
+
+  float* yb = y + (int64_t)b * L * C + c;
+#pragma unroll
+  for (int t = 0; t < TT; ++t) {
+    if (t0 + t < L) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) acc = fmaf(sv[2 * t + k], g[k], acc);
+      yb[(int64_t)(t0 + t) * C] = acc;
+    }
+  }
+}
+
+}  // namespace
+
+void aa_snake_cl(const float* x, float* y, int B, int L, int C, const float* log_alpha, const float* up_f,
+                 const float* down_f, cudaStream_t s) {
+  PT_CHECK(x && y && log_alpha && up_f && down_f, "aa_snake: null pointer");
+  PT_CHECK(x != y, "aa_snake: in-place operation is not supported");
+  PT_CHECK(B >= 1 && B <= 65535 && L >= 1 && C >= 1, "aa_snake: bad shape");
+  dim3 block(32, 8);
+  dim3 grid(ceil_div(C, 32), ceil_div(L, 8 * TT), B);
+  PT_CHECK(grid.y <= 65535, "aa_snake: L=%d too long for one launch", L);
+  aa_snake_kernel<<<grid, block, 0, s>>>(x, y, L, C, log_alpha, up_f, down_f);
+  PT_LAUNCHED();
+}
+
+}  // namespace pttspp
+
+extern "C" int pttspp_aa_snake_cl(const float* x, float* y, int B, int L, int C, const float* log_alpha,
+                                  const float* up_filter, const float* down_filter, pttspp_stream_t stream) {
+  PT_API_BEGIN
+  pttspp::aa_snake_cl(x, y, B, L, C, log_alpha, up_filter, down_filter, (cudaStream_t)stream);
+  PT_API_END
+}

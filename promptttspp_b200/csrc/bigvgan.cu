@@ -1,0 +1,252 @@
+// BigVGAN generator forward (promptttspp/vocoders/bigvgan.py:71-131) on channels-last activations.
+//
+//   mel [B][80][T] -> transpose -> conv_pre (k7) -> 4 x { polyphase ConvTranspose1d,
+//   3 AMP blocks x 3 layers of [AA-Snake -> dilated conv -> AA-Snake -> conv -> +x], averaged }
+//   -> AA-Snake -> conv_post (k7, C->1) -> tanh -> wav [B][1][240 T]
+//
+// Weight-norm is folded at finalize(); the MRF average is accumulated in the epilogue of each
+// block's last conv (out = (x + y)/n + out_old), so no separate add/div passes exist.
+#include "common.h"
+
+namespace pttspp {
+
+struct AAParams {
+  float* log_alpha = nullptr;
+  float* up_f = nullptr;
+  float* down_f = nullptr;
+};
+
+struct AMPLayerW {
+  PackedConv conv1, conv2;
+  AAParams act1, act2;
+};
+
+struct UpsampleW {
+  float* w = nullptr;  // [stride][J][Cin][w_ld]
+  float* bias = nullptr;
+  int Cin = 0, Cout = 0, Kt = 0, stride = 0, pad = 0, out_pad = 0, J = 0, w_ld = 0;
+};
+
+}  // namespace pttspp
+
+struct pttspp_bigvgan {
+  pttspp_bigvgan_config cfg;
+  pttspp::TensorStore store;
+  pttspp::DeviceBuffers dev;
+  bool finalized = false;
+  pttspp::PackedConv conv_pre, conv_post;
+  std::vector<pttspp::UpsampleW> ups;
+  std::vector<std::vector<std::vector<pttspp::AMPLayerW>>> mrfs;  // [stage][kernel][layer]
+  pttspp::AAParams act_post;
+};
+
+namespace pttspp {
+namespace {
+
+AAParams load_aa(const TensorStore& st, DeviceBuffers& dev, const std::string& prefix, int C) {
+  AAParams a;
+  a.log_alpha = dev.upload(st.get(prefix + ".act.alpha", C).data);
+  a.up_f = dev.upload(st.get(prefix + ".up.filter", 12).data);
+  a.down_f = dev.upload(st.get(prefix + ".down.lowpass.filter", 12).data);
+  return a;
+}
+
+int stage_channels(const pttspp_bigvgan_config& c, int stage /* 0 = conv_pre output */) {
+  return c.upsample_initial_channel >> stage;
+}
+
+int total_upsample(const pttspp_bigvgan_config& c) {
+  int r = 1;
+  for (int i = 0; i < c.num_upsamples; ++i) r *= c.upsample_rates[i];
+  return r;
+}
+
+int64_t max_stage_elems(const pttspp_bigvgan_config& c, int B, int T) {
+  int64_t mx = (int64_t)T * std::max(c.upsample_initial_channel, round_up(c.in_channel, 4));
+  int64_t L = T;
+  for (int i = 0; i < c.num_upsamples; ++i) {
+    L *= c.upsample_rates[i];
+    mx = std::max(mx, L * stage_channels(c, i + 1));
+  }
+  return mx * B;
+}
+
+}  // namespace
+}  // namespace pttspp
+
+using namespace pttspp;
+
+extern "C" int pttspp_bigvgan_create(const pttspp_bigvgan_config* cfg, pttspp_bigvgan_t** out) {
+  PT_API_BEGIN
+  PT_CHECK(cfg && out, "null argument");
+  PT_CHECK(cfg->num_upsamples >= 1 && cfg->num_upsamples <= 8 && cfg->num_kernels >= 1 && cfg->num_kernels <= 8 &&
+               cfg->num_dilations >= 1 && cfg->num_dilations <= 8,
+           "bigvgan: config out of range");
+  PT_CHECK(cfg->in_channel % 16 == 0, "bigvgan: in_channel=%d must be a multiple of 16", cfg->in_channel);
+  PT_CHECK((cfg->upsample_initial_channel >> cfg->num_upsamples) >= 16 &&
+               (cfg->upsample_initial_channel >> cfg->num_upsamples) % 16 == 0,
+           "bigvgan: channels must stay a multiple of 16 through all stages");
+  for (int i = 0; i < cfg->num_upsamples; ++i)
+    PT_CHECK(cfg->upsample_kernel_sizes[i] % cfg->upsample_rates[i] == 0,
+             "bigvgan: upsample kernel %d must be a multiple of its rate %d", cfg->upsample_kernel_sizes[i],
+             cfg->upsample_rates[i]);
+  for (int j = 0; j < cfg->num_kernels; ++j)
+    PT_CHECK(cfg->resblock_kernel_sizes[j] % 2 == 1, "bigvgan: resblock kernel sizes must be odd");
+  auto* h = new pttspp_bigvgan();
+  h->cfg = *cfg;
+  *out = h;
+  PT_API_END
+}
+
+extern "C" void pttspp_bigvgan_destroy(pttspp_bigvgan_t* h) { delete h; }
+
+extern "C" int pttspp_bigvgan_set_tensor(pttspp_bigvgan_t* h, const char* name, const float* data,
+                                         const int64_t* shape, int ndim, pttspp_stream_t stream) {
+  PT_API_BEGIN
+  PT_CHECK(h, "null handle");
+  h->store.set(name, data, shape, ndim, (cudaStream_t)stream);
+  h->finalized = false;
+  PT_API_END
+}
+
+extern "C" int pttspp_bigvgan_finalize(pttspp_bigvgan_t* h, pttspp_stream_t) {
+  PT_API_BEGIN
+  PT_CHECK(h, "null handle");
+  const auto& c = h->cfg;
+  h->dev.release();
+  h->ups.clear();
+  h->mrfs.clear();
+  const int C0 = c.upsample_initial_channel;
+  h->conv_pre = load_conv1d(h->store, h->dev, "conv_pre", C0, c.in_channel, 7, 1, 3);
+  for (int i = 0; i < c.num_upsamples; ++i) {
+    UpsampleW u;
+    u.Cin = C0 >> i;
+    u.Cout = C0 >> (i + 1);
+    u.Kt = c.upsample_kernel_sizes[i];
+    u.stride = c.upsample_rates[i];
+    u.pad = u.stride / 2 + u.stride % 2;  // bigvgan.py:98
+    u.out_pad = u.stride % 2;             // bigvgan.py:99
+    u.J = u.Kt / u.stride;
+    u.w_ld = round_up(u.Cout, 4);
+    const std::string p = "upsamples." + std::to_string(i);
+    std::vector<float> packed((size_t)u.stride * u.J * u.Cin * u.w_ld);
+    const int64_t n = (int64_t)u.Cin * u.Cout * u.Kt;
+    if (h->store.has(p + ".weight"))
+      pack_convtr_weight(h->store.get(p + ".weight", n).data.data(), nullptr, u.Cin, u.Cout, u.Kt, u.stride,
+                         packed.data(), u.w_ld, 0);
+    else
+      pack_convtr_weight(h->store.get(p + ".weight_v", n).data.data(), h->store.get(p + ".weight_g", u.Cin).data.data(),
+                         u.Cin, u.Cout, u.Kt, u.stride, packed.data(), u.w_ld, 0);
+    u.w = h->dev.upload(packed);
+    u.bias = h->dev.upload(h->store.get(p + ".bias", u.Cout).data);
+    h->ups.push_back(u);
+
+    std::vector<std::vector<AMPLayerW>> stage;
+    for (int j = 0; j < c.num_kernels; ++j) {
+      std::vector<AMPLayerW> block;
+      const int k = c.resblock_kernel_sizes[j];
+      for (int l = 0; l < c.num_dilations; ++l) {
+        const int dl = c.resblock_dilations[j][l];
+        const std::string lp = "mrfs." + std::to_string(i) + "." + std::to_string(j) + ".layers." + std::to_string(l);
+        AMPLayerW w;
+        w.conv1 = load_conv1d(h->store, h->dev, lp + ".conv1", u.Cout, u.Cout, k, dl, (k * dl - dl) / 2);
+        w.conv2 = load_conv1d(h->store, h->dev, lp + ".conv2", u.Cout, u.Cout, k, 1, k / 2);
+        w.act1 = load_aa(h->store, h->dev, lp + ".act1", u.Cout);
+        w.act2 = load_aa(h->store, h->dev, lp + ".act2", u.Cout);
+        block.push_back(w);
+      }
+      stage.push_back(block);
+    }
+    h->mrfs.push_back(stage);
+  }
+  const int Cl = C0 >> c.num_upsamples;
+  h->act_post = load_aa(h->store, h->dev, "act_post", Cl);
+  h->conv_post = load_conv1d(h->store, h->dev, "conv_post", 1, Cl, 7, 1, 3);
+  h->finalized = true;
+  PT_API_END
+}
+
+extern "C" size_t pttspp_bigvgan_workspace_bytes(const pttspp_bigvgan_t* h, int B, int T) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  const int64_t el = (max_stage_elems(h->cfg, B, T) + 63) / 64 * 64;
+  return (size_t)el * 6 * sizeof(float) + 256;
+}
+
+extern "C" int pttspp_bigvgan_forward(pttspp_bigvgan_t* h, const float* mel, int B, int T, float* wav, void* workspace,
+                                      size_t workspace_bytes, pttspp_stream_t stream) {
+  PT_API_BEGIN
+  PT_CHECK(h && mel && wav, "null argument");
+  PT_CHECK(h->finalized, "bigvgan: finalize() has not been called after the last set_tensor()");
+  PT_CHECK(B >= 1 && T >= 1, "bigvgan: empty input (B=%d, T=%d)", B, T);
+  PT_CHECK(workspace && workspace_bytes >= pttspp_bigvgan_workspace_bytes(h, B, T), "bigvgan: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  const auto& c = h->cfg;
+  const int64_t el = (max_stage_elems(c, B, T) + 63) / 64 * 64;
+  float* base = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  float* R[6];
+  for (int i = 0; i < 6; ++i) R[i] = base + (int64_t)i * el;
+  float *bx = R[0], *bxs = R[1], *bA = R[2], *bB = R[3], *t1 = R[4], *t2 = R[5];
+
+  // mel [B][C][T] -> [B][T][C]; conv_pre
+  transpose_bct_to_btc(mel, t1, B, c.in_channel, T, s);
+  {
+    auto d = conv_desc(h->conv_pre, t1, B, T, bxs);
+    conv1d_cl(d, s);
+  }
+  int L = T;
+  float* hcur = bxs;  // stage input [B][L][C]
+  for (int i = 0; i < c.num_upsamples; ++i) {
+    const UpsampleW& u = h->ups[i];
+    const int Lout = (L - 1) * u.stride - 2 * u.pad + u.Kt + u.out_pad;
+    // polyphase transposed conv: phase r writes rows m*stride + r - pad
+    for (int r = 0; r < u.stride; ++r) {
+      pttspp_conv1d_desc d;
+      memset(&d, 0, sizeof(d));
+      d.in = hcur; d.in_bs = (int64_t)L * u.Cin; d.in_ld = u.Cin; d.T_in = L; d.Cin = u.Cin;
+      d.w = u.w + (size_t)r * u.J * u.Cin * u.w_ld; d.w_ld = u.w_ld; d.bias = u.bias;
+      d.K = u.J; d.dil = 1; d.pad = u.J - 1; d.in_stride = 1;
+      d.out = bx; d.out_bs = (int64_t)Lout * u.Cout; d.out_ld = u.Cout; d.T_out = Lout; d.Cout = u.Cout;
+      const int off = r - u.pad;
+      d.m_begin = off < 0 ? ceil_div(-off, u.stride) : 0;
+      const int m_end = (Lout - 1 - off) / u.stride;  // last m with m*stride + off <= Lout-1
+      d.M = m_end - d.m_begin + 1;
+      d.out_mul = u.stride; d.out_off = off;
+      d.acc_scale = 1.f; d.res_scale = 1.f; d.alpha = 1.f; d.beta = 0.f; d.B = B;
+      conv1d_cl(d, s);
+    }
+    L = Lout;
+    const int C = u.Cout;
+    for (int j = 0; j < c.num_kernels; ++j) {
+      const float* cur = bx;
+      for (int l = 0; l < c.num_dilations; ++l) {
+        const AMPLayerW& w = h->mrfs[i][j][l];
+        aa_snake_cl(cur, t1, B, L, C, w.act1.log_alpha, w.act1.up_f, w.act1.down_f, s);
+        {
+          auto d = conv_desc(w.conv1, t1, B, L, t2);
+          conv1d_cl(d, s);
+        }
+        aa_snake_cl(t2, t1, B, L, C, w.act2.log_alpha, w.act2.up_f, w.act2.down_f, s);
+        const bool last = (l == c.num_dilations - 1);
+        float* dst = last ? bxs : ((cur == bA) ? bB : bA);
+        auto d = conv_desc(w.conv2, t1, B, L, dst);
+        d.res = cur; d.res_bs = (int64_t)L * C; d.res_ld = C;
+        if (last) {  // xs = (j ? xs : 0) + (x + y); the last block divides by num_kernels (bigvgan.py:124-127)
+          d.beta = (j == 0) ? 0.f : 1.f;
+          if (j == c.num_kernels - 1) d.out_div = (float)c.num_kernels;
+        }
+        conv1d_cl(d, s);
+        cur = dst;
+      }
+    }
+    hcur = bxs;
+    // the next stage's transposed conv reads bxs and writes bx: no aliasing
+  }
+  const int Cl = c.upsample_initial_channel >> c.num_upsamples;
+  aa_snake_cl(hcur, t1, B, L, Cl, h->act_post.log_alpha, h->act_post.up_f, h->act_post.down_f, s);
+  {
+    auto d = conv_desc(h->conv_post, t1, B, L, wav);
+    d.act = PTTSPP_ACT_TANH;
+    conv1d_cl(d, s);
+  }
+  PT_API_END
+}

@@ -1,0 +1,224 @@
+"""Generate the golden vectors under tests/golden/ by running the REFERENCE's own modules.
+
+Run where /root/reference exists (the build container), never on the GPU box:
+
+    python tests/golden/make_golden.py
+
+The reference has no tests, fixtures or pretrained weights, so parity is pinned
+by executing its nn.Modules on CPU with
+  * the synthetic, seeded checkpoints of promptttspp_b200/utils/synthetic.py (loaded strict into the
+    reference modules -- which also proves the state_dict key/shape contract),
+  * BERT replaced by a fixed sentence-embedding provider (no network / weights offline),
+  * Gaussian noise injected at the three places the reference draws it (model.py:191,
+    diffusion.py:332, diffusion.py:30-38/218), regenerated from a seed by `golden_noise`.
+Only inputs that cannot be regenerated from seeds and the reference OUTPUTS are stored (npz).
+"""
+import sys
+import warnings
+from contextlib import contextmanager
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+REF = Path("/root/reference")
+
+from golden_cases import (ACOUSTIC_CASES, AA_CASES, VOCODER_CASES, acoustic_inputs, golden_noise,  # noqa: E402
+                          vocoder_inputs)
+
+from promptttspp_b200.utils.synthetic import build_acoustic, build_vocoder, synthetic_state_dict  # noqa: E402
+
+warnings.filterwarnings("ignore")
+torch.set_grad_enabled(False)
+torch.set_num_threads(8)
+OUT = Path(__file__).resolve().parent
+
+
+class _FixedBert(torch.nn.Module):
+    """Stands in for promptttspp.modules.prompt_encoder.BertWrapper: returns the given embeddings."""
+
+    table = None
+
+    def __init__(self, *a, **k):
+        super().__init__()
+
+    def forward(self, prompts, device):
+        return _FixedBert.table[: len(prompts)].to(device)
+
+
+def reference_namespace():
+    sys.path.insert(0, str(REF))
+    import promptttspp.modules.prompt_encoder as pe
+
+    pe.BertWrapper = _FixedBert
+    from promptttspp.layers.embedding import PhonemeEmbedding
+    from promptttspp.models.prompttts_mdn_v2_final.model import PromptTTSMDNDurCFG
+    from promptttspp.modules.denoiser import DiffNet
+    from promptttspp.modules.diffusion import GaussianDiffusion
+    from promptttspp.modules.esp import ConformerEncoder
+    from promptttspp.modules.frame_prior import FramePriorNetwork
+    from promptttspp.modules.mdn import MDNLayer
+    from promptttspp.modules.prompt_encoder import PromptEncoder
+    from promptttspp.modules.style_encoder import StyleEncoder
+    from promptttspp.modules.variance_adaptor import MDNPredictor, Predictor, VarianceAdaptor
+
+    return dict(PhonemeEmbedding=PhonemeEmbedding, PromptTTSMDNDurCFG=PromptTTSMDNDurCFG, DiffNet=DiffNet,
+                GaussianDiffusion=GaussianDiffusion, ConformerEncoder=ConformerEncoder,
+                FramePriorNetwork=FramePriorNetwork, MDNLayer=MDNLayer, PromptEncoder=PromptEncoder,
+                StyleEncoder=StyleEncoder, MDNPredictor=MDNPredictor, Predictor=Predictor,
+                VarianceAdaptor=VarianceAdaptor)
+
+
+@contextmanager
+def injected_noise(z_style, x_T_fn, z_fn):
+    """Patch the reference's three noise sources.  x_T / z depend on Ty, known only mid-call."""
+    import promptttspp.modules.diffusion as dmod
+
+    state = {"n": 0}
+    orig_randn_like, orig_randn, orig_noise_like = torch.randn_like, torch.randn, dmod.noise_like
+
+    def randn_like(t, *a, **k):
+        assert tuple(t.shape) == tuple(z_style.shape), (t.shape, z_style.shape)
+        return z_style.clone()
+
+    def randn(*shape, **k):
+        shape = tuple(shape[0]) if len(shape) == 1 and not isinstance(shape[0], int) else tuple(shape)
+        return x_T_fn(shape)
+
+    def noise_like(shape, noise_fn, device, repeat=False):
+        out = z_fn(tuple(shape), state["n"])
+        state["n"] += 1
+        return out
+
+    torch.randn_like, torch.randn, dmod.noise_like = randn_like, randn, noise_like
+    try:
+        yield
+    finally:
+        torch.randn_like, torch.randn, dmod.noise_like = orig_randn_like, orig_randn, orig_noise_like
+
+
+def make_acoustic(ns):
+    for name, case in ACOUSTIC_CASES.items():
+        print("acoustic", name, case)
+        model = build_acoustic(rel_pos_type=case["rel_pos_type"], ns=ns, K_step=case["K_step"]).eval()
+        sd = synthetic_state_dict(build_acoustic(rel_pos_type=case["rel_pos_type"], bert=_FixedBert(),
+                                                 K_step=case["K_step"]),
+                                  seed=case["weight_seed"], frames_per_phoneme=case["frames_per_phoneme"])
+        missing = model.load_state_dict(sd, strict=True)  # key/shape contract with the reference
+        assert not missing.missing_keys and not missing.unexpected_keys
+        phoneme, lengths, cls_emb = acoustic_inputs(case)
+        _FixedBert.table = cls_emb
+        B = phoneme.shape[0]
+        noise = {}
+
+        def x_T_fn(shape):
+            noise["full"] = golden_noise(case, B, shape[-1])
+            return noise["full"].x_T.clone()
+
+        def z_fn(shape, n):
+            return noise["full"].z[n].clone()
+
+        z_style = golden_noise(case, B, None).z_style
+        inter = {}
+        va = model.variance_adaptor
+        orig_dur = va.duration_predictor.infer
+        va.duration_predictor.infer = lambda x, m: inter.setdefault("log_d", orig_dur(x, m))
+        orig_dec = model.decoder.inference
+        model.decoder.inference = lambda c, l, g=None: orig_dec(inter.setdefault("cond", c), l, g=g)
+        with injected_noise(z_style, x_T_fn, z_fn):
+            if case["api"] == "infer":
+                mel, log_cf0, vuv = model.infer(phoneme, style_prompt=["p"] * B, use_max=True,
+                                                noise_scale=case["noise_scale"], return_f0=True)
+                frame_lengths = torch.tensor([mel.shape[-1]], dtype=torch.float32)
+            else:
+                mel, log_cf0, vuv, frame_lengths = model.infer_batch(
+                    phoneme, lengths, style_prompt=["p"] * B, use_max=True, noise_scale=case["noise_scale"],
+                    return_f0=True)
+        log_d = inter["log_d"]
+        dur = log_d.exp().round().clamp_min(1).long().squeeze(1)
+        if case["api"] != "infer":
+            dur = dur * (torch.arange(phoneme.shape[1])[None] < lengths[:, None]).long()
+        print("   Ty", mel.shape[-1], "frame_lengths", frame_lengths.tolist(), "mel absmax", float(mel.abs().max()))
+        np.savez_compressed(
+            OUT / f"acoustic_{name}.npz",
+            mel=mel.numpy(), log_cf0=log_cf0.numpy(), vuv=vuv.numpy(), frame_lengths=frame_lengths.numpy(),
+            log_d=log_d.numpy(), duration=dur.numpy(), cond=inter["cond"].numpy(),
+        )
+
+
+def make_vocoder():
+    sys.path.insert(0, str(REF))
+    import promptttspp.vocoders as ref_voc
+
+    for name, case in VOCODER_CASES.items():
+        print("vocoder", name, case)
+        voc = build_vocoder(ns=ref_voc).eval()
+        sd = synthetic_state_dict(build_vocoder(), seed=case["weight_seed"])
+        voc.load_state_dict(sd, strict=True)
+        mel = vocoder_inputs(case)
+        wav = voc(mel)
+        print("   wav", tuple(wav.shape), "rms", float(wav.pow(2).mean().sqrt()))
+        out = {"wav": wav.numpy()}
+        if case.get("remove_weight_norm"):
+            from promptttspp.utils.model import remove_weight_norm_
+
+            voc.apply(remove_weight_norm_)
+            out["wav_nowm"] = voc(mel).numpy()
+        np.savez_compressed(OUT / f"vocoder_{name}.npz", **out)
+
+
+def make_ops():
+    """Op-level vectors from the reference layers: pin the closed forms used by the kernels."""
+    sys.path.insert(0, str(REF))
+    from promptttspp.layers.activations import AntiAliasActivation
+    from promptttspp.modules.esp.transformer.attention import (LegacyRelPositionMultiHeadedAttention,
+                                                               RelPositionMultiHeadedAttention)
+    from promptttspp.modules.esp.transformer.embedding import LegacyRelPositionalEncoding, RelPositionalEncoding
+    from promptttspp.utils.model import generate_path, sequence_mask
+
+    out = {}
+    g = torch.Generator().manual_seed(77)
+    for name, (B, C, L) in AA_CASES.items():
+        act = AntiAliasActivation(C).eval()
+        act.act.alpha.data = torch.rand(1, C, 1, generator=g) - 0.5
+        x = torch.randn(B, C, L, generator=g) * 2
+        out[f"aa_{name}_x"] = x.numpy()
+        out[f"aa_{name}_alpha"] = act.act.alpha.data.numpy()
+        out[f"aa_{name}_y"] = act(x).numpy()
+    out["aa_up_filter"] = AntiAliasActivation(1).up.filter.numpy()
+    out["aa_down_filter"] = AntiAliasActivation(1).down.lowpass.filter.numpy()
+    # rel_shift, both flavours, and the positional tables
+    T = 7
+    x = torch.randn(2, 2, T, T, generator=g)
+    out["rel_shift_legacy_in"] = x.numpy()
+    out["rel_shift_legacy_out"] = LegacyRelPositionMultiHeadedAttention(2, 8, 0.0).rel_shift(x).numpy()
+    x = torch.randn(2, 2, T, 2 * T - 1, generator=g)
+    out["rel_shift_new_in"] = x.numpy()
+    out["rel_shift_new_out"] = RelPositionMultiHeadedAttention(2, 8, 0.0).rel_shift(x).numpy()
+    d = torch.zeros(1, 9, 16)
+    out["pos_legacy"] = LegacyRelPositionalEncoding(16, 0.0).eval()(d)[1][0].numpy()
+    out["pos_new"] = RelPositionalEncoding(16, 0.0).eval()(d)[1][0].numpy()
+    # length regulator
+    dur = torch.tensor([[2, 1, 3, 0, 0], [1, 1, 1, 4, 2]])
+    xlen = torch.tensor([3, 5])
+    flen = dur.sum(1)
+    pm = sequence_mask(xlen, 5).unsqueeze(1).float()
+    fm = sequence_mask(flen).unsqueeze(1).float()
+    path = generate_path(dur, (pm.unsqueeze(-1) * fm.unsqueeze(2)).squeeze(1))
+    out["lr_dur"] = dur.numpy()
+    out["lr_path"] = path.numpy()
+    np.savez_compressed(OUT / "ops.npz", **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["ops", "vocoder", "acoustic"]
+    if "ops" in which:
+        make_ops()
+    if "vocoder" in which:
+        make_vocoder()
+    if "acoustic" in which:
+        make_acoustic(reference_namespace())
+    print("done")

@@ -1,0 +1,60 @@
+"""Case definitions shared by tests/golden/make_golden.py (reference side) and the parity tests.
+
+Everything here is regenerated from seeds with CPU generators, so only the reference's outputs
+need to be stored in tests/golden/*.npz.
+"""
+import torch
+
+from promptttspp_b200.models.prompttts_mdn_v2_final.model import InferNoise
+
+_randn = torch.randn  # bound at import: make_golden.py patches torch.randn while the reference runs
+
+ACOUSTIC_CASES = {
+    # B=3 ragged batch, legacy rel-pos (the released demo checkpoint's flavour)
+    "legacy_b3": dict(api="infer_batch", rel_pos_type="legacy", lengths=[10, 7, 4], weight_seed=1234,
+                      frames_per_phoneme=3.0, input_seed=2, noise_seed=102, noise_scale=1.0, K_step=100),
+    # new rel-pos flavour (training yaml), B=2
+    "new_b2": dict(api="infer_batch", rel_pos_type="new", lengths=[6, 9], weight_seed=1235,
+                   frames_per_phoneme=3.0, input_seed=3, noise_seed=103, noise_scale=0.5, K_step=100),
+    # single utterance through .infer (app.py path), BOS/EOS framed like text_to_sequence
+    "legacy_infer": dict(api="infer", rel_pos_type="legacy", lengths=[16], weight_seed=1234,
+                         frames_per_phoneme=3.0, input_seed=0, noise_seed=100, noise_scale=0.5, K_step=100),
+}
+
+VOCODER_CASES = {
+    "b2_t12": dict(weight_seed=4321, input_seed=3, B=2, T=12, remove_weight_norm=True),
+    "b1_t33": dict(weight_seed=4321, input_seed=4, B=1, T=33),
+}
+
+AA_CASES = {"c4_l37": (2, 4, 37), "c32_l3": (1, 32, 3), "c3_l1": (1, 3, 1), "c8_l64": (1, 8, 64)}
+
+
+def acoustic_inputs(case):
+    g = torch.Generator().manual_seed(case["input_seed"])
+    lengths = torch.tensor(case["lengths"], dtype=torch.int64)
+    B, Tx = len(case["lengths"]), int(lengths.max())
+    phoneme = torch.zeros(B, Tx, dtype=torch.int64)
+    for b, n in enumerate(case["lengths"]):
+        ids = torch.randint(3, 90, (n,), generator=g)
+        if case["api"] == "infer":
+            ids[0], ids[-1] = 1, 2  # BOS / EOS (promptttspp/text/eng.py:117)
+        phoneme[b, :n] = ids
+    cls_emb = torch.randn(B, 768, generator=g)
+    return phoneme, lengths, cls_emb
+
+
+def golden_noise(case, B, Ty, C=256, mel=80):
+    """z_style always; x_T / z once Ty is known (None otherwise)."""
+    g = torch.Generator().manual_seed(case["noise_seed"])
+    z_style = _randn(B, 1, C, generator=g)
+    if Ty is None:
+        return InferNoise(z_style, None, None)
+    x_T = _randn(B, mel, Ty, generator=g)
+    z = _randn(case["K_step"], B, mel, Ty, generator=g)
+    return InferNoise(z_style, x_T, z)
+
+
+def vocoder_inputs(case):
+    g = torch.Generator().manual_seed(case["input_seed"])
+    mel = torch.randn(case["B"], 80, case["T"], generator=g) * 2.0 - 5.0
+    return mel.clamp(-11.5, 2.0)

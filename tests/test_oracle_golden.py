@@ -1,0 +1,95 @@
+"""CPU: pin oracle/oracle.py against the golden vectors produced by the reference's own modules
+(tests/golden/make_golden.py).  The oracle is in turn the checker of every CUDA parity test."""
+import numpy as np
+import pytest
+import torch
+
+from golden_cases import ACOUSTIC_CASES, AA_CASES, VOCODER_CASES, acoustic_inputs, golden_noise, vocoder_inputs
+from oracle import oracle
+from promptttspp_b200.modules.prompt_encoder import FixedPromptEmbedding
+from promptttspp_b200.utils.synthetic import build_acoustic, build_vocoder, synthetic_state_dict
+
+torch.set_grad_enabled(False)
+
+
+@pytest.fixture(scope="module")
+def ops(golden_dir):
+    return {k: torch.from_numpy(v) for k, v in np.load(golden_dir / "ops.npz").items()}
+
+
+@pytest.mark.parametrize("name", list(AA_CASES))
+def test_aa_activation_matches_reference(ops, name):
+    x, alpha, y = ops[f"aa_{name}_x"], ops[f"aa_{name}_alpha"], ops[f"aa_{name}_y"]
+    up, down = ops["aa_up_filter"], ops["aa_down_filter"]
+    assert torch.allclose(oracle.aa_activation(x, alpha, up, down), y, atol=1e-6, rtol=1e-5)
+    # the closed form the CUDA kernel implements, incl. replicate padding on very short inputs
+    assert torch.allclose(oracle.aa_activation_closed_form(x, alpha, up, down), y, atol=2e-6, rtol=1e-5)
+
+
+def test_kaiser_filter_matches_reference_buffers(ops):
+    from promptttspp_b200.layers.activations import AntiAliasActivation
+
+    act = AntiAliasActivation(4)
+    assert torch.equal(act.up.filter, ops["aa_up_filter"])
+    assert torch.equal(act.down.lowpass.filter, ops["aa_down_filter"])
+
+
+def test_rel_shift_closed_forms(ops):
+    assert torch.equal(oracle.rel_shift_legacy(ops["rel_shift_legacy_in"]), ops["rel_shift_legacy_out"])
+    assert torch.equal(oracle.rel_shift_new(ops["rel_shift_new_in"]), ops["rel_shift_new_out"])
+
+
+def test_positional_tables(ops):
+    assert torch.equal(oracle.rel_pos_table(9, 16, legacy=True), ops["pos_legacy"])
+    assert torch.equal(oracle.rel_pos_table(9, 16, legacy=False), ops["pos_new"])
+
+
+def test_length_regulator_closed_form(ops):
+    dur, path = ops["lr_dur"], ops["lr_path"]
+    idx = oracle.length_regulate_indices(dur, path.shape[-1])
+    onehot = torch.zeros_like(path)
+    for b in range(idx.shape[0]):
+        for t in range(idx.shape[1]):
+            if idx[b, t] >= 0:
+                onehot[b, idx[b, t], t] = 1
+    assert torch.equal(onehot, path)
+
+
+@pytest.mark.parametrize("name", list(VOCODER_CASES))
+def test_bigvgan_oracle_matches_reference(golden_dir, name):
+    case = VOCODER_CASES[name]
+    gold = np.load(golden_dir / f"vocoder_{name}.npz")
+    sd = synthetic_state_dict(build_vocoder(), seed=case["weight_seed"])
+    wav = oracle.bigvgan_forward(sd, oracle.VOCODER_CFG, vocoder_inputs(case))
+    ref = torch.from_numpy(gold["wav"])
+    assert wav.shape == ref.shape
+    assert float((wav - ref).pow(2).mean().sqrt()) < 2e-6
+    if "wav_nowm" in gold.files:  # remove_weight_norm_ does not change the function
+        assert float((wav - torch.from_numpy(gold["wav_nowm"])).pow(2).mean().sqrt()) < 2e-6
+
+
+@pytest.mark.parametrize("name", list(ACOUSTIC_CASES))
+def test_acoustic_oracle_matches_reference(golden_dir, name):
+    case = ACOUSTIC_CASES[name]
+    gold = {k: torch.from_numpy(v) for k, v in np.load(golden_dir / f"acoustic_{name}.npz").items()}
+    model = build_acoustic(rel_pos_type=case["rel_pos_type"], bert=FixedPromptEmbedding(torch.zeros(1, 768)),
+                           K_step=case["K_step"])
+    sd = synthetic_state_dict(model, seed=case["weight_seed"], frames_per_phoneme=case["frames_per_phoneme"])
+    phoneme, lengths, cls_emb = acoustic_inputs(case)
+    B = phoneme.shape[0]
+    Ty = gold["mel"].shape[-1]
+    noise = golden_noise(case, B, Ty)
+    cfg = dict(oracle.ACOUSTIC_CFG, rel_pos_type=case["rel_pos_type"], K_step=case["K_step"])
+    mel, log_cf0, vuv, flen, inter = oracle.acoustic_infer_batch(
+        sd, cfg, phoneme, lengths, cls_emb, noise.z_style, noise.x_T, noise.z, noise_scale=case["noise_scale"],
+        return_intermediates=True)
+    assert torch.equal(inter["duration"].squeeze(1), gold["duration"]), "integer durations must be bit-exact"
+    assert torch.equal(flen, gold["frame_lengths"])
+    assert torch.allclose(inter["log_d"], gold["log_d"], atol=1e-5)
+    assert torch.allclose(inter["cond"].transpose(1, 2), gold["cond"], atol=2e-4)
+    assert torch.allclose(log_cf0, gold["log_cf0"], atol=1e-4)
+    assert torch.allclose(vuv, gold["vuv"], atol=1e-4)
+    err = (mel - gold["mel"]).abs().max()
+    sat = float((gold["mel"].abs() >= 5.999).float().mean())
+    print(f"{name}: mel max-abs err {float(err):.3e}, saturated fraction {sat:.3f}")
+    assert float(err) < 1e-3
