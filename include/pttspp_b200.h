@@ -38,6 +38,14 @@ int pttspp_device_check(void);
 int64_t pttspp_launch_count(void);
 void pttspp_reset_launch_count(void);
 
+/* Optional per-launch timing for bench.py's roofline leg (off by default, single-threaded use).
+ * While enabled, every op-level call records a CUDA event pair on its stream and accounts its
+ * ALGORITHMIC work; the report sums them per kernel family:
+ *   tag 0 conv1d CUDA-core, 1 conv1d tcgen05, 2 anti-aliased Snake, 3 LayerNorm, 4 attention, 5 other.
+ * ms / flops / bytes / calls: arrays of >= 6 entries.  prof_enable() also clears the counters. */
+void pttspp_prof_enable(int on);
+int pttspp_prof_report(double* ms, double* flops, double* bytes, int64_t* calls, int ntags);
+
 /* ---- op level -------------------------------------------------------------------- */
 
 enum {

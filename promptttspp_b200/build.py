@@ -23,7 +23,6 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
-    "-Xcompiler", "-fvisibility=hidden",
     "--expt-relaxed-constexpr",
 ]
 

@@ -89,6 +89,7 @@ void aa_snake_cl(const float* x, float* y, int B, int L, int C, const float* log
   PT_CHECK(x && y && log_alpha && up_f && down_f, "aa_snake: null pointer");
   PT_CHECK(x != y, "aa_snake: in-place operation is not supported");
   PT_CHECK(B >= 1 && B <= 65535 && L >= 1 && C >= 1, "aa_snake: bad shape");
+  ProfScope prof(PROF_AA_SNAKE, s, 0.0, 2.0 * 4.0 * B * (double)L * C);
   dim3 block(32, 8);
   dim3 grid(ceil_div(C, 32), ceil_div(L, 8 * TT), B);
   PT_CHECK(grid.y <= 65535, "aa_snake: L=%d too long for one launch", L);

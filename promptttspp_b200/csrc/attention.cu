@@ -191,6 +191,7 @@ void relpos_attention(const float* q, const float* k, const float* v, const floa
   PT_CHECK(B * H <= 65535 && B <= 65535, "relpos_attention: batch too large");
   if (B == 0 || T == 0) return;
   const int Tp = legacy ? T : 2 * T - 1;
+  ProfScope prof(PROF_ATTENTION, s, 2.0 * B * H * (double)T * dk * (2.0 * T + Tp), 4.0 * 4.0 * B * (double)T * H * dk);
   {
     const size_t smem = (size_t)2 * 32 * (dk + 1) * sizeof(float);
     if (smem > 48 * 1024)

@@ -62,6 +62,19 @@ struct Error : std::runtime_error {
   }                                       \
   return 0;
 
+// ---- optional per-launch timing (bench.py's roofline leg; off by default) -----------------
+// When enabled, a ProfScope records a CUDA event pair around the launches issued inside it and
+// accounts the ALGORITHMIC work of the call (flops / bytes as defined in DESIGN.md).
+enum ProfTag { PROF_CONV_SIMT = 0, PROF_CONV_UMMA = 1, PROF_AA_SNAKE = 2, PROF_LAYERNORM = 3, PROF_ATTENTION = 4,
+               PROF_OTHER = 5, PROF_NUM_TAGS = 6 };
+struct ProfScope {
+  int tag;
+  cudaStream_t s;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ProfScope(int tag, cudaStream_t s, double flops, double bytes);
+  ~ProfScope();
+};
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

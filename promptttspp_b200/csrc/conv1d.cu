@@ -201,6 +201,9 @@ void conv1d_cl(const pttspp_conv1d_desc& d, cudaStream_t s) {
   PT_CHECK(d.act != PTTSPP_ACT_GATE || d.Cout % 2 == 0, "conv1d: gate activation needs even Cout");
   PT_CHECK(d.B >= 1 && d.B <= 65535, "conv1d: batch %d out of range", d.B);
   if (d.M <= 0 || d.Cout <= 0) return;
+  const double flops = 2.0 * d.B * (double)d.M * d.Cout * (double)d.Cin * d.K;
+  const bool umma = (d.impl == 2) || (d.impl == 0 && conv1d_umma_supported(d));
+  ProfScope prof(umma ? PROF_CONV_UMMA : PROF_CONV_SIMT, s, flops, 0.0);
   if (d.impl == 2) {
     PT_CHECK(conv1d_umma_supported(d), "conv1d: tcgen05 path requested for an unsupported shape");
     conv1d_umma_cl(d, s);

@@ -87,6 +87,7 @@ void layernorm_cl(const pttspp_layernorm_desc& d, cudaStream_t s) {
            "layernorm: pointers must be 16-byte aligned");
   const int64_t rows = (int64_t)d.B * d.T;
   if (rows == 0) return;
+  ProfScope prof(PROF_LAYERNORM, s, 0.0, 2.0 * 4.0 * (double)rows * d.C);
   const int wpb = 8;
   layernorm_kernel<<<(unsigned)ceil_div64(rows, wpb), wpb * 32, 0, s>>>(d);
   PT_LAUNCHED();

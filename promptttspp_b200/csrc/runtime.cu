@@ -9,6 +9,33 @@ thread_local int64_t g_launch_count = 0;
 
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 
+// ---- per-launch profiler ---------------------------------------------------------------------
+namespace {
+struct ProfRec {
+  int tag;
+  cudaEvent_t e0, e1;
+};
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_recs;
+double g_prof_flops[PROF_NUM_TAGS] = {0}, g_prof_bytes[PROF_NUM_TAGS] = {0};
+int64_t g_prof_calls[PROF_NUM_TAGS] = {0};
+}  // namespace
+
+ProfScope::ProfScope(int tag_, cudaStream_t s_, double flops, double bytes) : tag(tag_), s(s_) {
+  if (!g_prof_on) return;
+  g_prof_flops[tag] += flops;
+  g_prof_bytes[tag] += bytes;
+  g_prof_calls[tag] += 1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, s);
+}
+ProfScope::~ProfScope() {
+  if (!e0) return;
+  cudaEventRecord(e1, s);
+  g_prof_recs.push_back({tag, e0, e1});
+}
+
 void TensorStore::set(const char* name, const float* data, const int64_t* shape, int ndim, cudaStream_t s) {
   PT_CHECK(name && data && (shape || ndim == 0), "set_tensor: null argument");
   HostTensor ht;
@@ -101,6 +128,31 @@ pttspp_conv1d_desc conv_desc(const PackedConv& c, const float* in, int B, int T,
 }
 
 }  // namespace pttspp
+
+extern "C" void pttspp_prof_enable(int on) {
+  using namespace pttspp;
+  for (auto& r : g_prof_recs) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof_recs.clear();
+  for (int i = 0; i < PROF_NUM_TAGS; ++i) g_prof_flops[i] = g_prof_bytes[i] = 0.0, g_prof_calls[i] = 0;
+  g_prof_on = on != 0;
+}
+
+extern "C" int pttspp_prof_report(double* ms, double* flops, double* bytes, int64_t* calls, int ntags) {
+  PT_API_BEGIN
+  using namespace pttspp;
+  PT_CHECK(ms && flops && bytes && calls && ntags >= PROF_NUM_TAGS, "prof_report: need %d slots", PROF_NUM_TAGS);
+  PT_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < PROF_NUM_TAGS; ++i) ms[i] = 0.0, flops[i] = g_prof_flops[i], bytes[i] = g_prof_bytes[i], calls[i] = g_prof_calls[i];
+  for (auto& r : g_prof_recs) {
+    float t = 0.f;
+    PT_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms[r.tag] += t;
+  }
+  PT_API_END
+}
 
 extern "C" const char* pttspp_last_error(void) { return pttspp::g_last_error.c_str(); }
 extern "C" int pttspp_abi_version(void) { return PTTSPP_ABI_VERSION; }

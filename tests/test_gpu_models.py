@@ -1,0 +1,136 @@
+"""GPU: model-level parity through the reference-facing module API (which calls the C ABI) against
+the committed golden vectors (reference outputs) and the oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from golden_cases import ACOUSTIC_CASES, VOCODER_CASES, acoustic_inputs, golden_noise, vocoder_inputs
+from oracle import oracle
+from promptttspp_b200.modules.prompt_encoder import FixedPromptEmbedding
+from promptttspp_b200.utils.synthetic import build_acoustic, build_vocoder, synthetic_state_dict
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+MEL_TOL = 1e-3   # max-abs on mel frames (BASELINE.json north_star)
+WAV_TOL = 1e-4   # RMS on vocoder waveforms
+
+
+def _rms(a, b):
+    return float((a - b).pow(2).mean().sqrt())
+
+
+@pytest.fixture(scope="module")
+def vocoder():
+    voc = build_vocoder()
+    voc.load_state_dict(synthetic_state_dict(voc, seed=4321), strict=True)
+    return voc.cuda().eval()
+
+
+@pytest.mark.parametrize("name", list(VOCODER_CASES))
+def test_bigvgan_matches_reference_golden(golden_dir, vocoder, name):
+    case = VOCODER_CASES[name]
+    ref = torch.from_numpy(np.load(golden_dir / f"vocoder_{name}.npz")["wav"])
+    wav = vocoder(vocoder_inputs(case).cuda()).cpu()
+    assert wav.shape == ref.shape
+    err = _rms(wav, ref)
+    print(f"bigvgan {name}: rms err {err:.3e}, max-abs {float((wav - ref).abs().max()):.3e}")
+    assert err < WAV_TOL
+
+
+def test_bigvgan_after_remove_weight_norm_and_reload(golden_dir, vocoder):
+    from promptttspp_b200.utils.model import remove_weight_norm_
+
+    case = VOCODER_CASES["b2_t12"]
+    ref = torch.from_numpy(np.load(golden_dir / "vocoder_b2_t12.npz")["wav"])
+    voc = build_vocoder()
+    voc.load_state_dict(synthetic_state_dict(voc, seed=999), strict=True)
+    voc = voc.cuda().eval()
+    mel = vocoder_inputs(case).cuda()
+    other = voc(mel).cpu()
+    assert _rms(other, ref) > 1e-2  # different weights -> different audio
+    voc.load_state_dict(synthetic_state_dict(build_vocoder(), seed=4321), strict=True)  # re-load must re-pack
+    assert _rms(voc(mel).cpu(), ref) < WAV_TOL
+    voc.apply(remove_weight_norm_)  # synthesize.py:116
+    assert _rms(voc(mel).cpu(), ref) < WAV_TOL
+
+
+def test_bigvgan_against_oracle_odd_shapes(vocoder):
+    sd = {k: v.cpu() for k, v in vocoder.state_dict().items()}
+    g = torch.Generator().manual_seed(9)
+    for B, T in ((1, 1), (3, 5), (1, 47)):
+        mel = (torch.randn(B, 80, T, generator=g) * 2 - 5).clamp(-11.5, 2)
+        ref = oracle.bigvgan_forward(sd, oracle.VOCODER_CFG, mel)
+        wav = vocoder(mel.cuda()).cpu()
+        assert wav.shape == (B, 1, 240 * T)
+        assert _rms(wav, ref) < WAV_TOL, (B, T, _rms(wav, ref))
+    assert vocoder(torch.zeros(0, 80, 4).cuda()).shape == (0, 1, 960)
+    with pytest.raises(ValueError):
+        vocoder(torch.zeros(1, 81, 4).cuda())
+
+
+def test_bigvgan_batch_invariance_full_size(vocoder):
+    """cfg3 size (16 x 1024 frames): every utterance must equal its own single-item run (utterances are
+    independent -- the property multi-GPU sharding relies on), and the output must be finite."""
+    g = torch.Generator().manual_seed(3)
+    mel = (torch.randn(16, 80, 1024, generator=g) * 2 - 5).clamp(-11.5, 2).cuda()
+    wav = vocoder(mel)
+    assert wav.shape == (16, 1, 245760) and torch.isfinite(wav).all()
+    for b in (0, 7, 15):
+        single = vocoder(mel[b:b + 1])
+        assert torch.equal(single, wav[b:b + 1])
+
+
+@pytest.mark.parametrize("name", list(ACOUSTIC_CASES))
+def test_acoustic_matches_reference_golden(golden_dir, name):
+    case = ACOUSTIC_CASES[name]
+    gold = {k: torch.from_numpy(v) for k, v in np.load(golden_dir / f"acoustic_{name}.npz").items()}
+    phoneme, lengths, cls_emb = acoustic_inputs(case)
+    model = build_acoustic(rel_pos_type=case["rel_pos_type"], bert=FixedPromptEmbedding(cls_emb),
+                           K_step=case["K_step"])
+    model.load_state_dict(synthetic_state_dict(model, seed=case["weight_seed"],
+                                               frames_per_phoneme=case["frames_per_phoneme"]), strict=True)
+    model = model.cuda().eval()
+    B = phoneme.shape[0]
+    Ty = gold["mel"].shape[-1]
+    noise = golden_noise(case, B, Ty)
+    if case["api"] == "infer":
+        mel, log_cf0, vuv = model.infer(phoneme.cuda(), style_prompt=["p"] * B, use_max=True,
+                                        noise_scale=case["noise_scale"], return_f0=True, noise=noise)
+        flen = torch.tensor([mel.shape[-1]], dtype=torch.float32)
+    else:
+        mel, log_cf0, vuv, flen = model.infer_batch(phoneme.cuda(), lengths.cuda(), style_prompt=["p"] * B,
+                                                    use_max=True, noise_scale=case["noise_scale"], return_f0=True,
+                                                    noise=noise)
+    ndiff = int((model.last_durations.cpu() != gold["duration"]).sum())
+    print(f"{name}: durations differing {ndiff}, log_d max err "
+          f"{float((model.last_log_durations.cpu() - gold['log_d'].squeeze(1)).abs().max()):.3e}")
+    assert ndiff == 0, "integer durations must be bit-exact"
+    assert torch.equal(flen.cpu(), gold["frame_lengths"])
+    assert torch.allclose(log_cf0.cpu(), gold["log_cf0"], atol=1e-3)
+    assert torch.allclose(vuv.cpu(), gold["vuv"], atol=1e-3)
+    err = float((mel.cpu() - gold["mel"]).abs().max())
+    print(f"{name}: mel max-abs err {err:.3e}")
+    assert err < MEL_TOL
+
+
+def test_acoustic_default_rng_and_shapes():
+    """Without injected noise the module draws torch.randn itself (same call sequence as the reference):
+    seeded runs reproduce, outputs are masked beyond frame_lengths."""
+    case = ACOUSTIC_CASES["legacy_b3"]
+    phoneme, lengths, cls_emb = acoustic_inputs(case)
+    model = build_acoustic(bert=FixedPromptEmbedding(cls_emb), K_step=8)
+    model.load_state_dict(synthetic_state_dict(model, seed=7, frames_per_phoneme=3.0), strict=True)
+    model = model.cuda().eval()
+    outs = []
+    for _ in range(2):
+        torch.manual_seed(123)
+        outs.append(model.infer_batch(phoneme.cuda(), lengths.cuda(), style_prompt=["a", "b", "c"], return_f0=True))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    mel, log_cf0, vuv, flen = outs[0]
+    assert flen.dtype == torch.float32 and mel.shape[-1] == int(flen.max())
+    for b in range(3):
+        n = int(flen[b])
+        assert torch.count_nonzero(mel[b, :, n:]) == 0 and torch.count_nonzero(log_cf0[b, :, n:]) == 0
+    assert isinstance(model.infer(phoneme[:1, :10].cuda(), style_prompt="one"), torch.Tensor)
