@@ -230,7 +230,9 @@ __global__ void __launch_bounds__(256) duration_quantize_kernel(const float* __r
   for (int i = threadIdx.x; i < Tx; i += blockDim.x) {
     long long dq = 0;
     if ((long long)i < len) {
-      const float e = rintf(expf(log_d[(int64_t)b * Tx + i]));  // round-half-to-even == torch.round
+      // exp in double, rounded once to fp32: the correctly rounded value (a 1-ulp deviation of expf can flip
+      // the integer at a .5 boundary and shift every later frame); rintf = round-half-to-even = torch.round
+      const float e = rintf((float)exp((double)log_d[(int64_t)b * Tx + i]));
       dq = (long long)fmaxf(e, 1.f);
     }
     dur[(int64_t)b * Tx + i] = dq;

@@ -156,7 +156,7 @@ def synthetic_state_dict(module, seed=1234, frames_per_phoneme=8.0):
         out[k] = out[k] * 0.5
     pre = "variance_adaptor.duration_predictor.out_layer."
     if pre + "mu.weight" in out:
-        out[pre + "mu.weight"] = out[pre + "mu.weight"] * 0.05 * math.sqrt(out[pre + "mu.weight"].shape[1])
+        out[pre + "mu.weight"] = out[pre + "mu.weight"] * 0.02 * math.sqrt(out[pre + "mu.weight"].shape[1])
         out[pre + "mu.bias"] = torch.full_like(out[pre + "mu.bias"], math.log(frames_per_phoneme)) + normal(
             tuple(out[pre + "mu.bias"].shape), 0.05)
         out[pre + "log_sigma.weight"] = out[pre + "log_sigma.weight"] * 0.2
