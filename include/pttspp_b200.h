@@ -101,6 +101,23 @@ typedef struct {
   float out_div; /* 0 = no division */
   int32_t B;
   int32_t impl; /* 0 = auto, 1 = force SIMT fp32, 2 = force tcgen05 split-fp16 */
+  /* ---- split-fp16 operands (tcgen05 path) -------------------------------------------------
+   * An fp32 value v travels as two fp16 planes hi = fp16(v), lo = fp16(v - hi); the tensor cores
+   * compute hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM (~2^-22 relative, fp32 class).
+   * in_hi/in_lo: [B][T_in][Cin] halves (row stride Cin, batch stride T_in*Cin), replace `in`;
+   * w_hi/w_lo: packed [K][Cout][Cin] halves of w * 2^s (pttspp_pack_conv_weight_split), w_scale_inv = 2^-s.
+   * out_hi/out_lo (optional, any path): planes of (out + out_plane_add[c]) for the next conv;
+   * `out` may be NULL then. */
+  const void* in_hi;
+  const void* in_lo;
+  const void* w_hi;
+  const void* w_lo;
+  float w_scale_inv;
+  void* out_hi;
+  void* out_lo;
+  const float* out_plane_add; /* optional [output columns] */
+  int64_t out_plane_bs;
+  int32_t out_plane_ld;
 } pttspp_conv1d_desc;
 
 int pttspp_conv1d_cl(const pttspp_conv1d_desc* d, pttspp_stream_t stream);
@@ -112,6 +129,13 @@ int pttspp_conv1d_cl(const pttspp_conv1d_desc* d, pttspp_stream_t stream);
  * packs output channel c of the first half to column 2c and of the second half to 2c+1. */
 int pttspp_pack_conv_weight(const float* v, const float* g, int Cout, int Cin, int K, float* packed,
                             int w_ld, int interleave_halves, pttspp_stream_t stream);
+/* Split-fp16 packing for the tcgen05 path: w_hi/w_lo [K][Cout][Cin] halves of w * 2^s with the largest
+ * power of two that keeps max|w| * 2^s <= 16384; returns 2^-s in *scale_inv.  Host pointers. */
+int pttspp_pack_conv_weight_split(const float* v, const float* g, int Cout, int Cin, int K, void* w_hi, void* w_lo,
+                                  int interleave_halves, float* scale_inv);
+/* x[n] (fp32, device) -> hi[n], lo[n] (fp16, device) planes of (x + add[i % C]) (add optional). */
+int pttspp_split_f16(const float* x, const float* add, int64_t n, int C, void* hi, void* lo, pttspp_stream_t stream);
+
 /* Repack a ConvTranspose1d weight [Cin][Cout][Kt] (+ optional weight-norm g[Cin]) into `stride`
  * polyphase 2-D conv weights [stride][Kt/stride][Cin][w_ld] (bigvgan.py:90-102). */
 int pttspp_pack_convtr_weight(const float* v, const float* g, int Cin, int Cout, int Kt, int stride,

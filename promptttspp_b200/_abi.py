@@ -32,6 +32,9 @@ class Conv1dDesc(C.Structure):
         ("res", C.c_void_p), ("res_bs", C.c_int64), ("res_ld", C.c_int32), ("res_scale", C.c_float),
         ("alpha", C.c_float), ("beta", C.c_float), ("out_div", C.c_float),
         ("B", C.c_int32), ("impl", C.c_int32),
+        ("in_hi", C.c_void_p), ("in_lo", C.c_void_p), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p),
+        ("w_scale_inv", C.c_float), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_plane_add", C.c_void_p),
+        ("out_plane_bs", C.c_int64), ("out_plane_ld", C.c_int32),
     ]
 
 
@@ -86,6 +89,9 @@ SIGNATURES = {
     "pttspp_conv1d_cl": (C.c_int, [C.POINTER(Conv1dDesc), C.c_void_p]),
     "pttspp_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                           C.c_int, C.c_void_p]),
+    "pttspp_pack_conv_weight_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                C.c_void_p, C.c_int, C.c_void_p]),
+    "pttspp_split_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pttspp_pack_convtr_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                             C.c_int, C.c_void_p]),
     "pttspp_layernorm_cl": (C.c_int, [C.POINTER(LayerNormDesc), C.c_void_p]),

@@ -75,6 +75,7 @@ struct pttspp_acoustic {
   pttspp::PackedConv in_proj, cond_all, skip_proj, out_proj;
   std::vector<pttspp::DiffLayerW> diff;
   float* step_table = nullptr;  // [K_step][layers][C]
+  bool use_umma = true;         // tcgen05 split-fp16 path for the DiffNet contractions (PTTSPP_DISABLE_UMMA=1: off)
   std::vector<float> c_recip, c_recipm1, coef1, coef2, logvar;
 };
 
@@ -207,6 +208,7 @@ EncodeWs carve_encode(const pttspp_acoustic_config& c, int B, int Tx, int Tp, Ca
 
 struct DecodeWs {
   float *xa, *xb, *tmp, *lcf0, *vuv, *condp, *xt, *h, *z, *skip, *s, *eps;
+  uint16_t *yh, *yl, *zh, *zl, *sh, *sl, *ph, *pl;  // split-fp16 operand planes [B][Ty][DC]
 };
 
 DecodeWs carve_decode(const pttspp_acoustic_config& c, int B, int Ty, Carver& cv) {
@@ -225,6 +227,10 @@ DecodeWs carve_decode(const pttspp_acoustic_config& c, int B, int Ty, Carver& cv
   w.skip = cv.take<float>(n * DC);
   w.s = cv.take<float>(n * DC);
   w.eps = cv.take<float>(n * c.mel_dim);
+  w.yh = cv.take<uint16_t>(n * DC); w.yl = cv.take<uint16_t>(n * DC);
+  w.zh = cv.take<uint16_t>(n * DC); w.zl = cv.take<uint16_t>(n * DC);
+  w.sh = cv.take<uint16_t>(n * DC); w.sl = cv.take<uint16_t>(n * DC);
+  w.ph = cv.take<uint16_t>(n * DC); w.pl = cv.take<uint16_t>(n * DC);
   return w;
 }
 
@@ -375,12 +381,20 @@ extern "C" int pttspp_acoustic_finalize(pttspp_acoustic_t* h, pttspp_stream_t) {
     w.dilated = load_conv1d(st, dev, p + "dilated_conv", 2 * DC, DC, c.diff_kernel, dl,
                             (c.diff_kernel * dl - dl) / 2, /*interleave=*/true);
     w.outp = load_conv1d(st, dev, p + "output_projection", 2 * DC, DC, 1, 1, 0);
+    attach_split_weights(st, dev, p + "dilated_conv", w.dilated, /*interleave=*/true);
+    attach_split_weights(st, dev, p + "output_projection", w.outp, false);
     h->diff.push_back(w);
     cond_names.push_back(p + "conditioner_projection");
   }
   h->cond_all = load_concat(st, dev, cond_names, 2 * DC, C, 1, /*interleave_each=*/true, true);
   h->skip_proj = load_conv1d(st, dev, dn + "skip_projection", DC, DC, 1, 1, 0);
   h->out_proj = load_conv1d(st, dev, dn + "output_projection", c.mel_dim, DC, 1, 1, 0);
+  attach_split_weights(st, dev, dn + "skip_projection", h->skip_proj, false);
+  attach_split_weights(st, dev, dn + "output_projection", h->out_proj, false);
+  {
+    const char* e = getenv("PTTSPP_DISABLE_UMMA");
+    h->use_umma = !(e && e[0] == '1') && DC % 64 == 0;
+  }
   h->step_table = dev.upload(build_step_table(st, c));
   h->c_recip = st.get("decoder.sqrt_recip_alphas_cumprod", c.K_step).data;
   h->c_recipm1 = st.get("decoder.sqrt_recipm1_alphas_cumprod", c.K_step).data;
@@ -595,37 +609,71 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
   const float sqrt2 = sqrtf(2.f);
   const float inv_sqrt_layers = 1.f / sqrtf((float)c.diff_layers);
   const int64_t bsD = (int64_t)Ty * DC;
+  const bool um = h->use_umma;
+  auto planes_in = [&](pttspp_conv1d_desc& q, const uint16_t* hi, const uint16_t* lo, const PackedConv& pc, int row_off) {
+    q.in_hi = hi; q.in_lo = lo; q.in_bs = bsD; q.in_ld = DC;
+    q.w_hi = (const uint16_t*)pc.w_hi + (size_t)row_off * pc.Cin;
+    q.w_lo = (const uint16_t*)pc.w_lo + (size_t)row_off * pc.Cin;
+    q.w_scale_inv = pc.w_scale_inv;
+    q.impl = 2;
+  };
+  auto planes_out = [&](pttspp_conv1d_desc& q, uint16_t* hi, uint16_t* lo, const float* add) {
+    q.out_hi = hi; q.out_lo = lo; q.out_plane_bs = bsD; q.out_plane_ld = DC; q.out_plane_add = add;
+  };
   for (int step = c.K_step - 1; step >= 0; --step) {
+    const float* step_emb = h->step_table + (size_t)step * c.diff_layers * DC;
     {
       auto d = conv_desc(h->in_proj, w.xt, B, Ty, w.h);
       d.act = PTTSPP_ACT_RELU;
+      if (um) planes_out(d, w.yh, w.yl, step_emb);  // y_0 = h + step_emb[0] as operand planes
       conv1d_cl(d, s);
     }
     for (int l = 0; l < c.diff_layers; ++l) {
       const DiffLayerW& lw = h->diff[l];
+      const bool last = (l + 1 == c.diff_layers);
       // z = sigmoid(gate) * tanh(filter) of dilated_conv(h + step_emb) + cond_proj  (denoiser.py:69-77)
       auto d = conv_desc(lw.dilated, w.h, B, Ty, w.z);
       d.out_bs = bsD; d.out_ld = DC;
-      d.in_add = h->step_table + ((size_t)step * c.diff_layers + l) * DC;
       d.addend = w.condp + (size_t)l * 2 * DC; d.addend_bs = (int64_t)Ty * CP; d.addend_ld = CP;
       d.act = PTTSPP_ACT_GATE;
+      if (um) {
+        planes_in(d, w.yh, w.yl, lw.dilated, 0);
+        d.out = nullptr;
+        planes_out(d, w.zh, w.zl, nullptr);
+      } else {
+        d.in_add = step_emb + (size_t)l * DC;
+      }
       conv1d_cl(d, s);
       // residual half: h = (h + W_r z + b_r) / sqrt(2)   (denoiser.py:79-83)
       auto r = conv_desc(lw.outp, w.z, B, Ty, w.h);
       r.Cout = DC; r.out_bs = bsD; r.out_ld = DC;
       r.res = w.h; r.res_bs = bsD; r.res_ld = DC; r.out_div = sqrt2;
+      if (um) {
+        planes_in(r, w.zh, w.zl, lw.outp, 0);
+        if (!last) planes_out(r, w.yh, w.yl, step_emb + (size_t)(l + 1) * DC);  // next layer's conv input
+      }
       conv1d_cl(r, s);
       // skip half: skip (+)= W_s z + b_s
       auto k = conv_desc(lw.outp, w.z, B, Ty, w.skip);
       k.w = lw.outp.w + DC; k.bias = lw.outp.bias + DC; k.Cout = DC; k.out_bs = bsD; k.out_ld = DC;
       k.beta = (l == 0) ? 0.f : 1.f;
+      if (um) {
+        planes_in(k, w.zh, w.zl, lw.outp, DC);
+        if (last) planes_out(k, w.sh, w.sl, nullptr);  // operand planes of the skip sum
+      }
       conv1d_cl(k, s);
     }
     {
       auto d = conv_desc(h->skip_proj, w.skip, B, Ty, w.s);
       d.acc_scale = inv_sqrt_layers; d.act = PTTSPP_ACT_RELU;
+      if (um) {
+        planes_in(d, w.sh, w.sl, h->skip_proj, 0);
+        d.out = nullptr;
+        planes_out(d, w.ph, w.pl, nullptr);
+      }
       conv1d_cl(d, s);
       auto e = conv_desc(h->out_proj, w.s, B, Ty, w.eps);
+      if (um) planes_in(e, w.ph, w.pl, h->out_proj, 0);
       conv1d_cl(e, s);
     }
     const float sigma = (step > 0) ? expf(0.5f * h->logvar[step]) : 0.f;

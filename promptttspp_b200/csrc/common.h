@@ -84,6 +84,9 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 void conv1d_cl(const pttspp_conv1d_desc& d, cudaStream_t s);
 void pack_conv_weight(const float* v, const float* g, int Cout, int Cin, int K, float* packed, int w_ld,
                       int interleave_halves, cudaStream_t s);
+void pack_conv_weight_split(const float* v, const float* g, int Cout, int Cin, int K, void* w_hi, void* w_lo,
+                            int interleave_halves, float* scale_inv);
+void split_f16_planes(const float* x, const float* add, int64_t n, int C, void* hi, void* lo, cudaStream_t s);
 void pack_convtr_weight(const float* v, const float* g, int Cin, int Cout, int Kt, int stride, float* packed,
                         int w_ld, cudaStream_t s);
 void layernorm_cl(const pttspp_layernorm_desc& d, cudaStream_t s);
@@ -146,13 +149,22 @@ struct DeviceBuffers {
   void release();
   float* upload(const std::vector<float>& host);
   float* upload(const float* host, size_t n);
+  void* upload_bytes(const void* host, size_t bytes);
 };
 
 struct PackedConv {
   float* w = nullptr;
   float* bias = nullptr;
   int Cin = 0, Cout = 0, K = 1, dil = 1, pad = 0, w_ld = 0;
+  // optional split-fp16 copy for the tcgen05 path: [K][Cout][Cin] halves of w * 2^s, w_scale_inv = 2^-s
+  void* w_hi = nullptr;
+  void* w_lo = nullptr;
+  float w_scale_inv = 0.f;
+  float* bias_cols = nullptr;  // bias in packed column order (== bias)
 };
+// adds the split-fp16 planes of the same torch weight to an already loaded PackedConv
+void attach_split_weights(const TensorStore& st, DeviceBuffers& dev, const std::string& prefix, PackedConv& c,
+                          bool interleave_halves);
 
 // Conv1d weights `prefix.weight` or weight-norm pair `prefix.weight_g/_v`, plus `prefix.bias`.
 PackedConv load_conv1d(const TensorStore& st, DeviceBuffers& dev, const std::string& prefix, int Cout, int Cin, int K,

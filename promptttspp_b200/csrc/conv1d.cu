@@ -10,6 +10,7 @@
 // thread owns a TM x TN register tile (rows strided by BM/TM so that the two/four row groups of
 // a warp hit different banks).  Full fp32 accumulation: this path is the numerical anchor.
 #include "common.h"
+#include "conv_epilogue.cuh"
 
 namespace pttspp {
 
@@ -17,16 +18,6 @@ namespace {
 
 constexpr int BK = 16;
 constexpr int LDA = BK + 4;
-
-__device__ __forceinline__ float act_apply(float v, int act) {
-  switch (act) {
-    case PTTSPP_ACT_RELU: return fmaxf(v, 0.f);
-    case PTTSPP_ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
-    case PTTSPP_ACT_SWISH: return v / (1.f + expf(-v));
-    case PTTSPP_ACT_TANH: return tanhf(v);
-    default: return v;
-  }
-}
 
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN), (BM * BN >= 128 * 128) ? 2 : 2)
@@ -118,9 +109,7 @@ conv1d_simt_kernel(const pttspp_conv1d_desc d) {
     }
   }
 
-  // ---- epilogue ----
-  const bool gate = (d.act == PTTSPP_ACT_GATE);
-  const int out_cols = gate ? d.Cout / 2 : d.Cout;
+  // ---- epilogue (conv_epilogue.cuh) ----
   long long olen = 0x7fffffffffffffffLL;
   if (d.out_len) olen = d.out_len[b];
 #pragma unroll
@@ -132,43 +121,8 @@ conv1d_simt_kernel(const pttspp_conv1d_desc d) {
     const float mask = ((long long)row < olen) ? 1.f : 0.f;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-      const int col = n0 + g * GS + tx * 4;
-      if (col >= d.Cout) continue;
-      float v[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c = col + e;
-        float t = acc[i][g * 4 + e] * d.acc_scale;
-        if (c < d.Cout) {
-          if (d.bias) t += d.bias[c];
-          if (d.addend) t += d.addend[(int64_t)b * d.addend_bs + (int64_t)row * d.addend_ld + c];
-        }
-        v[e] = t;
-      }
-      float o[4];
-      int nout, ocol;
-      if (gate) {
-        o[0] = (1.f / (1.f + expf(-v[0]))) * tanhf(v[1]);
-        o[1] = (1.f / (1.f + expf(-v[2]))) * tanhf(v[3]);
-        o[2] = o[3] = 0.f;
-        nout = 2;
-        ocol = col >> 1;
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = act_apply(v[e], d.act);
-        nout = 4;
-        ocol = col;
-      }
-      for (int e = 0; e < nout; ++e) {
-        const int oc = ocol + e;
-        if (oc >= out_cols) break;
-        const int64_t oidx = (int64_t)b * d.out_bs + (int64_t)row * d.out_ld + oc;
-        float y = d.alpha * mask * o[e];
-        if (d.res) y += d.res_scale * d.res[(int64_t)b * d.res_bs + (int64_t)row * d.res_ld + oc];
-        if (d.beta != 0.f) y += d.beta * d.out[oidx];
-        if (d.out_div != 0.f) y = y / d.out_div;
-        d.out[oidx] = y;
-      }
+      const float a4[4] = {acc[i][g * 4 + 0], acc[i][g * 4 + 1], acc[i][g * 4 + 2], acc[i][g * 4 + 3]};
+      conv_epilogue4(d, b, row, mask, n0 + g * GS + tx * 4, a4);
     }
   }
 }
@@ -192,10 +146,9 @@ void conv1d_umma_cl(const pttspp_conv1d_desc& d, cudaStream_t s);  // conv1d_umm
 bool conv1d_umma_supported(const pttspp_conv1d_desc& d);
 
 void conv1d_cl(const pttspp_conv1d_desc& d, cudaStream_t s) {
-  PT_CHECK(d.in && d.w && d.out, "conv1d: null pointer");
+  PT_CHECK(d.out || d.out_hi, "conv1d: no output (out and out_hi are NULL)");
+  PT_CHECK(!d.out_hi || d.out_lo, "conv1d: out_hi without out_lo");
   PT_CHECK(d.Cin > 0 && d.Cin % BK == 0, "conv1d: Cin=%d must be a positive multiple of %d", d.Cin, BK);
-  PT_CHECK(d.in_ld % 4 == 0 && aligned16(d.in), "conv1d: input must be 16-byte aligned, ld %% 4 == 0");
-  PT_CHECK(d.w_ld % 4 == 0 && d.w_ld >= d.Cout && aligned16(d.w), "conv1d: packed weight ld=%d invalid", d.w_ld);
   PT_CHECK(!d.in_add || aligned16(d.in_add), "conv1d: in_add must be 16-byte aligned");
   PT_CHECK(d.K >= 1 && d.dil >= 1 && d.in_stride >= 1 && d.out_mul >= 1, "conv1d: bad geometry");
   PT_CHECK(d.act != PTTSPP_ACT_GATE || d.Cout % 2 == 0, "conv1d: gate activation needs even Cout");
@@ -213,6 +166,9 @@ void conv1d_cl(const pttspp_conv1d_desc& d, cudaStream_t s) {
     conv1d_umma_cl(d, s);
     return;
   }
+  PT_CHECK(d.in && d.w, "conv1d: the CUDA-core path needs fp32 `in` and packed fp32 weights `w`");
+  PT_CHECK(d.in_ld % 4 == 0 && aligned16(d.in), "conv1d: input must be 16-byte aligned, ld %% 4 == 0");
+  PT_CHECK(d.w_ld % 4 == 0 && d.w_ld >= d.Cout && aligned16(d.w), "conv1d: packed weight ld=%d invalid", d.w_ld);
   if (d.Cout > 64)
     launch_simt<128, 128, 8, 8>(d, s);
   else if (d.Cout > 32)
@@ -272,7 +228,87 @@ void pack_convtr_weight(const float* v, const float* g, int Cin, int Cout, int K
   }
 }
 
+void pack_conv_weight_split(const float* v, const float* g, int Cout, int Cin, int K, void* w_hi, void* w_lo,
+                            int interleave_halves, float* scale_inv) {
+  PT_CHECK(!interleave_halves || Cout % 2 == 0, "pack_conv_weight_split: interleave needs even Cout");
+  std::vector<float> w((size_t)Cout * Cin * K);
+  float mx = 0.f;
+  for (int co = 0; co < Cout; ++co) {
+    const float* vr = v + (size_t)co * Cin * K;
+    float scale = 1.f;
+    if (g) {
+      double ss = 0.0;
+      for (int i = 0; i < Cin * K; ++i) ss += (double)vr[i] * vr[i];
+      scale = (float)((double)g[co] / std::sqrt(ss));
+    }
+    for (int i = 0; i < Cin * K; ++i) {
+      const float x = g ? vr[i] * scale : vr[i];
+      w[(size_t)co * Cin * K + i] = x;
+      mx = std::max(mx, std::fabs(x));
+    }
+  }
+  int e = 0;  // largest power of two with mx * 2^e <= 16384 (keeps hi and lo in fp16's normal range)
+  if (mx > 0.f) {
+    e = (int)std::floor(std::log2(16384.0 / (double)mx));
+    e = std::max(-14, std::min(e, 24));
+  }
+  const float sc = std::ldexp(1.f, e);
+  *scale_inv = std::ldexp(1.f, -e);
+  __half* hi = reinterpret_cast<__half*>(w_hi);
+  __half* lo = reinterpret_cast<__half*>(w_lo);
+  const int half = Cout / 2;
+  for (int co = 0; co < Cout; ++co) {
+    const int col = interleave_halves ? (co < half ? 2 * co : 2 * (co - half) + 1) : co;
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int k = 0; k < K; ++k) {
+        const float x = w[((size_t)co * Cin + ci) * K + k] * sc;
+        const __half h = __float2half_rn(x);
+        const size_t idx = ((size_t)k * Cout + col) * Cin + ci;
+        hi[idx] = h;
+        lo[idx] = __float2half_rn(x - __half2float(h));
+      }
+  }
+}
+
+namespace {
+__global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ x, const float* __restrict__ add,
+                                                        int64_t n, int C, __half* __restrict__ hi,
+                                                        __half* __restrict__ lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = x[i];
+  if (add) v += add[i % C];
+  __half h, l;
+  split_f16(v, h, l);
+  hi[i] = h;
+  lo[i] = l;
+}
+}  // namespace
+
+void split_f16_planes(const float* x, const float* add, int64_t n, int C, void* hi, void* lo, cudaStream_t s) {
+  PT_CHECK(x && hi && lo && C >= 1, "split_f16: bad argument");
+  if (n == 0) return;
+  ProfScope prof(PROF_OTHER, s, 0.0, 8.0 * (double)n);
+  split_f16_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(x, add, n, C, (__half*)hi, (__half*)lo);
+  PT_LAUNCHED();
+}
+
 }  // namespace pttspp
+
+extern "C" int pttspp_pack_conv_weight_split(const float* v, const float* g, int Cout, int Cin, int K, void* w_hi,
+                                             void* w_lo, int interleave_halves, float* scale_inv) {
+  PT_API_BEGIN
+  PT_CHECK(v && w_hi && w_lo && scale_inv, "null argument");
+  pttspp::pack_conv_weight_split(v, g, Cout, Cin, K, w_hi, w_lo, interleave_halves, scale_inv);
+  PT_API_END
+}
+
+extern "C" int pttspp_split_f16(const float* x, const float* add, int64_t n, int C, void* hi, void* lo,
+                                pttspp_stream_t stream) {
+  PT_API_BEGIN
+  pttspp::split_f16_planes(x, add, n, C, hi, lo, (cudaStream_t)stream);
+  PT_API_END
+}
 
 extern "C" int pttspp_conv1d_cl(const pttspp_conv1d_desc* d, pttspp_stream_t stream) {
   PT_API_BEGIN

@@ -79,6 +79,13 @@ float* DeviceBuffers::upload(const float* host, size_t n) {
   if (n) PT_CUDA(cudaMemcpy(p, host, n * sizeof(float), cudaMemcpyHostToDevice));
   return (float*)p;
 }
+void* DeviceBuffers::upload_bytes(const void* host, size_t bytes) {
+  void* p = nullptr;
+  PT_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+  ptrs.push_back(p);
+  if (bytes) PT_CUDA(cudaMemcpy(p, host, bytes, cudaMemcpyHostToDevice));
+  return p;
+}
 float* DeviceBuffers::upload(const std::vector<float>& host) { return upload(host.data(), host.size()); }
 
 PackedConv load_conv1d(const TensorStore& st, DeviceBuffers& dev, const std::string& prefix, int Cout, int Cin, int K,
@@ -107,6 +114,21 @@ PackedConv load_conv1d(const TensorStore& st, DeviceBuffers& dev, const std::str
     c.bias = dev.upload(bb);
   }
   return c;
+}
+
+void attach_split_weights(const TensorStore& st, DeviceBuffers& dev, const std::string& prefix, PackedConv& c,
+                          bool interleave_halves) {
+  const int64_t n = (int64_t)c.Cout * c.Cin * c.K;
+  std::vector<uint16_t> hi((size_t)n), lo((size_t)n);
+  if (st.has(prefix + ".weight")) {
+    pack_conv_weight_split(st.get(prefix + ".weight", n).data.data(), nullptr, c.Cout, c.Cin, c.K, hi.data(), lo.data(),
+                           interleave_halves, &c.w_scale_inv);
+  } else {
+    pack_conv_weight_split(st.get(prefix + ".weight_v", n).data.data(), st.get(prefix + ".weight_g", c.Cout).data.data(),
+                           c.Cout, c.Cin, c.K, hi.data(), lo.data(), interleave_halves, &c.w_scale_inv);
+  }
+  c.w_hi = dev.upload_bytes(hi.data(), hi.size() * 2);
+  c.w_lo = dev.upload_bytes(lo.data(), lo.size() * 2);
 }
 
 PackedConv load_linear(const TensorStore& st, DeviceBuffers& dev, const std::string& prefix, int Cout, int Cin,

@@ -126,3 +126,73 @@ def relpos_attention(q, k, v, p, bias_u, bias_v, lens, heads, legacy):
         _abi.ptr(q), _abi.ptr(k), _abi.ptr(v), _abi.ptr(p), _abi.ptr(bias_u), _abi.ptr(bias_v), _abi.ptr(lens), B, T,
         heads, dk, int(legacy), _abi.ptr(scratch), _abi.ptr(out), _abi.stream_ptr(q.device)))
     return out
+
+
+# ---- split-fp16 operand planes (tcgen05 path) --------------------------------------------------
+
+def split_f16(x, add=None):
+    """fp32 CUDA tensor [..., C] -> (hi, lo) fp16 planes of (x + add[c])."""
+    _abi.require_cuda(x, "split_f16")
+    x = x.contiguous()
+    hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    _abi.check(_abi.lib().pttspp_split_f16(_abi.ptr(x), _abi.ptr(add), x.numel(), x.shape[-1], _abi.ptr(hi),
+                                           _abi.ptr(lo), _abi.stream_ptr(x.device)))
+    return hi, lo
+
+
+def pack_conv_weight_split(weight, g=None, interleave_halves=False, device=None):
+    """torch Conv1d weight [Cout, Cin, K] -> (w_hi, w_lo [K, Cout, Cin] fp16, scale_inv)."""
+    w = weight.detach().float().cpu().contiguous()
+    if w.dim() == 2:
+        w = w.unsqueeze(-1)
+    Cout, Cin, K = w.shape
+    hi = torch.empty(K, Cout, Cin, dtype=torch.float16)
+    lo = torch.empty(K, Cout, Cin, dtype=torch.float16)
+    gp = None if g is None else g.detach().float().cpu().contiguous().view(-1)
+    sc = C.c_float(0.0)
+    _abi.check(_abi.lib().pttspp_pack_conv_weight_split(_abi.ptr(w), _abi.ptr(gp), Cout, Cin, K, _abi.ptr(hi),
+                                                        _abi.ptr(lo), int(interleave_halves), C.byref(sc)))
+    if device is not None:
+        hi, lo = hi.to(device), lo.to(device)
+    return hi, lo, sc.value
+
+
+def conv1d_umma_cl(x_planes, w_split, Cout, bias=None, K=1, dil=1, pad=0, act=ACT_NONE, out_len=None, addend=None,
+                   res=None, res_scale=1.0, alpha=1.0, beta=0.0, out=None, acc_scale=1.0, out_div=0.0,
+                   emit_planes=False, plane_add=None, write_f32=True):
+    """tcgen05 path on pre-split operands.  x_planes = (hi, lo) [B, T, Cin] fp16; w_split from
+    pack_conv_weight_split.  Returns out (fp32) and/or (out_hi, out_lo)."""
+    xh, xl = x_planes
+    wh, wl, scale_inv = w_split
+    _abi.require_cuda(xh, "conv1d_umma_cl")
+    B, T, Cin = xh.shape
+    out_cols = Cout // 2 if act == ACT_GATE else Cout
+    if out is None and write_f32:
+        out = torch.zeros(B, T, out_cols, device=xh.device, dtype=torch.float32)
+    d = _abi.Conv1dDesc()
+    d.in_bs = xh.stride(0); d.in_ld = xh.stride(1); d.T_in = T; d.Cin = Cin
+    d.in_hi = xh.data_ptr(); d.in_lo = xl.data_ptr(); d.w_hi = wh.data_ptr(); d.w_lo = wl.data_ptr()
+    d.w_scale_inv = scale_inv
+    d.bias = None if bias is None else bias.data_ptr()
+    d.K = K; d.dil = dil; d.pad = pad; d.in_stride = 1
+    if out is not None:
+        d.out = out.data_ptr(); d.out_bs = out.stride(0); d.out_ld = out.stride(1)
+    d.T_out = T; d.Cout = Cout; d.m_begin = 0; d.M = T; d.out_mul = 1; d.out_off = 0
+    d.out_len = None if out_len is None else out_len.data_ptr()
+    if addend is not None:
+        d.addend = addend.data_ptr(); d.addend_bs = addend.stride(0); d.addend_ld = addend.stride(1)
+    d.act = act; d.acc_scale = acc_scale
+    if res is not None:
+        d.res = res.data_ptr(); d.res_bs = res.stride(0); d.res_ld = res.stride(1)
+    d.res_scale = res_scale; d.alpha = alpha; d.beta = beta; d.out_div = out_div
+    d.B = B; d.impl = 2
+    planes = None
+    if emit_planes:
+        oh = torch.empty(B, T, out_cols, dtype=torch.float16, device=xh.device)
+        ol = torch.empty(B, T, out_cols, dtype=torch.float16, device=xh.device)
+        d.out_hi = oh.data_ptr(); d.out_lo = ol.data_ptr(); d.out_plane_bs = oh.stride(0); d.out_plane_ld = oh.stride(1)
+        d.out_plane_add = None if plane_add is None else plane_add.data_ptr()
+        planes = (oh, ol)
+    _abi.check(_abi.lib().pttspp_conv1d_cl(C.byref(d), _abi.stream_ptr(xh.device)))
+    return out, planes

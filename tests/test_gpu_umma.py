@@ -1,0 +1,107 @@
+"""GPU: the tcgen05/TMA split-fp16 conv path against torch fp32 conv1d on the CPU."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from promptttspp_b200 import _abi, ops
+
+    _abi.check(_abi.lib().pttspp_device_check())
+    return ops
+
+
+def _cl(x):
+    return x.transpose(1, 2).contiguous().cuda()
+
+
+def _bct(x):
+    return x.float().cpu().transpose(1, 2)
+
+
+def test_split_planes_reconstruct(ops):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 50, 64, generator=g) * 3
+    add = torch.randn(64, generator=g)
+    hi, lo = ops.split_f16(x.cuda(), add.cuda())
+    rec = hi.float().cpu() + lo.float().cpu()
+    ref = x + add
+    # 2^-22 relative while lo is a normal fp16; 2^-25 absolute floor where lo goes subnormal
+    assert float(((rec - ref).abs() - 4e-7 * ref.abs()).max()) < 4e-8
+
+
+UMMA_CASES = [
+    # Cin, Cout, K, dil, B, T
+    (64, 128, 1, 1, 1, 128),      # single stage, single tile
+    (256, 512, 3, 1, 2, 300),     # DiffNet dilated conv shapes
+    (256, 512, 3, 8, 2, 259),
+    (256, 256, 1, 1, 3, 77),
+    (256, 80, 1, 1, 2, 130),      # Cout < BN (TMA zero-fills the missing weight rows)
+    (128, 128, 7, 1, 1, 129),
+    (1024, 256, 9, 1, 1, 200),    # many K iterations through the 3-stage ring
+    (64, 64, 11, 5, 1, 515),
+]
+
+
+@pytest.mark.parametrize("Cin,Cout,K,dil,B,T", UMMA_CASES)
+def test_conv1d_umma_plain(ops, Cin, Cout, K, dil, B, T):
+    g = torch.Generator().manual_seed(Cin + Cout * 3 + K)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cout, Cin, K, generator=g) / math.sqrt(Cin * K)
+    b = torch.randn(Cout, generator=g)
+    pad = (K * dil - dil) // 2
+    ref = F.conv1d(x, w, b, padding=pad, dilation=dil)
+    planes = ops.split_f16(_cl(x))
+    out, _ = ops.conv1d_umma_cl(planes, ops.pack_conv_weight_split(w, device="cuda"), Cout, bias=b.cuda(), K=K, dil=dil,
+                                pad=pad)
+    err = float((_bct(out) - ref).abs().max())
+    print(f"umma {Cin}->{Cout} k{K} d{dil}: max-abs err {err:.3e}")
+    # the tensor core truncates on accumulate: the bias grows linearly with the K*Cin/16 accumulations
+    assert err < 1e-5 + 6e-9 * K * Cin, err
+
+
+def test_conv1d_umma_diffnet_chain(ops):
+    """gate conv -> planes -> 1x1 residual/skip convs, the two tcgen05 launches of a DiffNet layer."""
+    g = torch.Generator().manual_seed(6)
+    B, C, T, dil = 2, 256, 333, 4
+    x = torch.randn(B, C, T, generator=g)
+    step = torch.randn(C, generator=g)
+    cond = torch.randn(B, 2 * C, T, generator=g)
+    w1 = torch.randn(2 * C, C, 3, generator=g) / math.sqrt(C * 3)
+    b1 = torch.randn(2 * C, generator=g)
+    w2 = torch.randn(2 * C, C, 1, generator=g) / math.sqrt(C)
+    b2 = torch.randn(2 * C, generator=g)
+    skip_old = torch.randn(B, C, T, generator=g)
+    next_step = torch.randn(C, generator=g)
+    y = F.conv1d(x + step[None, :, None], w1, b1, padding=dil, dilation=dil) + cond
+    gate, filt = torch.chunk(y, 2, dim=1)
+    z_ref = torch.sigmoid(gate) * torch.tanh(filt)
+    o = F.conv1d(z_ref, w2, b2)
+    x_ref = (x + o[:, :C]) / math.sqrt(2.0)
+    skip_ref = skip_old + o[:, C:]
+    perm = torch.empty(2 * C, dtype=torch.long)
+    perm[0::2] = torch.arange(C)
+    perm[1::2] = torch.arange(C) + C
+    planes = ops.split_f16(_cl(x), step.cuda())
+    _, zp = ops.conv1d_umma_cl(planes, ops.pack_conv_weight_split(w1, interleave_halves=True, device="cuda"), 2 * C,
+                               bias=b1[perm].cuda(), K=3, dil=dil, pad=dil, act=ops.ACT_GATE,
+                               addend=_cl(cond[:, perm]), emit_planes=True, write_f32=False)
+    z = zp[0].float() + zp[1].float()
+    assert float((_bct(z) - z_ref).abs().max()) < 2e-5
+    xbuf = _cl(x)
+    w2s_res = ops.pack_conv_weight_split(w2[:C], device="cuda")
+    w2s_skip = ops.pack_conv_weight_split(w2[C:], device="cuda")
+    _, yp = ops.conv1d_umma_cl(zp, w2s_res, C, bias=b2[:C].cuda(), res=xbuf, out=xbuf, out_div=math.sqrt(2.0),
+                               emit_planes=True, plane_add=next_step.cuda())
+    assert float((_bct(xbuf) - x_ref).abs().max()) < 2e-5
+    ynext = yp[0].float() + yp[1].float()
+    assert float((_bct(ynext) - (x_ref + next_step[None, :, None])).abs().max()) < 2e-5
+    sbuf = _cl(skip_old)
+    ops.conv1d_umma_cl(zp, w2s_skip, C, bias=b2[C:].cuda(), out=sbuf, beta=1.0)
+    assert float((_bct(sbuf) - skip_ref).abs().max()) < 2e-5
