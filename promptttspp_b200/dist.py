@@ -1,0 +1,75 @@
+"""Utterance-batch sharding for multi-GPU batched synthesis.
+
+Utterances are independent in inference (eval-mode BatchNorm, per-utterance attention and masks), so the
+path shards with no data-path collective: one process per GPU (torchrun), every rank synthesises its own
+utterances; torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests) is used only to exchange
+lengths / results.  The sharding rule is deterministic so 1/2/4/8-GPU runs are reproducible: sort by
+phoneme count (cost is ~ linear in padded frames ~ 8 x phonemes), deal round-robin, then cut each rank's
+list into batches of neighbouring lengths to minimise padding.
+
+The reference has no batched-inference caller at all (egs/proposed/bin/synthesize.py:132 loops one
+utterance at a time); its trainer shards token-bucketed batches with x[rank::num_replicas]
+(promptttspp/trainers/tts.py:138-142), which is the precedent for the round-robin deal.
+"""
+from typing import Callable, Dict, List, Sequence
+
+import torch
+
+
+def shard_indices(lengths: Sequence[int], world_size: int, rank: int) -> List[int]:
+    """Indices of the utterances rank `rank` owns: sort by length (desc, stable), deal round-robin."""
+    if not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    return order[rank::world_size]
+
+
+def make_batches(indices: Sequence[int], lengths: Sequence[int], batch_size: int) -> List[List[int]]:
+    """Cut a rank's (length-sorted) utterance list into batches of neighbouring lengths."""
+    if batch_size < 1:
+        raise ValueError("batch_size must be >= 1")
+    idx = sorted(indices, key=lambda i: (-int(lengths[i]), i))
+    return [idx[k:k + batch_size] for k in range(0, len(idx), batch_size)]
+
+
+def pad_batch(seqs: Sequence[torch.Tensor], device=None):
+    """List of 1-D LongTensors -> (padded [B, Tmax] with 0, lengths [B])."""
+    lens = torch.tensor([int(s.numel()) for s in seqs], dtype=torch.int64)
+    out = torch.zeros(len(seqs), int(lens.max()) if len(seqs) else 0, dtype=torch.int64)
+    for b, s in enumerate(seqs):
+        out[b, : s.numel()] = s
+    if device is not None:
+        out, lens = out.to(device), lens.to(device)
+    return out, lens
+
+
+def synthesize_sharded(phonemes: Sequence[torch.Tensor], synth_batch: Callable, batch_size: int, world_size: int = 1,
+                       rank: int = 0) -> Dict[int, object]:
+    """Run `synth_batch(padded, lengths, utterance_indices) -> list of per-utterance results` over this rank's
+    shard.  Returns {utterance index: result} for the utterances this rank owns."""
+    lengths = [int(p.numel()) for p in phonemes]
+    mine = shard_indices(lengths, world_size, rank)
+    results: Dict[int, object] = {}
+    for batch in make_batches(mine, lengths, batch_size):
+        padded, lens = pad_batch([phonemes[i] for i in batch])
+        outs = synth_batch(padded, lens, batch)
+        if len(outs) != len(batch):
+            raise RuntimeError("synth_batch must return one result per utterance")
+        for i, o in zip(batch, outs):
+            results[i] = o
+    return results
+
+
+def gather_frame_counts(local: Dict[int, int], n_utts: int, group=None) -> List[int]:
+    """All ranks learn every utterance's frame count (one small all_reduce; the only collective of the path)."""
+    import torch.distributed as dist
+
+    t = torch.zeros(n_utts, dtype=torch.int64)
+    for i, n in local.items():
+        t[i] = int(n)
+    if dist.is_available() and dist.is_initialized():
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else t.device
+        t = t.to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t = t.cpu()
+    return t.tolist()
