@@ -121,6 +121,11 @@ typedef struct {
 } pttspp_conv1d_desc;
 
 int pttspp_conv1d_cl(const pttspp_conv1d_desc* d, pttspp_stream_t stream);
+/* tcgen05 path only: one contraction, two epilogues.  Output columns [0, d1->Cout) follow d1, the next d2->Cout columns
+ * follow d2 (its bias/res/out pointers are relative to its own first column).  Both must share the input planes and
+ * geometry, K == 1, d1->Cout % 128 == 0 and d2's weight planes must directly follow d1's.  Used for the residual |
+ * skip halves of DiffNet's output projection (denoiser.py:79-83). */
+int pttspp_conv1d_dual_cl(const pttspp_conv1d_desc* d1, const pttspp_conv1d_desc* d2, pttspp_stream_t stream);
 
 /* Weight packing runs once at load time on the HOST (v, g, packed are host pointers).
  * Repack a torch Conv1d weight [Cout][Cin][K] into [K][Cin][w_ld];
@@ -135,6 +140,12 @@ int pttspp_pack_conv_weight_split(const float* v, const float* g, int Cout, int 
                                   int interleave_halves, float* scale_inv);
 /* x[n] (fp32, device) -> hi[n], lo[n] (fp16, device) planes of (x + add[i % C]) (add optional). */
 int pttspp_split_f16(const float* x, const float* add, int64_t n, int C, void* hi, void* lo, pttspp_stream_t stream);
+
+/* Hardware probe (tests only): D[128][128] = A[row_off:row_off+128][0:64] . B[0:128][0:64]^T on tcgen05 with the A tile
+ * loaded once (144 rows, fp16) and the shared-memory descriptor start advanced by row_off rows; mode 1 sets the
+ * descriptor's base_offset field to (start >> 7) & 7. */
+int pttspp_umma_probe(const void* a_half, int rows, const void* b_half, int row_off, int mode, float* out,
+                      pttspp_stream_t stream);
 
 /* Repack a ConvTranspose1d weight [Cin][Cout][Kt] (+ optional weight-norm g[Cin]) into `stride`
  * polyphase 2-D conv weights [stride][Kt/stride][Cin][w_ld] (bigvgan.py:90-102). */

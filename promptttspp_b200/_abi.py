@@ -87,11 +87,13 @@ SIGNATURES = {
     "pttspp_prof_enable": (None, [C.c_int]),
     "pttspp_prof_report": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "pttspp_conv1d_cl": (C.c_int, [C.POINTER(Conv1dDesc), C.c_void_p]),
+    "pttspp_conv1d_dual_cl": (C.c_int, [C.POINTER(Conv1dDesc), C.POINTER(Conv1dDesc), C.c_void_p]),
     "pttspp_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                           C.c_int, C.c_void_p]),
     "pttspp_pack_conv_weight_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                                 C.c_void_p, C.c_int, C.c_void_p]),
     "pttspp_split_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pttspp_umma_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "pttspp_pack_convtr_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                             C.c_int, C.c_void_p]),
     "pttspp_layernorm_cl": (C.c_int, [C.POINTER(LayerNormDesc), C.c_void_p]),

@@ -9,16 +9,20 @@
 // A thread owns one channel and a strip of TT consecutive outputs: 2*TT+10 up-sampled values are
 // produced in registers and never touch memory.  A warp spans 32 consecutive channels, so every
 // row access is one coalesced 128-byte line.  HBM-bound: 2*4 bytes per element.
+#include <cuda_fp16.h>
+
 #include "common.h"
 
 namespace pttspp {
 namespace {
 
-constexpr int TT = 8;           // outputs per thread
+constexpr int TT = 16;          // outputs per thread
 constexpr int NX = TT + 10;     // input samples per strip
 constexpr int NS = 2 * TT + 10; // up-sampled samples per strip
 
-__global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__ x, float* __restrict__ y, int L,
+// y (fp32) and/or split-fp16 planes y_hi/y_lo (operands of the tcgen05 convs that consume the activation)
+__global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                       __half* __restrict__ y_hi, __half* __restrict__ y_lo, int L,
                                                        int C, const float* __restrict__ log_alpha,
                                                        const float* __restrict__ up_f,
                                                        const float* __restrict__ down_f) {
@@ -58,7 +62,13 @@ __global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__
       for (int dd = 0; dd < 6; ++dd) u = fmaf(xs[(i - 1) / 2 + dd], f[11 - 2 * dd], u);
     }
     u *= 2.f;
-    const float sn = sinf(u * alpha);
+    // MUFU sine after an explicit 2*pi range reduction: |error| < 1e-6 over the activations' range, far inside the
+    // 1e-4 RMS waveform bar; the libm sinf slow path made this kernel instruction bound
+    const float arg = u * alpha;
+    const float kq = rintf(arg * 0.15915494309189535f);           // Cody-Waite: 2*pi = hi + lo, two FMAs
+    float red = fmaf(-kq, 6.28318548202514648f, arg);              // fp32(2*pi)
+    red = fmaf(-kq, -1.74845553146951715e-07f, red);               // 2*pi - fp32(2*pi)
+    const float sn = __sinf(red);
     sv[i] = u + inv_alpha * (sn * sn);
   }
   // replicate padding of the up-sampled signal: indices below 0 / above 2L-1 repeat the edge value
@@ -70,14 +80,20 @@ __global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__
   for (int i = 1; i < NS; ++i)
     if (i > imax) sv[i] = sv[i - 1];
 
-  float* yb = y + (int64_t)b * L * C + c;
+  const int64_t ob = (int64_t)b * L * C + c;
 #pragma unroll
   for (int t = 0; t < TT; ++t) {
     if (t0 + t < L) {
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < 12; ++k) acc = fmaf(sv[2 * t + k], g[k], acc);
-      yb[(int64_t)(t0 + t) * C] = acc;
+      const int64_t o = ob + (int64_t)(t0 + t) * C;
+      if (y) y[o] = acc;
+      if (y_hi) {
+        const __half h = __float2half_rn(acc);
+        y_hi[o] = h;
+        y_lo[o] = __float2half_rn(acc - __half2float(h));
+      }
     }
   }
 }
@@ -85,15 +101,16 @@ __global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__
 }  // namespace
 
 void aa_snake_cl(const float* x, float* y, int B, int L, int C, const float* log_alpha, const float* up_f,
-                 const float* down_f, cudaStream_t s) {
-  PT_CHECK(x && y && log_alpha && up_f && down_f, "aa_snake: null pointer");
+                 const float* down_f, cudaStream_t s, void* y_hi, void* y_lo) {
+  PT_CHECK(x && (y || y_hi) && log_alpha && up_f && down_f, "aa_snake: null pointer");
+  PT_CHECK(!y_hi || y_lo, "aa_snake: y_hi without y_lo");
   PT_CHECK(x != y, "aa_snake: in-place operation is not supported");
   PT_CHECK(B >= 1 && B <= 65535 && L >= 1 && C >= 1, "aa_snake: bad shape");
   ProfScope prof(PROF_AA_SNAKE, s, 0.0, 2.0 * 4.0 * B * (double)L * C);
   dim3 block(32, 8);
   dim3 grid(ceil_div(C, 32), ceil_div(L, 8 * TT), B);
   PT_CHECK(grid.y <= 65535, "aa_snake: L=%d too long for one launch", L);
-  aa_snake_kernel<<<grid, block, 0, s>>>(x, y, L, C, log_alpha, up_f, down_f);
+  aa_snake_kernel<<<grid, block, 0, s>>>(x, y, (__half*)y_hi, (__half*)y_lo, L, C, log_alpha, up_f, down_f);
   PT_LAUNCHED();
 }
 

@@ -651,8 +651,9 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
       if (um) {
         planes_in(r, w.zh, w.zl, lw.outp, 0);
         if (!last) planes_out(r, w.yh, w.yl, step_emb + (size_t)(l + 1) * DC);  // next layer's conv input
+      } else {
+        conv1d_cl(r, s);
       }
-      conv1d_cl(r, s);
       // skip half: skip (+)= W_s z + b_s
       auto k = conv_desc(lw.outp, w.z, B, Ty, w.skip);
       k.w = lw.outp.w + DC; k.bias = lw.outp.bias + DC; k.Cout = DC; k.out_bs = bsD; k.out_ld = DC;
@@ -660,8 +661,10 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
       if (um) {
         planes_in(k, w.zh, w.zl, lw.outp, DC);
         if (last) planes_out(k, w.sh, w.sl, nullptr);  // operand planes of the skip sum
+        conv1d_umma_dual_cl(r, k, s);                   // one launch, two epilogues (residual | skip)
+      } else {
+        conv1d_cl(k, s);
       }
-      conv1d_cl(k, s);
     }
     {
       auto d = conv_desc(h->skip_proj, w.skip, B, Ty, w.s);

@@ -34,6 +34,7 @@ struct pttspp_bigvgan {
   pttspp::TensorStore store;
   pttspp::DeviceBuffers dev;
   bool finalized = false;
+  bool use_umma = true;  // PTTSPP_DISABLE_UMMA=1: every conv on the fp32 CUDA-core path
   pttspp::PackedConv conv_pre, conv_post;
   std::vector<pttspp::UpsampleW> ups;
   std::vector<std::vector<std::vector<pttspp::AMPLayerW>>> mrfs;  // [stage][kernel][layer]
@@ -117,6 +118,10 @@ extern "C" int pttspp_bigvgan_finalize(pttspp_bigvgan_t* h, pttspp_stream_t) {
   h->ups.clear();
   h->mrfs.clear();
   const int C0 = c.upsample_initial_channel;
+  {
+    const char* e = getenv("PTTSPP_DISABLE_UMMA");
+    h->use_umma = !(e && e[0] == '1');
+  }
   h->conv_pre = load_conv1d(h->store, h->dev, "conv_pre", C0, c.in_channel, 7, 1, 3);
   for (int i = 0; i < c.num_upsamples; ++i) {
     UpsampleW u;
@@ -151,6 +156,10 @@ extern "C" int pttspp_bigvgan_finalize(pttspp_bigvgan_t* h, pttspp_stream_t) {
         AMPLayerW w;
         w.conv1 = load_conv1d(h->store, h->dev, lp + ".conv1", u.Cout, u.Cout, k, dl, (k * dl - dl) / 2);
         w.conv2 = load_conv1d(h->store, h->dev, lp + ".conv2", u.Cout, u.Cout, k, 1, k / 2);
+        if (h->use_umma && u.Cout % 64 == 0) {  // tensor-core path for the dense C -> C contractions
+          attach_split_weights(h->store, h->dev, lp + ".conv1", w.conv1, false);
+          attach_split_weights(h->store, h->dev, lp + ".conv2", w.conv2, false);
+        }
         w.act1 = load_aa(h->store, h->dev, lp + ".act1", u.Cout);
         w.act2 = load_aa(h->store, h->dev, lp + ".act2", u.Cout);
         block.push_back(w);
@@ -220,15 +229,27 @@ extern "C" int pttspp_bigvgan_forward(pttspp_bigvgan_t* h, const float* mel, int
       const float* cur = bx;
       for (int l = 0; l < c.num_dilations; ++l) {
         const AMPLayerW& w = h->mrfs[i][j][l];
-        aa_snake_cl(cur, t1, B, L, C, w.act1.log_alpha, w.act1.up_f, w.act1.down_f, s);
+        const bool um = w.conv1.w_hi != nullptr;
+        // tcgen05 path: the activation writes its result as split-fp16 operand planes into the t1 region
+        // (hi = first half, lo = second half: 2 x 2 bytes per element, the same footprint as fp32)
+        uint16_t* ph = reinterpret_cast<uint16_t*>(t1);
+        uint16_t* pl = ph + (size_t)B * L * C;
+        auto use_planes = [&](pttspp_conv1d_desc& q, const PackedConv& pc) {
+          q.in_hi = ph; q.in_lo = pl; q.w_hi = pc.w_hi; q.w_lo = pc.w_lo; q.w_scale_inv = pc.w_scale_inv; q.impl = 2;
+        };
+        if (um) aa_snake_cl(cur, nullptr, B, L, C, w.act1.log_alpha, w.act1.up_f, w.act1.down_f, s, ph, pl);
+        else aa_snake_cl(cur, t1, B, L, C, w.act1.log_alpha, w.act1.up_f, w.act1.down_f, s);
         {
           auto d = conv_desc(w.conv1, t1, B, L, t2);
+          if (um) use_planes(d, w.conv1);
           conv1d_cl(d, s);
         }
-        aa_snake_cl(t2, t1, B, L, C, w.act2.log_alpha, w.act2.up_f, w.act2.down_f, s);
+        if (um) aa_snake_cl(t2, nullptr, B, L, C, w.act2.log_alpha, w.act2.up_f, w.act2.down_f, s, ph, pl);
+        else aa_snake_cl(t2, t1, B, L, C, w.act2.log_alpha, w.act2.up_f, w.act2.down_f, s);
         const bool last = (l == c.num_dilations - 1);
         float* dst = last ? bxs : ((cur == bA) ? bB : bA);
         auto d = conv_desc(w.conv2, t1, B, L, dst);
+        if (um) use_planes(d, w.conv2);
         d.res = cur; d.res_bs = (int64_t)L * C; d.res_ld = C;
         if (last) {  // xs = (j ? xs : 0) + (x + y); the last block divides by num_kernels (bigvgan.py:124-127)
           d.beta = (j == 0) ? 0.f : 1.f;

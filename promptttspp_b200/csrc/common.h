@@ -89,9 +89,12 @@ void pack_conv_weight_split(const float* v, const float* g, int Cout, int Cin, i
 void split_f16_planes(const float* x, const float* add, int64_t n, int C, void* hi, void* lo, cudaStream_t s);
 void pack_convtr_weight(const float* v, const float* g, int Cin, int Cout, int Kt, int stride, float* packed,
                         int w_ld, cudaStream_t s);
+// tcgen05 path, one launch with two epilogues: columns [0, Cout(d1)) follow d1, the next Cout(d2) columns follow d2
+void conv1d_umma_dual_cl(const pttspp_conv1d_desc& d1, const pttspp_conv1d_desc& d2, cudaStream_t s);
 void layernorm_cl(const pttspp_layernorm_desc& d, cudaStream_t s);
+// y (fp32) and/or y_hi/y_lo (split-fp16 planes, same indexing) receive the result
 void aa_snake_cl(const float* x, float* y, int B, int L, int C, const float* log_alpha, const float* up_f,
-                 const float* down_f, cudaStream_t s);
+                 const float* down_f, cudaStream_t s, void* y_hi = nullptr, void* y_lo = nullptr);
 void duration_quantize(const float* log_d, const int64_t* phone_len, int B, int Tx, int64_t* dur,
                        int64_t* frame_len, cudaStream_t s);
 void length_regulate(const float* x, const int64_t* dur, int B, int Tx, int C, int Ty, float* out,

@@ -317,6 +317,13 @@ extern "C" int pttspp_conv1d_cl(const pttspp_conv1d_desc* d, pttspp_stream_t str
   PT_API_END
 }
 
+extern "C" int pttspp_conv1d_dual_cl(const pttspp_conv1d_desc* d1, const pttspp_conv1d_desc* d2, pttspp_stream_t stream) {
+  PT_API_BEGIN
+  PT_CHECK(d1 && d2, "null descriptor");
+  pttspp::conv1d_umma_dual_cl(*d1, *d2, (cudaStream_t)stream);
+  PT_API_END
+}
+
 extern "C" int pttspp_pack_conv_weight(const float* v, const float* g, int Cout, int Cin, int K, float* packed,
                                        int w_ld, int interleave_halves, pttspp_stream_t stream) {
   PT_API_BEGIN

@@ -27,7 +27,8 @@ namespace {
 
 constexpr int UM_BM = 128;
 constexpr int UM_BK = 64;  // halves per slab row = 128 bytes = one swizzle span
-constexpr int UM_THREADS = 320;
+constexpr int UM_EPI_WARPS = 16;  // 4 TMEM lane quarters x 4 column groups
+constexpr int UM_THREADS = (UM_EPI_WARPS + 2) * 32;
 constexpr int UM_NACC = 2;  // TMEM accumulators per tile buffer: main (hi*hi) and cross-term (hi*lo + lo*hi)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -71,6 +72,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -112,6 +121,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Output tensor maps of one epilogue descriptor: the accumulator tile leaves through shared memory and TMA bulk
+// stores (whole lines, no LSU involvement) instead of 16-byte-per-row scattered stores.
+struct OutMaps {
+  CUtensorMap f32, hi, lo;
+};
+
 template <int BN>
 struct UmmaSmem {
   static constexpr int A_BYTES = UM_BM * 128;
@@ -123,16 +138,139 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// Epilogue of one accumulator tile by one of the 16 epilogue warps (TMEM -> registers -> fused epilogue -> HBM).
+template <int BN, int NACC>
+__device__ __forceinline__ void umma_tile_epilogue(const pttspp_conv1d_desc& d, const pttspp_conv1d_desc& d2, int cout1,
+                                                   int vec_ok, int mt, int nt, int b, int i, int warp, int lane,
+                                                   uint32_t tmem_base, uint32_t tfull, int n_main, const OutMaps* om,
+                                                   const OutMaps* om2, int tma_out, uint8_t* stage, uint32_t stage_u32) {
+  const int q = warp & 3;      // TMEM lane quarter this warp may access
+  const int cgrp = warp >> 2;  // column group (BN / 4 columns each)
+  const int u = i & 1;
+  const int m0 = d.m_begin + mt * UM_BM, n0g = nt * BN;
+  const bool second = n0g >= cout1;
+  const pttspp_conv1d_desc& de = second ? d2 : d;  // CTA-uniform
+  const int n0 = second ? n0g - cout1 : n0g;
+  const OutMaps* maps = second ? om2 : om;
+  const bool tma_st = ((tma_out >> (second ? 1 : 0)) & 1) != 0;  // CTA-uniform
+  const int m = m0 + q * 32 + lane;
+  const int row = m * de.out_mul + de.out_off;
+  const bool row_ok = (m < de.m_begin + de.M) && row >= 0 && row < de.T_out;
+  float mask = 1.f;
+  if (de.out_len && row_ok) mask = ((long long)row < (long long)de.out_len[b]) ? 1.f : 0.f;
+  constexpr int CW = BN / (UM_EPI_WARPS / 4);  // columns per warp
+  const int cbeg = cgrp * CW;
+  const bool vec = vec_ok != 0;
+  static_assert(CW == 32 || CW == 16, "one or two 16-column chunks per epilogue warp");
+  // operand tiles of BOTH chunks are requested before the accumulator is complete (memory-level parallelism is what
+  // bounds the read-modify-write epilogues of the 1x1 projections)
+  EpiOps16 ops0, ops1;
+  const bool v0 = vec && row_ok && n0 + cbeg + 16 <= de.Cout;
+  const bool v1 = vec && row_ok && n0 + cbeg + 32 <= de.Cout;
+  if (v0) conv_epilogue16_load(de, b, row, n0 + cbeg, ops0);
+  if (CW == 32 && v1) conv_epilogue16_load(de, b, row, n0 + cbeg + 16, ops1);
+  mbar_wait(tfull, ((uint32_t)i >> 1) & 1u);
+  tc_fence_after();
+  const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * NACC * BN);
+#pragma unroll
+  for (int c = 0; c < CW; c += 16) {
+    const int col0 = cbeg + c;
+    if (n0 + col0 >= de.Cout) continue;  // warp-uniform: chunk entirely past the last output column
+    float v[16], t[16];
+    tmem_ld16(tbase + (uint32_t)((NACC - 1) * BN + col0), v);  // cross terms; warp-collective: no divergence before
+    for (int a = 0; a < n_main; ++a) {                         // main accumulators (n_main is CTA-uniform)
+      tmem_ld16(tbase + (uint32_t)(a * BN + col0), t);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] += t[e];
+    }
+    if (tma_st) {
+      // all 32 rows of the warp leave together: registers -> 2 KB staging tile -> one TMA bulk store per output
+      // tensor (rows past the end of the utterance are clipped by the tensor map)
+      const bool gate = (de.act == PTTSPP_ACT_GATE);
+      const int nout = gate ? 8 : 16;
+      const int ocol = gate ? ((n0 + col0) >> 1) : (n0 + col0);
+      float o[16];
+      conv_epilogue16_math(de, b, row, mask, n0 + col0, v, c == 0 ? ops0 : ops1, o);
+      const int row_first = m0 + q * 32;
+      if (de.out) {
+        if (lane == 0) bulk_wait_read0();  // the previous store has finished reading the staging tile
+        __syncwarp();
+        float4* st = reinterpret_cast<float4*>(stage + lane * nout * 4);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          if (4 * k4 < nout) st[k4] = make_float4(o[4 * k4], o[4 * k4 + 1], o[4 * k4 + 2], o[4 * k4 + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&maps->f32, stage_u32, ocol, row_first, b);
+          bulk_commit();
+        }
+      }
+      if (de.out_hi) {
+        if (de.out_plane_add) {
+          const float4* pp = reinterpret_cast<const float4*>(de.out_plane_add + ocol);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            if (4 * k4 < nout) {
+              const float4 tq = __ldg(pp + k4);
+              o[4 * k4] += tq.x; o[4 * k4 + 1] += tq.y; o[4 * k4 + 2] += tq.z; o[4 * k4 + 3] += tq.w;
+            }
+        }
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        uint4* sh = reinterpret_cast<uint4*>(stage + lane * nout * 2);
+        uint4* sl = reinterpret_cast<uint4*>(stage + 1024 + lane * nout * 2);
+#pragma unroll
+        for (int k8 = 0; k8 < 2; ++k8)
+          if (8 * k8 < nout) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int j2 = 0; j2 < 4; ++j2) {
+              __half h0, l0, h1, l1;
+              split_f16(o[8 * k8 + 2 * j2], h0, l0);
+              split_f16(o[8 * k8 + 2 * j2 + 1], h1, l1);
+              hw[j2] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+              lw[j2] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            }
+            sh[k8] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            sl[k8] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&maps->hi, stage_u32, ocol, row_first, b);
+          tma_store_3d(&maps->lo, stage_u32 + 1024, ocol, row_first, b);
+          bulk_commit();
+        }
+      }
+    } else if (row_ok) {
+      if (c == 0 ? v0 : v1) {
+        conv_epilogue16_finish(de, b, row, mask, n0 + col0, v, c == 0 ? ops0 : ops1);
+      } else {
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          const float a4[4] = {v[gq * 4 + 0], v[gq * 4 + 1], v[gq * 4 + 2], v[gq * 4 + 3]};
+          conv_epilogue4(de, b, row, mask, n0 + col0 + gq * 4, a4);
+        }
+      }
+    }
+  }
+}
+
 // Persistent, warp-specialised: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA and MMA warps
 // run ahead into the next tile while the eight epilogue warps drain the previous accumulator: TMEM holds two
 // accumulator buffers of (main | cross-term) x BN columns.
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NACC>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                    const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
-                   const pttspp_conv1d_desc d, const int vec_ok, const int n_mt, const int n_nt, const int n_tiles) {
+                   const __grid_constant__ OutMaps om, const __grid_constant__ OutMaps om2,
+                   const pttspp_conv1d_desc d, const pttspp_conv1d_desc d2, const int cout1, const int vec_ok,
+                   const int tma_out, const int n_mt, const int n_nt, const int n_tiles) {
+  // d describes the contraction (shared by all tiles) and the epilogue of output columns [0, cout1); d2 (dual mode,
+  // cout1 < d.Cout) the epilogue of columns [cout1, d.Cout) -- e.g. the residual and skip halves of one projection.
   using SM = UmmaSmem<BN>;
-  constexpr uint32_t TMEM_COLS = 2 * UM_NACC * BN;  // 2 buffers x (main, cross)
+  constexpr uint32_t TMEM_COLS = 2 * NACC * BN;  // 2 buffers x (main accumulators, cross)
   static_assert(TMEM_COLS <= 512, "TMEM budget");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -158,17 +296,17 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
     }
     for (int u = 0; u < 2; ++u) {
       mbar_init(tfull_bar(u), 1);
-      mbar_init(tempty_bar(u), 8);  // one arrival per epilogue warp
+      mbar_init(tempty_bar(u), UM_EPI_WARPS);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
-  if (warp == 8 && lane == 0) {
+  if (warp == UM_EPI_WARPS && lane == 0) {
     tma_prefetch_desc(&mapAh);
     tma_prefetch_desc(&mapAl);
     tma_prefetch_desc(&mapBh);
     tma_prefetch_desc(&mapBl);
   }
-  if (warp == 9) {
+  if (warp == UM_EPI_WARPS + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -178,7 +316,7 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 8) {
+  if (warp == UM_EPI_WARPS) {
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t g = 0;  // ring position, continues across tiles
@@ -200,10 +338,11 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == UM_EPI_WARPS + 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(UM_BM, BN);
+      const uint64_t desc0 = umma_desc_k_sw128(base);
       uint32_t g = 0;
       int i = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
@@ -213,25 +352,28 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
         // The tensor core truncates when it adds into the fp32 accumulator, so the error grows linearly with the
         // number of accumulations into one accumulator: the 2^-11 smaller cross terms (hi*lo, lo*hi) get their
         // own accumulator, the epilogue adds the two in round-to-nearest fp32.
-        const uint32_t acc_main = tmem_base + (uint32_t)(u * UM_NACC * BN);
-        const uint32_t acc_cross = acc_main + (uint32_t)BN;
+        // NACC - 1 main accumulators are used round-robin by K iteration: the truncation bias of one accumulator
+        // grows with the number of MMAs that add into it.
+        const uint32_t acc0 = tmem_base + (uint32_t)(u * NACC * BN);
+        const uint32_t acc_cross = acc0 + (uint32_t)((NACC - 1) * BN);
         for (int it = 0; it < n_iter; ++it, ++g) {
           const int s = g % STAGES;
           const uint32_t ph = (g / STAGES) & 1u;
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t st = base + s * SM::STAGE_BYTES;
-          const uint64_t dAh = umma_desc_k_sw128(st);
-          const uint64_t dAl = umma_desc_k_sw128(st + SM::A_BYTES);
-          const uint64_t dBh = umma_desc_k_sw128(st + 2 * SM::A_BYTES);
-          const uint64_t dBl = umma_desc_k_sw128(st + 2 * SM::A_BYTES + SM::B_BYTES);
+          // descriptors of this stage: only the 14-bit start-address field differs from the stage-0 descriptor
+          const uint64_t dAh = desc0 + (uint64_t)((uint32_t)s * (uint32_t)(SM::STAGE_BYTES >> 4));
+          const uint64_t dAl = dAh + (uint64_t)(SM::A_BYTES >> 4);
+          const uint64_t dBh = dAh + (uint64_t)((2 * SM::A_BYTES) >> 4);
+          const uint64_t dBl = dAh + (uint64_t)((2 * SM::A_BYTES + SM::B_BYTES) >> 4);
+          const uint32_t acc_main = acc0 + (uint32_t)((it % (NACC - 1)) * BN);
+          const uint32_t first_main = (it >= NACC - 1) ? 1u : 0u;
 #pragma unroll
           for (int kk = 0; kk < UM_BK / 16; ++kk) {
-            const uint64_t adv = (uint64_t)(kk * 32 >> 4);  // 16 halves = 32 bytes along K inside the swizzle span
-            const uint32_t first = (it | kk) != 0;
-            umma_f16(acc_cross, dAl + adv, dBh + adv, idesc, first);
+            const uint64_t adv = (uint64_t)(kk * 2);  // 16 halves = 32 bytes along K inside the swizzle span
+            umma_f16(acc_cross, dAl + adv, dBh + adv, idesc, (kk != 0) ? 1u : (it != 0 ? 1u : 0u));
             umma_f16(acc_cross, dAh + adv, dBl + adv, idesc, 1u);
-            umma_f16(acc_main, dAh + adv, dBh + adv, idesc, first);
+            umma_f16(acc_main, dAh + adv, dBh + adv, idesc, (kk != 0) ? 1u : first_main);
           }
           umma_commit(empty_bar(s));  // frees the stage once these MMAs have read it
         }
@@ -239,52 +381,238 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
       }
     }
   } else {
-    // ================= epilogue: warps 0-7 =================
-    const int q = warp & 3;      // TMEM lane quarter this warp may access
-    const int hsel = warp >> 2;  // column half
+    // ================= epilogue: warps 0-15 =================
     int i = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
       const int nt = tile % n_nt, mt = (tile / n_nt) % n_mt, b = tile / (n_nt * n_mt);
-      const int m0 = d.m_begin + mt * UM_BM, n0 = nt * BN;
+      umma_tile_epilogue<BN, NACC>(d, d2, cout1, vec_ok, mt, nt, b, i, warp, lane, tmem_base, tfull_bar(i & 1),
+                                   n_iter < NACC - 1 ? n_iter : NACC - 1, &om, &om2, tma_out,
+                                   gen_base + STAGES * SM::STAGE_BYTES + 256 + warp * 2048,
+                                   base + STAGES * SM::STAGE_BYTES + 256 + warp * 2048);
       const int u = i & 1;
-      mbar_wait(tfull_bar(u), ((uint32_t)i >> 1) & 1u);
-      tc_fence_after();
-      const int m = m0 + q * 32 + lane;
-      const int row = m * d.out_mul + d.out_off;
-      const bool row_ok = (m < d.m_begin + d.M) && row >= 0 && row < d.T_out;
-      float mask = 1.f;
-      if (d.out_len && row_ok) mask = ((long long)row < (long long)d.out_len[b]) ? 1.f : 0.f;
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * UM_NACC * BN);
-#pragma unroll 1
-      for (int c = 0; c < BN / 2; c += 16) {
-        const int col0 = hsel * (BN / 2) + c;
-        float v[16], t[16];
-        tmem_ld16(tbase + (uint32_t)col0, v);         // warp-collective: no divergence before these
-        tmem_ld16(tbase + (uint32_t)(BN + col0), t);  // cross terms
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] += t[e];
-        if (row_ok) {
-          if (vec_ok && n0 + col0 + 16 <= d.Cout) {
-            conv_epilogue16_vec(d, b, row, mask, n0 + col0, v);
-          } else {
-#pragma unroll
-            for (int gq = 0; gq < 4; ++gq) {
-              const float a4[4] = {v[gq * 4 + 0], v[gq * 4 + 1], v[gq * 4 + 2], v[gq * 4 + 3]};
-              conv_epilogue4(d, b, row, mask, n0 + col0 + gq * 4, a4);
-            }
-          }
-        }
-      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(u));
     }
+    if (tma_out && lane == 0) bulk_wait0();  // all bulk stores of this warp have been written
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == UM_EPI_WARPS + 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+
+// ---- A-stationary variant ---------------------------------------------------------------------------------------
+// Shared-memory fill bandwidth (L2 -> SM) bounds the streaming kernel above: every (tap, N tile) re-loads its
+// activation slab.  Here a CTA owns 128 output rows of one utterance, loads their activation planes ONCE -- all Cin
+// slabs, 128 + halo rows -- and walks all N tiles and taps over them, streaming only weights through the ring.
+// Taps share the halo tile: the UMMA descriptor start is simply advanced by tap*dil rows (the swizzle XOR is taken
+// from absolute shared-memory address bits, so any row offset is legal -- verified on B200 by tools/probe_desc.py).
+template <int BN>
+__global__ void __launch_bounds__(UM_THREADS, 1)
+conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                      const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
+                      const pttspp_conv1d_desc d, const pttspp_conv1d_desc d2, const int cout1, const int cout_total,
+                      const int vec_ok, const int n_mt, const int n_nt, const int n_units, const int rowsA,
+                      const int nbst) {
+  constexpr uint32_t TMEM_COLS = 2 * UM_NACC * BN;
+  constexpr int B_BYTES = BN * 128;        // one plane of one weight tile
+  constexpr int BST_BYTES = 2 * B_BYTES;   // hi + lo
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int nslab = d.Cin / UM_BK;
+  const uint32_t a_plane = (uint32_t)rowsA * 128u;          // bytes of one (slab, plane) tile; rowsA % 8 == 0
+  const uint32_t a_bytes = (uint32_t)nslab * 2u * a_plane;  // whole activation block
+  const uint32_t ring = base + a_bytes;
+  const uint32_t bars = ring + (uint32_t)nbst * BST_BYTES;  // fullA, emptyA, fullB[nbst], emptyB[nbst], tfull[2], tempty[2]
+  const int nbars = 2 + 2 * nbst + 4;
+  const uint32_t tmem_slot = bars + nbars * 8;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + a_bytes + nbst * BST_BYTES + nbars * 8);
+  const uint32_t fullA = bars, emptyA = bars + 8;
+  auto fullB = [&](int s) { return bars + (2 + s) * 8; };
+  auto emptyB = [&](int s) { return bars + (2 + nbst + s) * 8; };
+  auto tfull_bar = [&](int u) { return bars + (2 + 2 * nbst + u) * 8; };
+  auto tempty_bar = [&](int u) { return bars + (2 + 2 * nbst + 2 + u) * 8; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(fullA, 1);
+    mbar_init(emptyA, 1);
+    for (int s = 0; s < nbst; ++s) {
+      mbar_init(fullB(s), 1);
+      mbar_init(emptyB(s), 1);
+    }
+    for (int u = 0; u < 2; ++u) {
+      mbar_init(tfull_bar(u), 1);
+      mbar_init(tempty_bar(u), UM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == UM_EPI_WARPS && lane == 0) {
+    tma_prefetch_desc(&mapAh);
+    tma_prefetch_desc(&mapAl);
+    tma_prefetch_desc(&mapBh);
+    tma_prefetch_desc(&mapBl);
+  }
+  if (warp == UM_EPI_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == UM_EPI_WARPS) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t g = 0;
+      int j = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++j) {
+        const int mt = unit % n_mt, b = unit / n_mt;
+        const int row0 = d.m_begin + mt * UM_BM - d.pad;  // first input row of the halo block (may be negative)
+        mbar_wait(emptyA, ((uint32_t)j & 1u) ^ 1u);        // previous unit's MMAs have retired
+        mbar_expect_tx(fullA, a_bytes);
+        for (int slab = 0; slab < nslab; ++slab) {
+          tma_load_3d(base + (uint32_t)(2 * slab) * a_plane, &mapAh, fullA, slab * UM_BK, row0, b);
+          tma_load_3d(base + (uint32_t)(2 * slab + 1) * a_plane, &mapAl, fullA, slab * UM_BK, row0, b);
+        }
+        for (int nt = 0; nt < n_nt; ++nt)
+          for (int slab = 0; slab < nslab; ++slab)
+            for (int tap = 0; tap < d.K; ++tap, ++g) {
+              const int s = g % nbst;
+              const uint32_t ph = (g / nbst) & 1u;
+              mbar_wait(emptyB(s), ph ^ 1u);
+              mbar_expect_tx(fullB(s), BST_BYTES);
+              const uint32_t st = ring + (uint32_t)s * BST_BYTES;
+              tma_load_2d(st, &mapBh, fullB(s), slab * UM_BK, tap * cout_total + nt * BN);
+              tma_load_2d(st + B_BYTES, &mapBl, fullB(s), slab * UM_BK, tap * cout_total + nt * BN);
+            }
+      }
+    }
+  } else if (warp == UM_EPI_WARPS + 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(UM_BM, BN);
+      uint32_t g = 0;
+      int j = 0, i = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++j) {
+        mbar_wait(fullA, (uint32_t)j & 1u);
+        tc_fence_after();
+        for (int nt = 0; nt < n_nt; ++nt, ++i) {
+          const int u = i & 1;
+          mbar_wait(tempty_bar(u), (((uint32_t)i >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t acc_main = tmem_base + (uint32_t)(u * UM_NACC * BN);
+          const uint32_t acc_cross = acc_main + (uint32_t)BN;
+          uint32_t first = 0;
+          for (int slab = 0; slab < nslab; ++slab)
+            for (int tap = 0; tap < d.K; ++tap, ++g) {
+              const int s = g % nbst;
+              const uint32_t ph = (g / nbst) & 1u;
+              mbar_wait(fullB(s), ph);
+              tc_fence_after();
+              const uint32_t a_off = (uint32_t)(tap * d.dil) * 128u;  // taps share the halo tile
+              const uint64_t dAh = umma_desc_k_sw128(base + (uint32_t)(2 * slab) * a_plane + a_off);
+              const uint64_t dAl = umma_desc_k_sw128(base + (uint32_t)(2 * slab + 1) * a_plane + a_off);
+              const uint32_t st = ring + (uint32_t)s * BST_BYTES;
+              const uint64_t dBh = umma_desc_k_sw128(st);
+              const uint64_t dBl = umma_desc_k_sw128(st + B_BYTES);
+#pragma unroll
+              for (int kk = 0; kk < UM_BK / 16; ++kk) {
+                const uint64_t adv = (uint64_t)(kk * 32 >> 4);
+                umma_f16(acc_cross, dAl + adv, dBh + adv, idesc, first);
+                umma_f16(acc_cross, dAh + adv, dBl + adv, idesc, 1u);
+                umma_f16(acc_main, dAh + adv, dBh + adv, idesc, first);
+                first = 1u;
+              }
+              umma_commit(emptyB(s));
+            }
+          umma_commit(tfull_bar(u));
+        }
+        umma_commit(emptyA);  // the activation block may be overwritten once everything issued so far has retired
+      }
+    }
+  } else {
+    // ================= epilogue: warps 0-15 =================
+    int i = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const int mt = unit % n_mt, b = unit / n_mt;
+      for (int nt = 0; nt < n_nt; ++nt, ++i) {
+        umma_tile_epilogue<BN, UM_NACC>(d, d2, cout1, vec_ok, mt, nt, b, i, warp, lane, tmem_base, tfull_bar(i & 1), 1,
+                                        nullptr, nullptr, 0, nullptr, 0u);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(i & 1));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == UM_EPI_WARPS + 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- probe: UMMA shared-memory descriptors whose start row is not a multiple of 8 --------------------------------
+// D[128][128] = A[row_off : row_off + 128][0:64] . B[0:128][0:64]^T with the A tile loaded ONCE (144 rows) and the
+// descriptor start advanced by row_off * 128 bytes.  mode 0: base_offset field 0; mode 1: base_offset =
+// (start_address >> 7) & 7 as the PTX ISA prescribes for starts that are not aligned to the 1024-byte swizzle
+// pattern.  Decides whether a conv can share one halo tile between its taps.
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int row_off,
+                  int mode, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base, sB = base + 144 * 128;  // 18432 = 18 * 1024: B stays 1024-aligned
+  const uint32_t bar_full = base + 144 * 128 + 128 * 128, bar_done = bar_full + 8, slot = bar_full + 16;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 144 * 128 + 128 * 128 + 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_full, 1);
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot_ptr;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar_full, 144 * 128 + 128 * 128);
+    tma_load_2d(sA, &mapA, bar_full, 0, 0);
+    tma_load_2d(sB, &mapB, bar_full, 0, 0);
+    mbar_wait(bar_full, 0);
+    tc_fence_after();
+    const uint32_t a_start = sA + (uint32_t)row_off * 128u;
+    uint64_t dA = umma_desc_k_sw128(a_start);
+    if (mode == 1) dA |= (uint64_t)((a_start >> 7) & 7u) << 49;
+    const uint64_t dB = umma_desc_k_sw128(sB);
+    for (int kk = 0; kk < 4; ++kk) umma_f16(tmem, dA + (uint64_t)(kk * 2), dB + (uint64_t)(kk * 2), umma_idesc_f16(128, 128), kk != 0);
+    umma_commit(bar_done);
+  }
+  mbar_wait(bar_done, 0);
+  tc_fence_after();
+  for (int c = 0; c < 128; c += 16) {
+    float v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+    for (int e = 0; e < 16; ++e) out[(warp * 32 + lane) * 128 + c + e] = v[e];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
   }
 }
 
@@ -304,7 +632,9 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-CUtensorMap make_map(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+CUtensorMap make_map(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                     CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                     CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   PT_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   CUtensorMap m;
@@ -312,8 +642,8 @@ CUtensorMap make_map(const void* ptr, int rank, const uint64_t* dims, const uint
   cuuint32_t gbox[3], estr[3] = {1, 1, 1};
   for (int i = 0; i < rank; ++i) gdim[i] = dims[i], gbox[i] = box[i];
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr, gbox, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(&m, dtype, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr, gbox, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PT_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d (rank %d, dims %llu x %llu)", (int)r, rank,
            (unsigned long long)dims[0], (unsigned long long)dims[1]);
@@ -323,6 +653,34 @@ CUtensorMap make_map(const void* ptr, int rank, const uint64_t* dims, const uint
 constexpr int UM_BN = 128;
 constexpr int UM_STAGES = 3;
 
+// TMA bulk stores need the plain row mapping (row = m) over the whole output and 16-byte aligned strides
+bool tma_out_ok(const pttspp_conv1d_desc& d) {
+  if (!conv_epilogue_vec_ok(d)) return false;
+  if (d.out_mul != 1 || d.out_off != 0 || d.m_begin != 0 || d.M != d.T_out) return false;
+  if (d.out && (d.out_ld % 4 != 0 || d.out_bs % 4 != 0)) return false;
+  if (d.out_hi && (d.out_plane_ld % 8 != 0 || d.out_plane_bs % 8 != 0)) return false;
+  return getenv("PTTSPP_UMMA_NO_TMA_STORE") == nullptr;
+}
+
+OutMaps make_out_maps(const pttspp_conv1d_desc& d) {
+  OutMaps om;
+  memset(&om, 0, sizeof(om));
+  const bool gate = d.act == PTTSPP_ACT_GATE;
+  const uint64_t cols = gate ? d.Cout / 2 : d.Cout;
+  const uint32_t box[3] = {gate ? 8u : 16u, 32u, 1u};
+  const uint64_t dims[3] = {cols, (uint64_t)d.T_out, (uint64_t)d.B};
+  if (d.out) {
+    const uint64_t str[2] = {(uint64_t)d.out_ld * 4, (uint64_t)d.out_bs * 4};
+    om.f32 = make_map(d.out, 3, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE);
+  }
+  if (d.out_hi) {
+    const uint64_t str[2] = {(uint64_t)d.out_plane_ld * 2, (uint64_t)d.out_plane_bs * 2};
+    om.hi = make_map(d.out_hi, 3, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_NONE);
+    om.lo = make_map(d.out_lo, 3, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_NONE);
+  }
+  return om;
+}
+
 }  // namespace
 
 bool conv1d_umma_supported(const pttspp_conv1d_desc& d) {
@@ -331,28 +689,26 @@ bool conv1d_umma_supported(const pttspp_conv1d_desc& d) {
          aligned16(d.w_lo) && d.w_scale_inv > 0.f;
 }
 
-void conv1d_umma_cl(const pttspp_conv1d_desc& d_in, cudaStream_t s) {
+// d2 != nullptr: dual-epilogue launch.  d and d2 must describe the same contraction input (planes, K, dil, pad, Cin,
+// row range); the packed weight planes of d2 must directly follow those of d (K == 1), so that one tensor map covers
+// the Cout(d) + Cout(d2) rows.
+void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc* d2_in, cudaStream_t s) {
   pttspp_conv1d_desc d = d_in;
   d.acc_scale = d_in.acc_scale * d_in.w_scale_inv;  // undo the power-of-two weight scale on the accumulator
-  // activation planes [B][T_in][Cin]: dims innermost first
-  const uint64_t adims[3] = {(uint64_t)d.Cin, (uint64_t)d.T_in, (uint64_t)d.B};
-  const uint64_t astr[2] = {(uint64_t)d.in_ld * 2, (uint64_t)d.in_bs * 2};
-  const uint32_t abox[3] = {UM_BK, UM_BM, 1};
-  // weight planes [K*Cout][Cin]
-  const uint64_t wdims[2] = {(uint64_t)d.Cin, (uint64_t)d.K * d.Cout};
-  const uint64_t wstr[1] = {(uint64_t)d.Cin * 2};
-  const uint32_t wbox[2] = {UM_BK, UM_BN};
-  const CUtensorMap mAh = make_map(d.in_hi, 3, adims, astr, abox);
-  const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox);
-  const CUtensorMap mBh = make_map(d.w_hi, 2, wdims, wstr, wbox);
-  const CUtensorMap mBl = make_map(d.w_lo, 2, wdims, wstr, wbox);
-  using SM = UmmaSmem<UM_BN>;
-  const size_t smem = (size_t)UM_STAGES * SM::STAGE_BYTES + 256 + 1024;
-  auto kern = conv1d_umma_kernel<UM_BN, UM_STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+  pttspp_conv1d_desc d2 = d2_in ? *d2_in : d_in;
+  const int cout1 = d_in.Cout;
+  bool vec = conv_epilogue_vec_ok(d);
+  if (d2_in) {
+    PT_CHECK(d.K == 1 && d2.K == 1 && d2.Cin == d.Cin && d2.in_hi == d.in_hi && d2.M == d.M && d2.m_begin == d.m_begin &&
+                 d2.B == d.B && d2.T_in == d.T_in,
+             "conv1d dual launch: the two descriptors must share the contraction input");
+    PT_CHECK((const char*)d2.w_hi == (const char*)d.w_hi + (size_t)cout1 * d.Cin * 2 &&
+                 (const char*)d2.w_lo == (const char*)d.w_lo + (size_t)cout1 * d.Cin * 2 && d2.w_scale_inv == d.w_scale_inv,
+             "conv1d dual launch: weight planes must be contiguous");
+    PT_CHECK(cout1 % 128 == 0, "conv1d dual launch: first Cout must be a multiple of the N tile");
+    d2.acc_scale = d2_in->acc_scale * d2_in->w_scale_inv;
+    vec = vec && conv_epilogue_vec_ok(d2);
+    d.Cout = cout1 + d2.Cout;  // contraction-wide column count (TMA rows, tile count)
   }
   static int num_sms = 0;
   if (num_sms == 0) {
@@ -360,12 +716,138 @@ void conv1d_umma_cl(const pttspp_conv1d_desc& d_in, cudaStream_t s) {
     PT_CUDA(cudaGetDevice(&dev));
     PT_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int n_mt = ceil_div(d.M, UM_BM), n_nt = ceil_div(d.Cout, UM_BN);
+  const int total_cout = d.Cout;
+  if (d2_in) d.Cout = cout1;  // the epilogue of the first half sees its own column count again
+  const int n_mt = ceil_div(d.M, UM_BM), n_nt = ceil_div(total_cout, UM_BN);
+  const int nslab = d.Cin / UM_BK;
+  // weight planes [K*Cout][Cin]
+  const uint64_t wdims[2] = {(uint64_t)d.Cin, (uint64_t)d.K * total_cout};
+  const uint64_t wstr[1] = {(uint64_t)d.Cin * 2};
+  const uint32_t wbox[2] = {UM_BK, UM_BN};
+  const CUtensorMap mBh = make_map(d.w_hi, 2, wdims, wstr, wbox);
+  const CUtensorMap mBl = make_map(d.w_lo, 2, wdims, wstr, wbox);
+  // activation planes [B][T_in][Cin]: dims innermost first
+  const uint64_t adims[3] = {(uint64_t)d.Cin, (uint64_t)d.T_in, (uint64_t)d.B};
+  const uint64_t astr[2] = {(uint64_t)d.in_ld * 2, (uint64_t)d.in_bs * 2};
+
+  // A-stationary kernel when the activation block of a 128-row unit fits next to >= 2 weight stages and there are
+  // enough units to fill the machine; otherwise the streaming kernel.
+  const int rowsA = UM_BM + round_up((d.K - 1) * d.dil, 8);
+  const size_t a_bytes = (size_t)nslab * 2 * rowsA * 128;
+  const size_t bst = 2 * (size_t)UM_BN * 128;
+  const size_t cap = 227 * 1024 - 1024 - 512;
+  const long long n_units = (long long)n_mt * d.B;
+  // The streaming kernel measured faster on every shape of this model (tools/bench_conv.py: the A-stationary kernel
+  // is left with two weight stages in flight and becomes latency bound), so the latter is opt-in.
+  const bool a_stationary = getenv("PTTSPP_UMMA_AS") != nullptr;
+  if (a_stationary && rowsA <= 256 && a_bytes + 2 * bst <= cap && n_units * 2 >= num_sms) {
+    const int nbst = (int)std::min<size_t>(6, (cap - a_bytes) / bst);
+    const uint32_t abox[3] = {UM_BK, (uint32_t)rowsA, 1};
+    const CUtensorMap mAh = make_map(d.in_hi, 3, adims, astr, abox);
+    const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox);
+    const size_t smem = a_bytes + nbst * bst + 512 + 1024;
+    auto kern = conv1d_umma_as_kernel<UM_BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    const int grid = (int)std::min<long long>(n_units, num_sms);
+    kern<<<grid, UM_THREADS, smem, s>>>(mAh, mAl, mBh, mBl, d, d2, d2_in ? cout1 : total_cout, total_cout, vec ? 1 : 0,
+                                        n_mt, n_nt, (int)n_units, rowsA, nbst);
+    PT_LAUNCHED();
+    return;
+  }
+  const uint32_t abox[3] = {UM_BK, UM_BM, 1};
+  const CUtensorMap mAh = make_map(d.in_hi, 3, adims, astr, abox);
+  const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox);
+  // epilogue output maps (per descriptor, with its own column count)
+  pttspp_conv1d_desc e1 = d, e2 = d2;
+  if (d2_in) e1.Cout = cout1;
+  int tma_out = 0;
+  OutMaps om, om2;
+  memset(&om, 0, sizeof(om));
+  memset(&om2, 0, sizeof(om2));
+  if (vec && tma_out_ok(e1)) {
+    om = make_out_maps(e1);
+    tma_out |= 1;
+  }
+  if (d2_in && vec && tma_out_ok(e2)) {
+    om2 = make_out_maps(e2);
+    tma_out |= 2;
+  }
+  if (d2_in) d.Cout = total_cout;  // the streaming kernel's producer derives weight rows from d.Cout
+  // Long contractions (many MMAs into one accumulator) and narrow outputs take the 64-column tile with three
+  // round-robin main accumulators; everything else the 128-column tile with one.
+  const int accumulations = d.K * d.Cin / 16;
+  const bool narrow = !d2_in && (total_cout <= 64 || accumulations > 64);
+  if (narrow) {
+    constexpr int BN = 64, ST = 4, NA = 4;
+    const uint32_t wbox64[2] = {UM_BK, BN};
+    const CUtensorMap mBh64 = make_map(d.w_hi, 2, wdims, wstr, wbox64);
+    const CUtensorMap mBl64 = make_map(d.w_lo, 2, wdims, wstr, wbox64);
+    const size_t smem = (size_t)ST * UmmaSmem<BN>::STAGE_BYTES + 256 + UM_EPI_WARPS * 2048 + 1024;
+    auto kern = conv1d_umma_kernel<BN, ST, NA>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    const int nnt = ceil_div(total_cout, BN);
+    const long long n_tiles = (long long)n_mt * nnt * d.B;
+    PT_CHECK(n_tiles < (1ll << 30), "conv1d: too many tiles");
+    const int grid = (int)std::min<long long>(n_tiles, num_sms);
+    kern<<<grid, UM_THREADS, smem, s>>>(mAh, mAl, mBh64, mBl64, om, om2, d, d2, total_cout, vec ? 1 : 0, tma_out, n_mt,
+                                        nnt, (int)n_tiles);
+    PT_LAUNCHED();
+    return;
+  }
+  using SM = UmmaSmem<UM_BN>;
+  const size_t smem = (size_t)UM_STAGES * SM::STAGE_BYTES + 256 + UM_EPI_WARPS * 2048 + 1024;
+  auto kern = conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
   const long long n_tiles = (long long)n_mt * n_nt * d.B;
   PT_CHECK(n_tiles < (1ll << 30), "conv1d: too many tiles");
   const int grid = (int)std::min<long long>(n_tiles, num_sms);
-  kern<<<grid, UM_THREADS, smem, s>>>(mAh, mAl, mBh, mBl, d, conv_epilogue_vec_ok(d) ? 1 : 0, n_mt, n_nt, (int)n_tiles);
+  kern<<<grid, UM_THREADS, smem, s>>>(mAh, mAl, mBh, mBl, om, om2, d, d2, d2_in ? cout1 : total_cout, vec ? 1 : 0, tma_out,
+                                      n_mt, n_nt, (int)n_tiles);
+  PT_LAUNCHED();
+}
+
+void conv1d_umma_cl(const pttspp_conv1d_desc& d, cudaStream_t s) { conv1d_umma_launch(d, nullptr, s); }
+
+void conv1d_umma_dual_cl(const pttspp_conv1d_desc& d1, const pttspp_conv1d_desc& d2, cudaStream_t s) {
+  PT_CHECK(conv1d_umma_supported(d1) && conv1d_umma_supported(d2), "conv1d dual launch: unsupported descriptor");
+  const double flops = 2.0 * d1.B * (double)d1.M * (d1.Cout + d2.Cout) * (double)d1.Cin * d1.K;
+  ProfScope prof(PROF_CONV_UMMA, s, flops, 0.0);
+  conv1d_umma_launch(d1, &d2, s);
+}
+
+void umma_probe(const void* a_half /*[rows][64]*/, int rows, const void* b_half /*[128][64]*/, int row_off, int mode,
+                float* out, cudaStream_t s) {
+  PT_CHECK(rows >= 144 && row_off >= 0 && row_off + 128 <= 144, "umma_probe: bad geometry");
+  const uint64_t adims[2] = {64, (uint64_t)rows}, astr[1] = {128};
+  const uint32_t abox[2] = {64, 144};
+  const uint64_t bdims[2] = {64, 128}, bstr[1] = {128};
+  const uint32_t bbox[2] = {64, 128};
+  const CUtensorMap mA = make_map(a_half, 2, adims, astr, abox);
+  const CUtensorMap mB = make_map(b_half, 2, bdims, bstr, bbox);
+  const size_t smem = 144 * 128 + 128 * 128 + 64 + 1024;
+  PT_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_probe_kernel<<<1, 128, smem, s>>>(mA, mB, row_off, mode, out);
   PT_LAUNCHED();
 }
 
 }  // namespace pttspp
+
+extern "C" int pttspp_umma_probe(const void* a_half, int rows, const void* b_half, int row_off, int mode, float* out,
+                                 pttspp_stream_t stream) {
+  PT_API_BEGIN
+  pttspp::umma_probe(a_half, rows, b_half, row_off, mode, out, (cudaStream_t)stream);
+  PT_API_END
+}
+

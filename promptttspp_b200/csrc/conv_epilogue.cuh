@@ -98,8 +98,37 @@ __device__ __forceinline__ float gate_fast(float g, float f) {
 // (col % 16 == 0, col + 16 <= Cout) of one row and moves them with 16-byte accesses (every 32-byte sector it
 // touches is fully used).  Preconditions (checked on the host, see conv_epilogue_vec_ok): all row strides are
 // multiples of 4 floats / 8 halves and all base pointers are 16-byte aligned.
-__device__ __forceinline__ void conv_epilogue16_vec(const pttspp_conv1d_desc& d, int b, int row, float mask, int col,
-                                                    float (&v)[16]) {
+// Split in two phases so the kernel can issue the operand loads of the next chunk (or of the next tile, before its
+// accumulator is even complete) while it works on the current one.
+// One operand tile is prefetched per 16-column chunk (priority: addend, else residual, else previous output --
+// the DiffNet launches each have exactly one of them); further operands are loaded in place.
+struct EpiOps16 {
+  float4 p[4];
+};
+
+__device__ __forceinline__ int conv_epilogue_prefetch_kind(const pttspp_conv1d_desc& d) {
+  return d.addend ? 1 : (d.res ? 2 : ((d.out && d.beta != 0.f) ? 3 : 0));
+}
+
+__device__ __forceinline__ void conv_epilogue16_load(const pttspp_conv1d_desc& d, int b, int row, int col, EpiOps16& o) {
+  const bool gate = (d.act == PTTSPP_ACT_GATE);
+  const int ocol = gate ? (col >> 1) : col;
+  const int kind = conv_epilogue_prefetch_kind(d);
+  const float4* src = nullptr;
+  if (kind == 1) src = reinterpret_cast<const float4*>(d.addend + (int64_t)b * d.addend_bs + (int64_t)row * d.addend_ld + col);
+  else if (kind == 2) src = reinterpret_cast<const float4*>(d.res + (int64_t)b * d.res_bs + (int64_t)row * d.res_ld + ocol);
+  else if (kind == 3) src = reinterpret_cast<const float4*>(d.out + (int64_t)b * d.out_bs + (int64_t)row * d.out_ld + ocol);
+  const int nq = (kind == 1 || !gate) ? 4 : 2;
+  if (src) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < nq) o.p[i] = src[i];
+  }
+}
+
+// arithmetic only: o[0..nout) = final output values of columns ocol.. (nout = 8 for the gate activation, else 16)
+__device__ __forceinline__ void conv_epilogue16_math(const pttspp_conv1d_desc& d, int b, int row, float mask, int col,
+                                                     float (&v)[16], const EpiOps16& ops, float (&o)[16]) {
   const bool gate = (d.act == PTTSPP_ACT_GATE);
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] *= d.acc_scale;
@@ -111,20 +140,27 @@ __device__ __forceinline__ void conv_epilogue16_vec(const pttspp_conv1d_desc& d,
       v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
     }
   }
+  const int pk = conv_epilogue_prefetch_kind(d);
   if (d.addend) {
-    const float4* ap = reinterpret_cast<const float4*>(d.addend + (int64_t)b * d.addend_bs + (int64_t)row * d.addend_ld + col);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 t = __ldg(ap + i);
+      const float4 t = ops.p[i];
       v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
     }
   }
-  float o[16];
   const int nout = gate ? 8 : 16;
   const int ocol = gate ? (col >> 1) : col;
   if (gate) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = gate_fast(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+    for (int i = 8; i < 16; ++i) o[i] = 0.f;
+  } else if (d.act == PTTSPP_ACT_NONE) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = v[i];
+  } else if (d.act == PTTSPP_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = fmaxf(v[i], 0.f);
   } else {
 #pragma unroll
     for (int i = 0; i < 16; ++i) o[i] = act_apply(v[i], d.act);
@@ -138,34 +174,38 @@ __device__ __forceinline__ void conv_epilogue16_vec(const pttspp_conv1d_desc& d,
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (4 * i < nout) {
-        const float4 t = rp[i];
+        const float4 t = (pk == 2) ? ops.p[i] : rp[i];
         o[4 * i] += d.res_scale * t.x; o[4 * i + 1] += d.res_scale * t.y;
         o[4 * i + 2] += d.res_scale * t.z; o[4 * i + 3] += d.res_scale * t.w;
       }
   }
+  if (d.out && d.beta != 0.f) {
+    const float4* op = reinterpret_cast<const float4*>(d.out + (int64_t)b * d.out_bs + (int64_t)row * d.out_ld + ocol);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (4 * i < nout) {
+        const float4 t = (pk == 3) ? ops.p[i] : op[i];
+        o[4 * i] += d.beta * t.x; o[4 * i + 1] += d.beta * t.y; o[4 * i + 2] += d.beta * t.z; o[4 * i + 3] += d.beta * t.w;
+      }
+  }
+  if (d.out_div != 0.f) {
+    const float inv = 1.f / d.out_div;  // <= 1 ulp from the IEEE division of the reference
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nout) o[i] = o[i] * inv;
+  }
+}
+
+// direct (row-per-lane) stores of the values computed by conv_epilogue16_math
+__device__ __forceinline__ void conv_epilogue16_store(const pttspp_conv1d_desc& d, int b, int row, int col, float (&o)[16]) {
+  const bool gate = (d.act == PTTSPP_ACT_GATE);
+  const int nout = gate ? 8 : 16;
+  const int ocol = gate ? (col >> 1) : col;
   if (d.out) {
     float4* op = reinterpret_cast<float4*>(d.out + (int64_t)b * d.out_bs + (int64_t)row * d.out_ld + ocol);
-    if (d.beta != 0.f) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (4 * i < nout) {
-          const float4 t = op[i];
-          o[4 * i] += d.beta * t.x; o[4 * i + 1] += d.beta * t.y; o[4 * i + 2] += d.beta * t.z; o[4 * i + 3] += d.beta * t.w;
-        }
-    }
-    if (d.out_div != 0.f) {
-      const float inv = 1.f / d.out_div;
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i < nout) o[i] = o[i] * inv;
-    }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (4 * i < nout) op[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-  } else if (d.out_div != 0.f) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i < nout) o[i] = o[i] / d.out_div;
   }
   if (d.out_hi) {
     if (d.out_plane_add) {
@@ -198,7 +238,14 @@ __device__ __forceinline__ void conv_epilogue16_vec(const pttspp_conv1d_desc& d,
   }
 }
 
-// host-side precondition of conv_epilogue16_vec
+__device__ __forceinline__ void conv_epilogue16_finish(const pttspp_conv1d_desc& d, int b, int row, float mask, int col,
+                                                       float (&v)[16], const EpiOps16& ops) {
+  float o[16];
+  conv_epilogue16_math(d, b, row, mask, col, v, ops, o);
+  conv_epilogue16_store(d, b, row, col, o);
+}
+
+// host-side precondition of the conv_epilogue16_* vector path
 static inline bool conv_epilogue_vec_ok(const pttspp_conv1d_desc& d) {
   auto ok4 = [](const void* p, int64_t bs, int ld) { return !p || (aligned16(p) && bs % 4 == 0 && ld % 4 == 0); };
   if (d.Cout % 16 != 0) return false;

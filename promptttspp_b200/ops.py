@@ -160,7 +160,7 @@ def pack_conv_weight_split(weight, g=None, interleave_halves=False, device=None)
 
 def conv1d_umma_cl(x_planes, w_split, Cout, bias=None, K=1, dil=1, pad=0, act=ACT_NONE, out_len=None, addend=None,
                    res=None, res_scale=1.0, alpha=1.0, beta=0.0, out=None, acc_scale=1.0, out_div=0.0,
-                   emit_planes=False, plane_add=None, write_f32=True):
+                   emit_planes=False, plane_add=None, write_f32=True, _desc_only=False):
     """tcgen05 path on pre-split operands.  x_planes = (hi, lo) [B, T, Cin] fp16; w_split from
     pack_conv_weight_split.  Returns out (fp32) and/or (out_hi, out_lo)."""
     xh, xl = x_planes
@@ -194,5 +194,20 @@ def conv1d_umma_cl(x_planes, w_split, Cout, bias=None, K=1, dil=1, pad=0, act=AC
         d.out_hi = oh.data_ptr(); d.out_lo = ol.data_ptr(); d.out_plane_bs = oh.stride(0); d.out_plane_ld = oh.stride(1)
         d.out_plane_add = None if plane_add is None else plane_add.data_ptr()
         planes = (oh, ol)
+    if _desc_only:
+        return d, out, planes, (xh, xl, wh, wl)
     _abi.check(_abi.lib().pttspp_conv1d_cl(C.byref(d), _abi.stream_ptr(xh.device)))
     return out, planes
+
+
+def conv1d_umma_dual_cl(x_planes, w_split, cout1, kw1, kw2):
+    """One tcgen05 launch, two epilogues: columns [0, cout1) use kw1, the rest kw2 (kwargs of conv1d_umma_cl).
+    w_split packs all Cout rows; returns ((out1, planes1), (out2, planes2))."""
+    wh, wl, sc = w_split
+    Cin = wh.shape[-1]
+    cout2 = wh.shape[1] - cout1
+    d1, o1, p1, keep1 = conv1d_umma_cl(x_planes, (wh, wl, sc), cout1, _desc_only=True, **kw1)
+    wh2, wl2 = wh.view(-1, Cin)[cout1:], wl.view(-1, Cin)[cout1:]
+    d2, o2, p2, keep2 = conv1d_umma_cl(x_planes, (wh2, wl2, sc), cout2, _desc_only=True, **kw2)
+    _abi.check(_abi.lib().pttspp_conv1d_dual_cl(C.byref(d1), C.byref(d2), _abi.stream_ptr(x_planes[0].device)))
+    return (o1, p1), (o2, p2)

@@ -46,11 +46,29 @@ UMMA_CASES = [
     (128, 128, 7, 1, 1, 129),
     (1024, 256, 9, 1, 1, 200),    # many K iterations through the 3-stage ring
     (64, 64, 11, 5, 1, 515),
+    # enough 128-row units (>= half the SMs) to take the A-stationary kernel (taps share one halo tile)
+    (256, 512, 3, 1, 4, 2500),
+    (256, 512, 3, 2, 4, 2431),
+    (256, 512, 3, 4, 3, 3333),
+    (256, 512, 3, 8, 4, 2500),
+    (256, 256, 1, 1, 4, 2500),
+    (256, 80, 1, 1, 4, 2500),
+    (128, 128, 7, 1, 2, 6000),
+    (128, 128, 11, 5, 2, 6000),
+    (64, 64, 11, 5, 1, 12000),
+    (256, 256, 17, 1, 4, 2500),   # frame-prior shape: halo of 16 rows
+    (256, 256, 5, 1, 4, 2500),
 ]
 
 
+@pytest.mark.parametrize("a_stationary", [False, True])
 @pytest.mark.parametrize("Cin,Cout,K,dil,B,T", UMMA_CASES)
-def test_conv1d_umma_plain(ops, Cin, Cout, K, dil, B, T):
+def test_conv1d_umma_plain(ops, monkeypatch, Cin, Cout, K, dil, B, T, a_stationary):
+    # both tcgen05 kernels: streaming (default) and A-stationary with taps sharing one halo tile (opt-in)
+    if a_stationary:
+        monkeypatch.setenv("PTTSPP_UMMA_AS", "1")
+    else:
+        monkeypatch.delenv("PTTSPP_UMMA_AS", raising=False)
     g = torch.Generator().manual_seed(Cin + Cout * 3 + K)
     x = torch.randn(B, Cin, T, generator=g)
     w = torch.randn(Cout, Cin, K, generator=g) / math.sqrt(Cin * K)
@@ -105,3 +123,28 @@ def test_conv1d_umma_diffnet_chain(ops):
     sbuf = _cl(skip_old)
     ops.conv1d_umma_cl(zp, w2s_skip, C, bias=b2[C:].cuda(), out=sbuf, beta=1.0)
     assert float((_bct(sbuf) - skip_ref).abs().max()) < 2e-5
+
+
+def test_conv1d_umma_dual_epilogue(ops):
+    """residual | skip halves of the DiffNet output projection in ONE launch."""
+    g = torch.Generator().manual_seed(12)
+    B, C, T = 4, 256, 2600
+    z = torch.rand(B, C, T, generator=g) * 2 - 1
+    x = torch.randn(B, C, T, generator=g)
+    skip_old = torch.randn(B, C, T, generator=g)
+    w2 = torch.randn(2 * C, C, 1, generator=g) / math.sqrt(C)
+    b2 = torch.randn(2 * C, generator=g)
+    nxt = torch.randn(C, generator=g)
+    o = F.conv1d(z, w2, b2)
+    x_ref = (x + o[:, :C]) / math.sqrt(2.0)
+    skip_ref = skip_old + o[:, C:]
+    zp = ops.split_f16(_cl(z))
+    xbuf, sbuf = _cl(x), _cl(skip_old)
+    (o1, p1), (o2, p2) = ops.conv1d_umma_dual_cl(
+        zp, ops.pack_conv_weight_split(w2, device="cuda"), C,
+        dict(bias=b2[:C].cuda(), res=xbuf, out=xbuf, out_div=math.sqrt(2.0), emit_planes=True, plane_add=nxt.cuda()),
+        dict(bias=b2[C:].cuda(), out=sbuf, beta=1.0, emit_planes=True))
+    assert float((_bct(xbuf) - x_ref).abs().max()) < 2e-5
+    assert float((_bct(sbuf) - skip_ref).abs().max()) < 2e-5
+    assert float((_bct(p1[0].float() + p1[1].float()) - (x_ref + nxt[None, :, None])).abs().max()) < 2e-5
+    assert float((_bct(p2[0].float() + p2[1].float()) - skip_ref).abs().max()) < 2e-5

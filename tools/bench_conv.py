@@ -45,10 +45,19 @@ def main():
     fl2 = 2.0 * B * T * C * C
     rows = []
 
+    import os
+
     def add(name, fl, fn):
-        ms = timeit(fn)
-        rows.append((name, ms, fl / ms / 1e9))
-        print(f"{name:58s} {ms*1e3:9.1f} us   {fl / ms / 1e9:8.1f} TFLOP/s (algorithmic)", flush=True)
+        modes = (("str", None), ("AS ", "1")) if name.startswith("umma") else (("   ", None),)
+        for tag, env in modes:
+            if env is None:
+                os.environ.pop("PTTSPP_UMMA_AS", None)
+            else:
+                os.environ["PTTSPP_UMMA_AS"] = env
+            ms = timeit(fn)
+            rows.append((name, ms, fl / ms / 1e9))
+            print(f"{tag} {name:58s} {ms*1e3:9.1f} us   {fl / ms / 1e9:8.1f} TFLOP/s (algorithmic)", flush=True)
+        os.environ.pop("PTTSPP_UMMA_AS", None)
 
     for dil in (1, 8):
         add(f"umma dilated k3 d{dil} 256->512 plain fp32 out", fl1,
@@ -61,6 +70,13 @@ def main():
                                    plane_add=b2))
     add("umma 1x1 256->256 skip accumulate", fl2,
         lambda: ops.conv1d_umma_cl(planes, w2s, C, bias=b2, out=skip, beta=1.0))
+    w2full = ops.pack_conv_weight_split(torch.randn(2 * C, C, 1, generator=g) / math.sqrt(C), device="cuda")
+    b2f = torch.randn(2 * C, generator=g).cuda()
+    add("umma 1x1 256->512 DUAL residual+planes | skip accumulate", 2 * fl2,
+        lambda: ops.conv1d_umma_dual_cl(planes, w2full, C,
+                                        dict(bias=b2f[:C], res=h, out=h, out_div=math.sqrt(2.0), emit_planes=True,
+                                             plane_add=b2),
+                                        dict(bias=b2f[C:], out=skip, beta=1.0)))
     add("simt dilated k3 d1 256->512 gate+addend", fl1,
         lambda: ops.conv1d_cl(x, w1p, 2 * C, bias=b1, K=3, dil=1, pad=1, act=ops.ACT_GATE, addend=cond, in_add=b2, impl=1))
     add("simt 1x1 256->256 residual", fl2, lambda: ops.conv1d_cl(x, w2p, C, bias=b2, res=h, out=h, out_div=1.41421, impl=1))

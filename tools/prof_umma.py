@@ -1,4 +1,4 @@
-"""Tiny driver for ncu: a few launches of the tcgen05 conv on the DiffNet dilated-conv shape."""
+"""Tiny driver for ncu: the two tcgen05 launches of a DiffNet layer on the cfg2 shape."""
 import math
 import sys
 from pathlib import Path
@@ -17,10 +17,14 @@ cond = torch.randn(B, T, 2 * C, generator=g).cuda()
 w1 = torch.randn(2 * C, C, 3, generator=g) / math.sqrt(3 * C)
 b1 = torch.randn(2 * C, generator=g).cuda()
 w1s = ops.pack_conv_weight_split(w1, interleave_halves=True, device="cuda")
-w2s = ops.pack_conv_weight_split(torch.randn(C, C, 1, generator=g) / 16, device="cuda")
+w2s = ops.pack_conv_weight_split(torch.randn(2 * C, C, 1, generator=g) / 16, device="cuda")
+b2 = torch.randn(2 * C, generator=g).cuda()
 h = x.clone()
+skip = torch.zeros_like(x)
 for _ in range(3):
     _, zp = ops.conv1d_umma_cl(planes, w1s, 2 * C, bias=b1, K=3, dil=2, pad=2, act=ops.ACT_GATE, addend=cond,
                                emit_planes=True, write_f32=False)
-    ops.conv1d_umma_cl(zp, w2s, C, res=h, out=h, out_div=math.sqrt(2.0), emit_planes=True)
+    ops.conv1d_umma_dual_cl(zp, w2s, C,
+                            dict(bias=b2[:C], res=h, out=h, out_div=math.sqrt(2.0), emit_planes=True, plane_add=b1[:C]),
+                            dict(bias=b2[C:], out=skip, beta=1.0))
 torch.cuda.synchronize()
