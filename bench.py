@@ -280,6 +280,19 @@ def run_native(args, rank, local_rank, world):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps, out, lib.pttspp_launch_count(), clk.summary()
 
+    if args.leg != "both":
+        # profiling aid: exactly `warmup` + `steps` passes of one leg, nothing else launched (ncu -s/-c friendly)
+        if args.leg == "acoustic":
+            ms, out, launches, _ = timed(step_device, args.steps, args.warmup)
+        else:
+            mel_d = cfg3_inputs(seed=3 + rank).to(device)
+            ms, out, launches, _ = timed(lambda: voc(mel_d), args.steps, args.warmup)
+        if rank == 0:
+            print(json.dumps({"leg": args.leg, "ms_per_step": ms, "gpu_launches_per_step": launches // args.steps}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- acoustic leg (headline) ----
     ms_dev, out, launches, clocks = timed(step_device, args.steps, args.warmup)
     flen = out[3]
@@ -357,6 +370,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--leg", default="both", choices=["both", "acoustic", "bigvgan"],
+                    help="profiling aid (ncu launch lists): run only one leg; the default line carries both")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

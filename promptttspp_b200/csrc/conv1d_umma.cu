@@ -40,10 +40,11 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// bounded spin: a protocol bug traps (launch error) instead of hanging the GPU
+// bounded spin: a protocol bug traps (launch error) after ~2 s instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
-  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -52,8 +53,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) return;
+    if ((spin & 0xFFFu) == 0xFFFu) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
   }
-  __trap();
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -121,6 +126,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// tcgen05.ld without the wait: under a running MMA stream every TMEM read round-trip costs microseconds, so the
+// epilogue issues ALL loads of its accumulator slice back to back and waits once (tmem_wait_ld).
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // Output tensor maps of one epilogue descriptor: the accumulator tile leaves through shared memory and TMA bulk
 // stores (whole lines, no LSU involvement) instead of 16-byte-per-row scattered stores.
 struct OutMaps {
@@ -134,8 +150,236 @@ struct UmmaSmem {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
 };
 
+// one lane of a converged warp (the control flow around it stays warp-uniform, so descriptors and barrier addresses
+// live in uniform registers instead of being broadcast lane -> uniform per instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// ---- cluster / CTA-pair (cta_group::2) wrappers ------------------------------------------------------------------
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the pair's even CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster.  Relaxed: the only thing the
+// arrival publishes is "my tcgen05.ld of this accumulator buffer has completed" (tcgen05.wait::ld + fence precede
+// it); a release would make the lane wait for the acknowledgement of all its earlier global stores.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
+// TMA loads of a CTA pair: data lands in the issuing CTA, the transaction bytes are signalled on the LEADER's barrier
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once the MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+
+// ---- coalescing epilogue -------------------------------------------------------------------------------------------
+// The accumulator leaves TMEM row-per-lane (lane = tile row), crosses a 2 KB per-warp staging tile (XOR-swizzled:
+// conflict-free both ways) and is finished in a row-coalesced layout: lane = (row lane/4 of an 8-row group, 16-byte
+// column quad lane%4), so every global access of a warp instruction covers 8 rows x 64 contiguous bytes (full
+// sectors) and nothing waits on the async proxy.  Operand tiles (conditioner / residual / previous output) are
+// requested in the same layout before the accumulator is complete.
+// `de` must be one of the kernel's by-value descriptor parameters, selected by a BRANCH at the call site (not by
+// `cond ? d2 : d`): then every field is an immediate constant-bank operand; a run-time selected reference makes
+// each access an indexed LDC with a long-scoreboard wait (that was most of the old epilogue's time).
+// Precondition (host: epilogue_co_ok): the vector-path alignment rules, and no residual / beta with the gate.
+template <int BN, int NACC, int EW>
+__device__ __forceinline__ void umma_tile_epilogue_co(const pttspp_conv1d_desc& de, int n0, int mt, int b, int i,
+                                                      int warp, int lane, uint32_t tmem_base, uint32_t tfull,
+                                                      int n_main, float* stage, int dbg) {
+  const int q = warp & 3, cgrp = warp >> 2, u = i & 1;
+  const int m0 = de.m_begin + mt * UM_BM;
+  constexpr int CW = BN / (EW / 4);
+  constexpr int NCH = CW / 16;
+  const int cbeg = cgrp * CW;
+  const bool gate = (de.act == PTTSPP_ACT_GATE);
+  const int rsub = lane >> 2, cq = lane & 3;
+  const int kind = conv_epilogue_prefetch_kind(de);
+  const long long omask_len = de.out_len ? (long long)de.out_len[b] : (1ll << 62);
+  // rows of this lane in the coalesced layout
+  int rows[4];
+  bool rok[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int m = m0 + q * 32 + 8 * j + rsub;
+    rows[j] = m * de.out_mul + de.out_off;
+    rok[j] = (m < de.m_begin + de.M) && rows[j] >= 0 && rows[j] < de.T_out;
+  }
+  float4 pre[NCH][4];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = n0 + cbeg + 16 * c + 4 * cq;  // first pre-activation column of this lane
+    const int ocol = gate ? (col >> 1) : col;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      pre[c][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rok[j] && col < de.Cout && !(dbg & 4)) {
+        if (kind == 1)
+          pre[c][j] = *reinterpret_cast<const float4*>(de.addend + (int64_t)b * de.addend_bs + (int64_t)rows[j] * de.addend_ld + col);
+        else if (kind == 2)
+          pre[c][j] = *reinterpret_cast<const float4*>(de.res + (int64_t)b * de.res_bs + (int64_t)rows[j] * de.res_ld + ocol);
+        else if (kind == 3)
+          pre[c][j] = *reinterpret_cast<const float4*>(de.out + (int64_t)b * de.out_bs + (int64_t)rows[j] * de.out_ld + ocol);
+      }
+    }
+  }
+  mbar_wait(tfull, ((uint32_t)i >> 1) & 1u);
+  tc_fence_after();
+  if (dbg & 64) return;  // experiment: mainloop only
+  const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * NACC * BN);
+  float4* st4 = reinterpret_cast<float4*>(stage);
+  const float inv_div = (de.out_div != 0.f) ? 1.f / de.out_div : 1.f;  // <= 1 ulp from the reference's IEEE division
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col0 = cbeg + 16 * c;
+    if (n0 + col0 >= de.Cout) continue;  // warp-uniform
+    float v[16];
+    {
+      // all accumulators of this chunk are requested back to back, one wait
+      uint32_t acc[NACC][16];
+      if (dbg & 32) {  // experiment: no TMEM reads
+#pragma unroll
+        for (int a = 0; a < NACC; ++a)
+#pragma unroll
+          for (int e = 0; e < 16; ++e) acc[a][e] = 0u;
+      } else {
+        tmem_ld16_nowait(tbase + (uint32_t)((NACC - 1) * BN + col0), acc[NACC - 1]);
+#pragma unroll
+        for (int a = 0; a < NACC - 1; ++a)
+          if (a < n_main) tmem_ld16_nowait(tbase + (uint32_t)(a * BN + col0), acc[a]);
+        tmem_wait_ld();
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(acc[NACC - 1][e]);
+#pragma unroll
+      for (int a = 0; a < NACC - 1; ++a)
+        if (a < n_main) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] += __uint_as_float(acc[a][e]);
+        }
+    }
+    __syncwarp();  // the previous chunk's reads of the staging tile are done
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      st4[lane * 4 + (k ^ ((lane >> 1) & 3))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    __syncwarp();
+    const int col = n0 + col0 + 4 * cq;
+    const int ocol = gate ? (col >> 1) : col;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (de.bias) bias4 = __ldg(reinterpret_cast<const float4*>(de.bias + col));
+    float4 padd = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (de.out_hi && de.out_plane_add) {
+      if (gate) {
+        const float2 t2 = __ldg(reinterpret_cast<const float2*>(de.out_plane_add + ocol));
+        padd.x = t2.x; padd.y = t2.y;
+      } else {
+        padd = __ldg(reinterpret_cast<const float4*>(de.out_plane_add + ocol));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = 8 * j + rsub;
+      const float4 a = st4[r * 4 + (cq ^ ((r >> 1) & 3))];
+      if (!rok[j]) continue;
+      const float mask = ((long long)rows[j] < omask_len) ? 1.f : 0.f;
+      float x0 = a.x * de.acc_scale + bias4.x, x1 = a.y * de.acc_scale + bias4.y;
+      float x2 = a.z * de.acc_scale + bias4.z, x3 = a.w * de.acc_scale + bias4.w;
+      if (kind == 1) { x0 += pre[c][j].x; x1 += pre[c][j].y; x2 += pre[c][j].z; x3 += pre[c][j].w; }
+      const float am = de.alpha * mask;
+      if (gate) {
+        float o0 = gate_fast(x0, x1) * am, o1 = gate_fast(x2, x3) * am;
+        o0 *= inv_div; o1 *= inv_div;
+        if (de.out && !(dbg & 8))
+          *reinterpret_cast<float2*>(de.out + (int64_t)b * de.out_bs + (int64_t)rows[j] * de.out_ld + ocol) = make_float2(o0, o1);
+        if (de.out_hi && !(dbg & 8)) {
+          __half h0, l0, h1, l1;
+          split_f16(o0 + padd.x, h0, l0);
+          split_f16(o1 + padd.y, h1, l1);
+          const int64_t pidx = (int64_t)b * de.out_plane_bs + (int64_t)rows[j] * de.out_plane_ld + ocol;
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(de.out_hi) + pidx) =
+              (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(de.out_lo) + pidx) =
+              (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
+      } else {
+        float o0, o1, o2, o3;
+        if (de.act == PTTSPP_ACT_NONE) { o0 = x0; o1 = x1; o2 = x2; o3 = x3; }
+        else if (de.act == PTTSPP_ACT_RELU) { o0 = fmaxf(x0, 0.f); o1 = fmaxf(x1, 0.f); o2 = fmaxf(x2, 0.f); o3 = fmaxf(x3, 0.f); }
+        else { o0 = act_apply(x0, de.act); o1 = act_apply(x1, de.act); o2 = act_apply(x2, de.act); o3 = act_apply(x3, de.act); }
+        o0 *= am; o1 *= am; o2 *= am; o3 *= am;
+        if (de.res) {
+          float4 rv = pre[c][j];
+          if (kind != 2) rv = *reinterpret_cast<const float4*>(de.res + (int64_t)b * de.res_bs + (int64_t)rows[j] * de.res_ld + ocol);
+          o0 += de.res_scale * rv.x; o1 += de.res_scale * rv.y; o2 += de.res_scale * rv.z; o3 += de.res_scale * rv.w;
+        }
+        if (de.out && de.beta != 0.f) {
+          float4 ov = pre[c][j];
+          if (kind != 3) ov = *reinterpret_cast<const float4*>(de.out + (int64_t)b * de.out_bs + (int64_t)rows[j] * de.out_ld + ocol);
+          o0 += de.beta * ov.x; o1 += de.beta * ov.y; o2 += de.beta * ov.z; o3 += de.beta * ov.w;
+        }
+        o0 *= inv_div; o1 *= inv_div; o2 *= inv_div; o3 *= inv_div;
+        if (de.out && !(dbg & 8))
+          *reinterpret_cast<float4*>(de.out + (int64_t)b * de.out_bs + (int64_t)rows[j] * de.out_ld + ocol) = make_float4(o0, o1, o2, o3);
+        if (de.out_hi && !(dbg & 8)) {
+          __half h[4], l[4];
+          split_f16(o0 + padd.x, h[0], l[0]);
+          split_f16(o1 + padd.y, h[1], l[1]);
+          split_f16(o2 + padd.z, h[2], l[2]);
+          split_f16(o3 + padd.w, h[3], l[3]);
+          const int64_t pidx = (int64_t)b * de.out_plane_bs + (int64_t)rows[j] * de.out_plane_ld + ocol;
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(de.out_hi) + pidx) =
+              make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
+                         (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(de.out_lo) + pidx) =
+              make_uint2((uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
+                         (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+        }
+      }
+    }
+  }
 }
 
 // Epilogue of one accumulator tile by one of the 16 epilogue warps (TMEM -> registers -> fused epilogue -> HBM).
@@ -317,8 +561,8 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == UM_EPI_WARPS) {
-    // ================= TMA producer =================
-    if (lane == 0) {
+    // ================= TMA producer (whole warp walks the loop, one elected lane issues) =================
+    {
       uint32_t g = 0;  // ring position, continues across tiles
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int nt = tile % n_nt, mt = (tile / n_nt) % n_mt, b = tile / (n_nt * n_mt);
@@ -329,18 +573,21 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
           mbar_wait(empty_bar(s), ph ^ 1u);
           const int slab = it / d.K, tap = it % d.K;  // taps innermost: the shifted row windows overlap in L2
           const uint32_t st = base + s * SM::STAGE_BYTES;
-          mbar_expect_tx(full_bar(s), SM::STAGE_BYTES);
           const int row = m0 + tap * d.dil - d.pad;
-          tma_load_3d(st, &mapAh, full_bar(s), slab * UM_BK, row, b);
-          tma_load_3d(st + SM::A_BYTES, &mapAl, full_bar(s), slab * UM_BK, row, b);
-          tma_load_2d(st + 2 * SM::A_BYTES, &mapBh, full_bar(s), slab * UM_BK, tap * d.Cout + n0);
-          tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &mapBl, full_bar(s), slab * UM_BK, tap * d.Cout + n0);
+          if (elect_one()) {
+            mbar_expect_tx(full_bar(s), SM::STAGE_BYTES);
+            tma_load_3d(st, &mapAh, full_bar(s), slab * UM_BK, row, b);
+            tma_load_3d(st + SM::A_BYTES, &mapAl, full_bar(s), slab * UM_BK, row, b);
+            tma_load_2d(st + 2 * SM::A_BYTES, &mapBh, full_bar(s), slab * UM_BK, tap * d.Cout + n0);
+            tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &mapBl, full_bar(s), slab * UM_BK, tap * d.Cout + n0);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == UM_EPI_WARPS + 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (warp-uniform loop, one elected lane issues) =================
+    {
       constexpr uint32_t idesc = umma_idesc_f16(UM_BM, BN);
       const uint64_t desc0 = umma_desc_k_sw128(base);
       uint32_t g = 0;
@@ -368,16 +615,19 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
           const uint64_t dBl = dAh + (uint64_t)((2 * SM::A_BYTES + SM::B_BYTES) >> 4);
           const uint32_t acc_main = acc0 + (uint32_t)((it % (NACC - 1)) * BN);
           const uint32_t first_main = (it >= NACC - 1) ? 1u : 0u;
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < UM_BK / 16; ++kk) {
-            const uint64_t adv = (uint64_t)(kk * 2);  // 16 halves = 32 bytes along K inside the swizzle span
-            umma_f16(acc_cross, dAl + adv, dBh + adv, idesc, (kk != 0) ? 1u : (it != 0 ? 1u : 0u));
-            umma_f16(acc_cross, dAh + adv, dBl + adv, idesc, 1u);
-            umma_f16(acc_main, dAh + adv, dBh + adv, idesc, (kk != 0) ? 1u : first_main);
+            for (int kk = 0; kk < UM_BK / 16; ++kk) {
+              const uint64_t adv = (uint64_t)(kk * 2);  // 16 halves = 32 bytes along K inside the swizzle span
+              umma_f16(acc_cross, dAl + adv, dBh + adv, idesc, (kk != 0) ? 1u : (it != 0 ? 1u : 0u));
+              umma_f16(acc_cross, dAh + adv, dBl + adv, idesc, 1u);
+              umma_f16(acc_main, dAh + adv, dBh + adv, idesc, (kk != 0) ? 1u : first_main);
+            }
+            umma_commit(empty_bar(s));  // frees the stage once these MMAs have read it
+            if (it + 1 == n_iter) umma_commit(tfull_bar(u));  // accumulator buffer u complete
           }
-          umma_commit(empty_bar(s));  // frees the stage once these MMAs have read it
+          __syncwarp();
         }
-        umma_commit(tfull_bar(u));  // accumulator buffer u complete
       }
     }
   } else {
@@ -385,16 +635,27 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
     int i = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
       const int nt = tile % n_nt, mt = (tile / n_nt) % n_mt, b = tile / (n_nt * n_mt);
-      umma_tile_epilogue<BN, NACC>(d, d2, cout1, vec_ok, mt, nt, b, i, warp, lane, tmem_base, tfull_bar(i & 1),
-                                   n_iter < NACC - 1 ? n_iter : NACC - 1, &om, &om2, tma_out,
-                                   gen_base + STAGES * SM::STAGE_BYTES + 256 + warp * 2048,
-                                   base + STAGES * SM::STAGE_BYTES + 256 + warp * 2048);
+      if (tma_out & 4) {
+        float* stg = reinterpret_cast<float*>(gen_base + STAGES * SM::STAGE_BYTES + 256 + warp * 2048);
+        const int nm = n_iter < NACC - 1 ? n_iter : NACC - 1;
+        if (nt * BN >= cout1)  // CTA-uniform branch: each side reads its descriptor with immediate constant operands
+          umma_tile_epilogue_co<BN, NACC, UM_EPI_WARPS>(d2, nt * BN - cout1, mt, b, i, warp, lane, tmem_base,
+                                                        tfull_bar(i & 1), nm, stg, 0);
+        else
+          umma_tile_epilogue_co<BN, NACC, UM_EPI_WARPS>(d, nt * BN, mt, b, i, warp, lane, tmem_base, tfull_bar(i & 1),
+                                                        nm, stg, 0);
+      }
+      else
+        umma_tile_epilogue<BN, NACC>(d, d2, cout1, vec_ok, mt, nt, b, i, warp, lane, tmem_base, tfull_bar(i & 1),
+                                     n_iter < NACC - 1 ? n_iter : NACC - 1, &om, &om2, tma_out,
+                                     gen_base + STAGES * SM::STAGE_BYTES + 256 + warp * 2048,
+                                     base + STAGES * SM::STAGE_BYTES + 256 + warp * 2048);
       const int u = i & 1;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(u));
     }
-    if (tma_out && lane == 0) bulk_wait0();  // all bulk stores of this warp have been written
+    if ((tma_out & 3) && lane == 0) bulk_wait0();  // all bulk stores of this warp have been written
   }
   tc_fence_before();
   __syncthreads();
@@ -560,6 +821,258 @@ conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_co
   }
 }
 
+
+// ---- CTA-pair (cta_group::2), A-stationary kernel ------------------------------------------------------------------
+// The streaming kernel above is bound by the L2 -> SM fill rate (ncu: 11.3 TB/s = the LTS cap, tensor pipe 45 %):
+// every (tap, N tile) re-loads its activation slab and every CTA loads the whole weight tile.  Here two CTAs of one
+// TPC form a pair: one tcgen05.mma.cta_group::2 computes 256 rows x 128 columns, each CTA supplying ITS 128
+// activation rows and HALF (64 rows) of the weight tile -- weight traffic per SM is halved.  The activation block of
+// a 256-row unit (all Cin slabs, 128 + halo rows per CTA) is loaded ONCE per unit and all N tiles / taps walk over
+// it (taps share the halo tile by advancing the descriptor start by tap*dil rows); only the 16 KB weight half-tiles
+// stream through a ring.  Per-slab full/empty barriers let the next unit's block stream in while the last tile of
+// the current unit still computes.  Tiles (unit, N tile) are dealt to the clusters in contiguous chunks, so the
+// machine is filled to 1/tiles granularity instead of 1/units.
+// Barrier ownership: "full" barriers live in the leader (even) CTA and receive the TMA bytes of both CTAs;
+// "empty"/"tfull" barriers exist in both CTAs and are signalled by multicast tcgen05.commit; the leader's "tempty"
+// collects the epilogue warps of both CTAs (remote arrive).
+constexpr int UP_BN = 128;
+constexpr int UP_BHALF = UP_BN / 2;
+constexpr int UP_BST_BYTES = 2 * UP_BHALF * 128;  // hi + lo half-tiles of one stage
+constexpr int UP_MAX_SLAB = 8;
+
+// EW epilogue warps (4 TMEM lane quarters x EW/4 column groups): 16 drain a tile fastest, 8 leave shared memory for
+// one more weight stage.
+template <int NBST, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((EW + 2) * 32, 1)
+conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                        const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
+                        const pttspp_conv1d_desc d, const pttspp_conv1d_desc d2, const int cout1, const int cout_total,
+                        const int n_mt2, const int n_nt, const int n_tiles, const int rowsA, const int mma_order) {
+  constexpr uint32_t TMEM_COLS = 2 * UM_NACC * UP_BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const int nslab = d.Cin / UM_BK;
+  const uint32_t a_plane = (uint32_t)rowsA * 128u;
+  const uint32_t a_bytes = (uint32_t)nslab * 2u * a_plane;
+  const uint32_t ring = base + a_bytes;
+  const uint32_t stg_off = a_bytes + (uint32_t)NBST * UP_BST_BYTES;  // epilogue staging, 2 KB per warp
+  const uint32_t bars_off = stg_off + EW * 2048;
+  const uint32_t bars = base + bars_off;
+  // fullA[8], emptyA[8], fullB[NBST], emptyB[NBST], tfull[2], tempty[2]
+  constexpr int NBARS = 2 * UP_MAX_SLAB + 2 * NBST + 4;
+  auto fullA = [&](int sl) { return bars + sl * 8; };
+  auto emptyA = [&](int sl) { return bars + (UP_MAX_SLAB + sl) * 8; };
+  auto fullB = [&](int st) { return bars + (2 * UP_MAX_SLAB + st) * 8; };
+  auto emptyB = [&](int st) { return bars + (2 * UP_MAX_SLAB + NBST + st) * 8; };
+  auto tfull_bar = [&](int u) { return bars + (2 * UP_MAX_SLAB + 2 * NBST + u) * 8; };
+  auto tempty_bar = [&](int u) { return bars + (2 * UP_MAX_SLAB + 2 * NBST + 2 + u) * 8; };
+  const uint32_t tmem_slot = bars + NBARS * 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + bars_off + NBARS * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int t_begin = (int)((long long)cluster_id * n_tiles / n_clusters);
+  const int t_end = (int)((long long)(cluster_id + 1) * n_tiles / n_clusters);
+
+  if (threadIdx.x == 0) {
+    for (int sl = 0; sl < UP_MAX_SLAB; ++sl) {
+      mbar_init(fullA(sl), 1);
+      mbar_init(emptyA(sl), 1);
+    }
+    for (int st = 0; st < NBST; ++st) {
+      mbar_init(fullB(st), 1);
+      mbar_init(emptyB(st), 1);
+    }
+    for (int u = 0; u < 2; ++u) {
+      mbar_init(tfull_bar(u), 1);
+      mbar_init(tempty_bar(u), 2 * EW);  // epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == EW && lane == 0) {
+    tma_prefetch_desc(&mapAh);
+    tma_prefetch_desc(&mapAl);
+    tma_prefetch_desc(&mapBh);
+    tma_prefetch_desc(&mapBl);
+  }
+  if (warp == EW + 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits and the TMEM allocation of both CTAs are visible pair-wide
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == EW) {
+    // ================= TMA producer (both CTAs: own activation rows, own half of every weight tile) =================
+    // the whole warp walks the loop (warp-uniform control flow), one elected lane issues
+    {
+      uint32_t g = 0;
+      int ablk = 0, cur_unit = -1;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int unit = t / n_nt, nt = t - unit * n_nt;
+        const bool new_unit = unit != cur_unit;
+        cur_unit = unit;
+        const int b = unit / n_mt2, mt2 = unit - b * n_mt2;
+        const int row0 = d.m_begin + mt2 * (2 * UM_BM) + (int)rank * UM_BM - d.pad;
+        if (mma_order & 16) {  // experiment (measured harmful: the bulk prefetches queue in front of the TMA loads)
+          // The producer runs one to two tiles ahead of the epilogue: pull the epilogue's operand tile (conditioner /
+          // residual / previous output, 128 rows x 512 B) into L2 now, so that the epilogue's loads are L2 hits.
+          const bool second = nt * UP_BN >= cout1;
+          const pttspp_conv1d_desc& de = second ? d2 : d;
+          const int n0 = second ? nt * UP_BN - cout1 : nt * UP_BN;
+          const int kind = conv_epilogue_prefetch_kind(de);
+          if (kind != 0 && n0 + UP_BN <= de.Cout) {
+            const bool gate = (de.act == PTTSPP_ACT_GATE);
+            const float* src = (kind == 1) ? de.addend : (kind == 2 ? de.res : de.out);
+            const int64_t bs = (kind == 1) ? de.addend_bs : (kind == 2 ? de.res_bs : de.out_bs);
+            const int ld = (kind == 1) ? de.addend_ld : (kind == 2 ? de.res_ld : de.out_ld);
+            const int c0 = (kind == 1 || !gate) ? n0 : (n0 >> 1);
+            const uint32_t bytes = (kind == 1 || !gate) ? UP_BN * 4 : UP_BN * 2;
+#pragma unroll
+            for (int rr = 0; rr < UM_BM / 32; ++rr) {
+              const int m = d.m_begin + mt2 * (2 * UM_BM) + (int)rank * UM_BM + rr * 32 + lane;
+              const int row = m * de.out_mul + de.out_off;
+              if (m < de.m_begin + de.M && row >= 0 && row < de.T_out)
+                l2_prefetch_bulk(src + (int64_t)b * bs + (int64_t)row * ld + c0, bytes);
+            }
+          }
+          __syncwarp();
+        }
+        for (int slab = 0; slab < nslab; ++slab) {
+          if (new_unit) {
+            // this slab of the previous unit has been consumed (released early in that unit's last tile)
+            mbar_wait(emptyA(slab), ((uint32_t)ablk & 1u) ^ 1u);
+            if (elect_one()) {
+              if (rank == 0) mbar_expect_tx(fullA(slab), 4u * a_plane);
+              tma_load_3d_pair(base + (uint32_t)(2 * slab) * a_plane, &mapAh, fullA(slab), slab * UM_BK, row0, b);
+              tma_load_3d_pair(base + (uint32_t)(2 * slab + 1) * a_plane, &mapAl, fullA(slab), slab * UM_BK, row0, b);
+            }
+            __syncwarp();
+          }
+          for (int tap = 0; tap < d.K; ++tap, ++g) {
+            const int st = g % NBST;
+            const uint32_t ph = (g / NBST) & 1u;
+            mbar_wait(emptyB(st), ph ^ 1u);
+            const uint32_t dst = ring + (uint32_t)st * UP_BST_BYTES;
+            const int wrow = tap * cout_total + nt * UP_BN + (int)rank * UP_BHALF;
+            if (elect_one()) {
+              if (rank == 0) mbar_expect_tx(fullB(st), 2u * UP_BST_BYTES);
+              tma_load_2d_pair(dst, &mapBh, fullB(st), slab * UM_BK, wrow);
+              tma_load_2d_pair(dst + UP_BHALF * 128, &mapBl, fullB(st), slab * UM_BK, wrow);
+            }
+            __syncwarp();
+          }
+        }
+        if (new_unit) ++ablk;
+      }
+    }
+  } else if (warp == EW + 1) {
+    // ================= MMA issuer (leader CTA only; warp-uniform loop, one elected lane issues) =================
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(2 * UM_BM, UP_BN);
+      const uint64_t desc0 = umma_desc_k_sw128(base);  // descriptors differ only in the start-address field
+      uint32_t g = 0;
+      int i = 0, ablk = 0, cur_unit = -1;
+      for (int t = t_begin; t < t_end; ++t, ++i) {
+        const int unit = t / n_nt;
+        const bool new_unit = unit != cur_unit;
+        cur_unit = unit;
+        const bool last_of_unit = (t + 1 == t_end) || ((t + 1) / n_nt != unit);
+        const int u = i & 1;
+        mbar_wait(tempty_bar(u), (((uint32_t)i >> 1) & 1u) ^ 1u);  // both CTAs' epilogues have drained buffer u
+        tc_fence_after();
+        const uint32_t acc_main = tmem_base + (uint32_t)(u * UM_NACC * UP_BN);
+        const uint32_t acc_cross = acc_main + (uint32_t)UP_BN;
+        uint32_t first = 0;
+        for (int slab = 0; slab < nslab; ++slab) {
+          if (new_unit) {
+            mbar_wait(fullA(slab), (uint32_t)ablk & 1u);
+            tc_fence_after();
+          }
+          for (int tap = 0; tap < d.K; ++tap, ++g) {
+            const int st = g % NBST;
+            const uint32_t ph = (g / NBST) & 1u;
+            mbar_wait(fullB(st), ph);
+            tc_fence_after();
+            const uint32_t a_off = (uint32_t)(2 * slab) * a_plane + (uint32_t)(tap * d.dil) * 128u;  // taps share the halo tile
+            const uint64_t dAh = desc0 + (uint64_t)(a_off >> 4);
+            const uint64_t dAl = dAh + (uint64_t)(a_plane >> 4);
+            const uint64_t dBh = desc0 + (uint64_t)((a_bytes + (uint32_t)st * UP_BST_BYTES) >> 4);
+            const uint64_t dBl = dBh + (uint64_t)((UP_BHALF * 128) >> 4);
+            const bool release_a = last_of_unit && (tap + 1 == d.K);
+            const bool tile_done = (slab + 1 == nslab) && (tap + 1 == d.K);
+            if (elect_one()) {
+              if ((mma_order & 3) == 0) {
+#pragma unroll
+                for (int kk = 0; kk < UM_BK / 16; ++kk) {
+                  const uint64_t adv = (uint64_t)(kk * 2);
+                  umma_f16_pair(acc_cross, dAl + adv, dBh + adv, idesc, kk ? 1u : first);
+                  umma_f16_pair(acc_cross, dAh + adv, dBl + adv, idesc, 1u);
+                  umma_f16_pair(acc_main, dAh + adv, dBh + adv, idesc, kk ? 1u : first);
+                }
+              } else if ((mma_order & 3) == 1) {
+                // grouped by accumulator: the destination changes twice per stage instead of after every MMA
+#pragma unroll
+                for (int kk = 0; kk < UM_BK / 16; ++kk)
+                  umma_f16_pair(acc_cross, dAl + (uint64_t)(kk * 2), dBh + (uint64_t)(kk * 2), idesc, kk ? 1u : first);
+#pragma unroll
+                for (int kk = 0; kk < UM_BK / 16; ++kk)
+                  umma_f16_pair(acc_cross, dAh + (uint64_t)(kk * 2), dBl + (uint64_t)(kk * 2), idesc, 1u);
+#pragma unroll
+                for (int kk = 0; kk < UM_BK / 16; ++kk)
+                  umma_f16_pair(acc_main, dAh + (uint64_t)(kk * 2), dBh + (uint64_t)(kk * 2), idesc, kk ? 1u : first);
+              } else {
+                // timing experiment only (wrong numerics budget): one accumulator, one MMA per product
+#pragma unroll
+                for (int kk = 0; kk < UM_BK / 16; ++kk)
+                  umma_f16_pair(acc_main, dAh + (uint64_t)(kk * 2), dBh + (uint64_t)(kk * 2), idesc, kk ? 1u : first);
+                if (first == 0) umma_f16_pair(acc_cross, dAl, dBh, idesc, 0u);
+              }
+              umma_commit_pair(emptyB(st));
+              if (release_a) umma_commit_pair(emptyA(slab));  // this slab may be overwritten by the next unit
+              if (tile_done) umma_commit_pair(tfull_bar(u));
+            }
+            __syncwarp();
+            first = 1u;
+          }
+        }
+        if (new_unit) ++ablk;
+      }
+    }
+  } else {
+    // ================= epilogue: warps 0-15 of both CTAs, each CTA drains its own 128 TMEM lanes =================
+    int i = 0;
+    float* stage = reinterpret_cast<float*>(gen_base + stg_off + warp * 2048);
+    for (int t = t_begin; t < t_end; ++t, ++i) {
+      const int unit = t / n_nt, nt = t - unit * n_nt;
+      const int b = unit / n_mt2, mt2 = unit - b * n_mt2;
+      if (nt * UP_BN >= cout1)  // CTA-uniform branch, see umma_tile_epilogue_co
+        umma_tile_epilogue_co<UP_BN, UM_NACC, EW>(d2, nt * UP_BN - cout1, 2 * mt2 + (int)rank, b, i, warp, lane, tmem_base,
+                                                  tfull_bar(i & 1), 1, stage, mma_order);
+      else
+        umma_tile_epilogue_co<UP_BN, UM_NACC, EW>(d, nt * UP_BN, 2 * mt2 + (int)rank, b, i, warp, lane, tmem_base,
+                                                  tfull_bar(i & 1), 1, stage, mma_order);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(tempty_bar(i & 1));
+        else mbar_arrive_cluster(tempty_bar(i & 1), 0);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still signal it
+  if (warp == EW + 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---- probe: UMMA shared-memory descriptors whose start row is not a multiple of 8 --------------------------------
 // D[128][128] = A[row_off : row_off + 128][0:64] . B[0:128][0:64]^T with the A tile loaded ONCE (144 rows) and the
 // descriptor start advanced by row_off * 128 bytes.  mode 0: base_offset field 0; mode 1: base_offset =
@@ -681,6 +1194,143 @@ OutMaps make_out_maps(const pttspp_conv1d_desc& d) {
   return om;
 }
 
+
+// coalescing epilogue preconditions: the vector-path alignment rules; the gate activation only without residual / beta
+bool epilogue_co_ok(const pttspp_conv1d_desc& d) {
+  if (!conv_epilogue_vec_ok(d)) return false;
+  if (d.act == PTTSPP_ACT_GATE && (d.res || (d.out && d.beta != 0.f))) return false;
+  return true;
+}
+
+// A 1x1 contraction over densely packed [B][T] rows is one [B*T]-row problem: no halo, no per-utterance tile tails.
+bool flatten_batch_ok(const pttspp_conv1d_desc& d) {
+  if (d.K != 1 || d.pad != 0 || d.m_begin != 0 || d.M != d.T_out || d.M != d.T_in || d.out_mul != 1 || d.out_off != 0)
+    return false;
+  if (d.out_len || d.in_len) return false;
+  if (d.in_bs != (int64_t)d.T_in * d.in_ld) return false;
+  if (d.out && d.out_bs != (int64_t)d.T_out * d.out_ld) return false;
+  if (d.res && d.res_bs != (int64_t)d.T_out * d.res_ld) return false;
+  if (d.addend && d.addend_bs != (int64_t)d.T_out * d.addend_ld) return false;
+  if (d.out_hi && d.out_plane_bs != (int64_t)d.T_out * d.out_plane_ld) return false;
+  return (int64_t)d.B * d.T_in < (1ll << 30);
+}
+void flatten_batch(pttspp_conv1d_desc& d) {
+  const int rows = d.B * d.T_in;
+  d.T_in = d.T_out = d.M = rows;
+  d.B = 1;
+}
+
+int pair_clusters(const void* kern, size_t smem, int threads) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  return n;
+}
+
+// one-time setup per kernel instantiation: opt in to 227 KB of dynamic shared memory, query resident clusters
+template <int NBST, int EW>
+int pair_kernel_setup(int num_sms, bool debug) {
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    auto kern = conv1d_umma_pair_kernel<NBST, EW>;
+    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int n = pair_clusters((const void*)kern, 227 * 1024, (EW + 2) * 32);
+    if (debug) fprintf(stderr, "[pttspp] pair kernel<%d>: cudaOccupancyMaxActiveClusters -> %d\n", NBST, n);
+    max_clusters = (n > 0) ? std::min(n, num_sms / 2) : num_sms / 2;
+  }
+  return max_clusters;
+}
+
+// Pair kernel launch; returns false when the shape does not qualify (caller falls back to the streaming kernel).
+bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool dual, int cout1, int total_cout,
+                             cudaStream_t s, int num_sms) {
+  const char* env = getenv("PTTSPP_UMMA_PAIR");
+  if (env && env[0] == '0') return false;
+  if (!epilogue_co_ok(d) || (dual && !epilogue_co_ok(d2))) return false;
+  if (total_cout % UP_BN != 0 || d.Cin % UM_BK != 0 || d.Cin / UM_BK > UP_MAX_SLAB) return false;
+  if (d.K * d.Cin / 16 > 64) return false;  // long contractions keep the multi-accumulator streaming kernel
+  if (flatten_batch_ok(d) && (!dual || flatten_batch_ok(d2))) {
+    flatten_batch(d);
+    if (dual) flatten_batch(d2);
+  }
+  const int nslab = d.Cin / UM_BK;
+  const int rowsA = UM_BM + round_up((d.K - 1) * d.dil, 8);
+  if (rowsA > 256) return false;
+  const size_t a_bytes = (size_t)nslab * 2 * rowsA * 128;
+  const char* ewe = getenv("PTTSPP_UMMA_EW");
+  const int ew = (ewe && atoi(ewe) == 8) ? 8 : 16;
+  const size_t fixed = a_bytes + (size_t)ew * 2048 + (2 * UP_MAX_SLAB + 2 * 6 + 4) * 8 + 16 + 1024;
+  const size_t cap = 227 * 1024;
+  if (fixed + 3 * UP_BST_BYTES > cap) return false;
+  const int nbst = (int)std::min<size_t>(6, (cap - fixed) / UP_BST_BYTES);
+  const int n_mt2 = ceil_div(d.M, 2 * UM_BM), n_nt = total_cout / UP_BN;
+  const long long n_tiles = (long long)n_mt2 * d.B * n_nt;
+  if (n_tiles >= (1ll << 30)) return false;
+  // worth it only when every pair gets at least a couple of tiles (the activation block is loaded per unit)
+  if (!(env && env[0] == '2') && n_tiles < num_sms) return false;
+
+  const uint64_t wdims[2] = {(uint64_t)d.Cin, (uint64_t)d.K * total_cout};
+  const uint64_t wstr[1] = {(uint64_t)d.Cin * 2};
+  const uint32_t wbox[2] = {UM_BK, UP_BHALF};
+  const CUtensorMap mBh = make_map(d.w_hi, 2, wdims, wstr, wbox);
+  const CUtensorMap mBl = make_map(d.w_lo, 2, wdims, wstr, wbox);
+  const uint64_t adims[3] = {(uint64_t)d.Cin, (uint64_t)d.T_in, (uint64_t)d.B};
+  const uint64_t astr[2] = {(uint64_t)d.in_ld * 2, (uint64_t)d.in_bs * 2};
+  const uint32_t abox[3] = {UM_BK, (uint32_t)rowsA, 1};
+  const CUtensorMap mAh = make_map(d.in_hi, 3, adims, astr, abox);
+  const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox);
+  const size_t smem = fixed + (size_t)nbst * UP_BST_BYTES;
+
+  const bool debug = getenv("PTTSPP_UMMA_DEBUG") != nullptr;
+  auto launch = [&](auto kern, int max_clusters) {
+    const int n_clusters = (int)std::min<long long>(n_tiles, std::min(max_clusters, num_sms / 2));
+    int cout_first = dual ? cout1 : total_cout, cout_all = total_cout, a_n_mt2 = n_mt2, a_n_nt = n_nt, a_tiles = (int)n_tiles,
+        a_rowsA = rowsA;
+    const char* oe = getenv("PTTSPP_UMMA_ORDER");  // experiments: bits 0-1 MMA order, 4 no operand loads, 8 no stores, 16 no L2 prefetch
+    int a_order = oe ? atoi(oe) : 0;
+    void* args[] = {(void*)&mAh, (void*)&mAl, (void*)&mBh, (void*)&mBl, (void*)&d, (void*)&d2, &cout_first, &cout_all,
+                    &a_n_mt2, &a_n_nt, &a_tiles, &a_rowsA, &a_order};
+    if (debug)
+      fprintf(stderr, "[pttspp] pair launch: clusters %d tiles %lld (units %d x nt %d) rowsA %d nbst %d smem %zu\n",
+              n_clusters, n_tiles, n_mt2 * d.B, n_nt, rowsA, nbst, smem);
+    cudaGetLastError();  // a stale error of an earlier call must not be attributed to this launch
+    PT_CUDA(cudaLaunchKernel((const void*)kern, dim3(2 * n_clusters), dim3((ew + 2) * 32), args, smem, s));
+    ++g_launch_count;
+  };
+#define PT_PAIR_CASE(N, E) launch(conv1d_umma_pair_kernel<N, E>, pair_kernel_setup<N, E>(num_sms, debug))
+  if (ew == 8) {
+    switch (nbst) {
+      case 3: PT_PAIR_CASE(3, 8); break;
+      case 4: PT_PAIR_CASE(4, 8); break;
+      case 5: PT_PAIR_CASE(5, 8); break;
+      default: PT_PAIR_CASE(6, 8); break;
+    }
+  } else {
+    switch (nbst) {
+      case 3: PT_PAIR_CASE(3, 16); break;
+      case 4: PT_PAIR_CASE(4, 16); break;
+      case 5: PT_PAIR_CASE(5, 16); break;
+      default: PT_PAIR_CASE(6, 16); break;
+    }
+  }
+#undef PT_PAIR_CASE
+  return true;
+}
+
 }  // namespace
 
 bool conv1d_umma_supported(const pttspp_conv1d_desc& d) {
@@ -718,6 +1368,7 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
   }
   const int total_cout = d.Cout;
   if (d2_in) d.Cout = cout1;  // the epilogue of the first half sees its own column count again
+  if (conv1d_umma_pair_launch(d, d2, d2_in != nullptr, cout1, total_cout, s, num_sms)) return;
   const int n_mt = ceil_div(d.M, UM_BM), n_nt = ceil_div(total_cout, UM_BN);
   const int nslab = d.Cin / UM_BK;
   // weight planes [K*Cout][Cin]
@@ -768,11 +1419,18 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
   OutMaps om, om2;
   memset(&om, 0, sizeof(om));
   memset(&om2, 0, sizeof(om2));
-  if (vec && tma_out_ok(e1)) {
+  // streaming kernel: the TMA bulk-store epilogue measured ~7 % faster than the coalescing one on the BigVGAN shapes
+  // (tools/bench_conv.py); PTTSPP_UMMA_EPI=co selects the latter
+  const char* epi_env = getenv("PTTSPP_UMMA_EPI");
+  const bool want_co = epi_env && epi_env[0] == 'c';
+  const bool tma_possible = vec && tma_out_ok(e1) && (!d2_in || tma_out_ok(e2));
+  if ((want_co || !tma_possible) && epilogue_co_ok(e1) && (!d2_in || epilogue_co_ok(e2))) {
+    tma_out = 4;  // coalescing epilogue
+  } else if (vec && tma_out_ok(e1)) {
     om = make_out_maps(e1);
     tma_out |= 1;
   }
-  if (d2_in && vec && tma_out_ok(e2)) {
+  if (!(tma_out & 4) && d2_in && vec && tma_out_ok(e2)) {
     om2 = make_out_maps(e2);
     tma_out |= 2;
   }

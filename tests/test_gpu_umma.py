@@ -61,14 +61,27 @@ UMMA_CASES = [
 ]
 
 
-@pytest.mark.parametrize("a_stationary", [False, True])
+VARIANTS = {
+    # env of the kernel selection in conv1d_umma_launch
+    "stream": {"PTTSPP_UMMA_PAIR": "0", "PTTSPP_UMMA_EPI": "co"},      # streaming kernel, coalescing epilogue
+    "stream_tma": {"PTTSPP_UMMA_PAIR": "0"},                           # ... TMA bulk-store epilogue (its default)
+    "astat": {"PTTSPP_UMMA_PAIR": "0", "PTTSPP_UMMA_AS": "1"},         # single-CTA A-stationary (opt-in)
+    "pair": {"PTTSPP_UMMA_PAIR": "2"},                                 # CTA-pair kernel forced wherever it applies
+}
+
+
+def _select(monkeypatch, variant):
+    for k in ("PTTSPP_UMMA_PAIR", "PTTSPP_UMMA_EPI", "PTTSPP_UMMA_AS"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in VARIANTS[variant].items():
+        monkeypatch.setenv(k, v)
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
 @pytest.mark.parametrize("Cin,Cout,K,dil,B,T", UMMA_CASES)
-def test_conv1d_umma_plain(ops, monkeypatch, Cin, Cout, K, dil, B, T, a_stationary):
-    # both tcgen05 kernels: streaming (default) and A-stationary with taps sharing one halo tile (opt-in)
-    if a_stationary:
-        monkeypatch.setenv("PTTSPP_UMMA_AS", "1")
-    else:
-        monkeypatch.delenv("PTTSPP_UMMA_AS", raising=False)
+def test_conv1d_umma_plain(ops, monkeypatch, Cin, Cout, K, dil, B, T, variant):
+    # every tcgen05 kernel variant: streaming, A-stationary with taps sharing one halo tile, cta_group::2 pair
+    _select(monkeypatch, variant)
     g = torch.Generator().manual_seed(Cin + Cout * 3 + K)
     x = torch.randn(B, Cin, T, generator=g)
     w = torch.randn(Cout, Cin, K, generator=g) / math.sqrt(Cin * K)
@@ -84,8 +97,10 @@ def test_conv1d_umma_plain(ops, monkeypatch, Cin, Cout, K, dil, B, T, a_stationa
     assert err < 1e-5 + 6e-9 * K * Cin, err
 
 
-def test_conv1d_umma_diffnet_chain(ops):
+@pytest.mark.parametrize("variant", ["stream", "stream_tma", "pair"])
+def test_conv1d_umma_diffnet_chain(ops, monkeypatch, variant):
     """gate conv -> planes -> 1x1 residual/skip convs, the two tcgen05 launches of a DiffNet layer."""
+    _select(monkeypatch, variant)
     g = torch.Generator().manual_seed(6)
     B, C, T, dil = 2, 256, 333, 4
     x = torch.randn(B, C, T, generator=g)
@@ -125,8 +140,10 @@ def test_conv1d_umma_diffnet_chain(ops):
     assert float((_bct(sbuf) - skip_ref).abs().max()) < 2e-5
 
 
-def test_conv1d_umma_dual_epilogue(ops):
+@pytest.mark.parametrize("variant", ["stream", "stream_tma", "pair"])
+def test_conv1d_umma_dual_epilogue(ops, monkeypatch, variant):
     """residual | skip halves of the DiffNet output projection in ONE launch."""
+    _select(monkeypatch, variant)
     g = torch.Generator().manual_seed(12)
     B, C, T = 4, 256, 2600
     z = torch.rand(B, C, T, generator=g) * 2 - 1

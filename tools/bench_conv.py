@@ -1,5 +1,6 @@
 """Micro-benchmark of the conv kernels on DiffNet / BigVGAN shapes (CUDA-event timing, algorithmic TFLOP/s)."""
 import math
+import os
 import sys
 from pathlib import Path
 
@@ -25,7 +26,7 @@ def timeit(fn, iters=20, warm=3):
 
 
 def main():
-    B, T, C = 16, 2048, 256
+    B, T, C = 16, 2582, 256  # cfg2: 41 312 padded frames
     g = torch.Generator().manual_seed(0)
     x = torch.randn(B, T, C, generator=g).cuda()
     planes = ops.split_f16(x)
@@ -45,19 +46,33 @@ def main():
     fl2 = 2.0 * B * T * C * C
     rows = []
 
-    import os
+    def pv(order=None, ew=None):
+        e = {"PTTSPP_UMMA_PAIR": "2"}
+        if order is not None:
+            e["PTTSPP_UMMA_ORDER"] = str(order)
+        if ew is not None:
+            e["PTTSPP_UMMA_EW"] = str(ew)
+        return e
+
+    # experiment bits: 2 one MMA per product, 4 no operand loads, 8 no stores, 32 no TMEM reads, 64 no epilogue
+    VARIANTS = (("str", {"PTTSPP_UMMA_PAIR": "0", "PTTSPP_UMMA_EPI": "co"}), ("tma", {"PTTSPP_UMMA_PAIR": "0"}),
+                ("pair", pv()), ("p-1mma", pv(2)), ("p-noLS", pv(12)), ("p-noTM", pv(32)), ("p-noLSTM", pv(44)),
+                ("p-noEpi", pv(64)), ("p-noEpi1", pv(66)), ("p8", pv(None, 8)), ("p8noLSTM", pv(44, 8)))
+    KEYS = ("PTTSPP_UMMA_PAIR", "PTTSPP_UMMA_EPI", "PTTSPP_UMMA_AS", "PTTSPP_UMMA_ORDER", "PTTSPP_UMMA_EW")
+    if os.environ.get("BENCH_QUICK"):
+        VARIANTS = VARIANTS[0:1] + VARIANTS[2:]
 
     def add(name, fl, fn):
-        modes = (("str", None), ("AS ", "1")) if name.startswith("umma") else (("   ", None),)
+        modes = VARIANTS if name.startswith("umma") else (("    ", {}),)
         for tag, env in modes:
-            if env is None:
-                os.environ.pop("PTTSPP_UMMA_AS", None)
-            else:
-                os.environ["PTTSPP_UMMA_AS"] = env
+            for k in KEYS:
+                os.environ.pop(k, None)
+            os.environ.update(env)
             ms = timeit(fn)
             rows.append((name, ms, fl / ms / 1e9))
-            print(f"{tag} {name:58s} {ms*1e3:9.1f} us   {fl / ms / 1e9:8.1f} TFLOP/s (algorithmic)", flush=True)
-        os.environ.pop("PTTSPP_UMMA_AS", None)
+            print(f"{tag:8s} {name:58s} {ms*1e3:9.1f} us   {fl / ms / 1e9:8.1f} TFLOP/s (algorithmic)", flush=True)
+        for k in KEYS:
+            os.environ.pop(k, None)
 
     for dil in (1, 8):
         add(f"umma dilated k3 d{dil} 256->512 plain fp32 out", fl1,
@@ -77,6 +92,8 @@ def main():
                                         dict(bias=b2f[:C], res=h, out=h, out_div=math.sqrt(2.0), emit_planes=True,
                                              plane_add=b2),
                                         dict(bias=b2f[C:], out=skip, beta=1.0)))
+    if os.environ.get("BENCH_QUICK"):
+        return
     add("simt dilated k3 d1 256->512 gate+addend", fl1,
         lambda: ops.conv1d_cl(x, w1p, 2 * C, bias=b1, K=3, dil=1, pad=1, act=ops.ACT_GATE, addend=cond, in_add=b2, impl=1))
     add("simt 1x1 256->256 residual", fl2, lambda: ops.conv1d_cl(x, w2p, C, bias=b2, res=h, out=h, out_div=1.41421, impl=1))
