@@ -216,6 +216,15 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       : "memory");
 }
 
+// split two fp32 values into packed (hi, hi) and (lo, lo) half pairs: 2 F2FP + 2 conversions back + 2 FADD
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // ---- coalescing epilogue -------------------------------------------------------------------------------------------
 // The accumulator leaves TMEM row-per-lane (lane = tile row), crosses a 2 KB per-warp staging tile (XOR-swizzled:
 // conflict-free both ways) and is finished in a row-coalesced layout: lane = (row lane/4 of an 8-row group, 16-byte
@@ -227,10 +236,10 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 // each access an indexed LDC with a long-scoreboard wait (that was most of the old epilogue's time).
 // Precondition (host: epilogue_co_ok): the vector-path alignment rules, and no residual / beta with the gate.
 template <int BN, int NACC, int EW>
-__device__ __forceinline__ void umma_tile_epilogue_co(const pttspp_conv1d_desc& de, int n0, int mt, int b, int i,
+__device__ __forceinline__ void umma_tile_epilogue_co(const pttspp_conv1d_desc& de, int n0, int mt, int b, int u, uint32_t tparity,
                                                       int warp, int lane, uint32_t tmem_base, uint32_t tfull,
                                                       int n_main, float* stage, int dbg) {
-  const int q = warp & 3, cgrp = warp >> 2, u = i & 1;
+  const int q = warp & 3, cgrp = warp >> 2;
   const int m0 = de.m_begin + mt * UM_BM;
   constexpr int CW = BN / (EW / 4);
   constexpr int NCH = CW / 16;
@@ -266,7 +275,27 @@ __device__ __forceinline__ void umma_tile_epilogue_co(const pttspp_conv1d_desc& 
       }
     }
   }
-  mbar_wait(tfull, ((uint32_t)i >> 1) & 1u);
+  // per-column operands of this lane (same columns for all its rows), requested before the accumulator is complete
+  float4 bias_c[NCH], padd_c[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = n0 + cbeg + 16 * c + 4 * cq;
+    const int ocol = gate ? (col >> 1) : col;
+    bias_c[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    padd_c[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < de.Cout) {
+      if (de.bias) bias_c[c] = __ldg(reinterpret_cast<const float4*>(de.bias + col));
+      if (de.out_hi && de.out_plane_add) {
+        if (gate) {
+          const float2 t2 = __ldg(reinterpret_cast<const float2*>(de.out_plane_add + ocol));
+          padd_c[c].x = t2.x; padd_c[c].y = t2.y;
+        } else {
+          padd_c[c] = __ldg(reinterpret_cast<const float4*>(de.out_plane_add + ocol));
+        }
+      }
+    }
+  }
+  mbar_wait(tfull, tparity);
   tc_fence_after();
   if (dbg & 64) return;  // experiment: mainloop only
   const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * NACC * BN);
@@ -308,17 +337,7 @@ __device__ __forceinline__ void umma_tile_epilogue_co(const pttspp_conv1d_desc& 
     __syncwarp();
     const int col = n0 + col0 + 4 * cq;
     const int ocol = gate ? (col >> 1) : col;
-    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (de.bias) bias4 = __ldg(reinterpret_cast<const float4*>(de.bias + col));
-    float4 padd = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (de.out_hi && de.out_plane_add) {
-      if (gate) {
-        const float2 t2 = __ldg(reinterpret_cast<const float2*>(de.out_plane_add + ocol));
-        padd.x = t2.x; padd.y = t2.y;
-      } else {
-        padd = __ldg(reinterpret_cast<const float4*>(de.out_plane_add + ocol));
-      }
-    }
+    const float4 bias4 = bias_c[c], padd = padd_c[c];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int r = 8 * j + rsub;
@@ -335,68 +354,253 @@ __device__ __forceinline__ void umma_tile_epilogue_co(const pttspp_conv1d_desc& 
         if (de.out && !(dbg & 8))
           *reinterpret_cast<float2*>(de.out + (int64_t)b * de.out_bs + (int64_t)rows[j] * de.out_ld + ocol) = make_float2(o0, o1);
         if (de.out_hi && !(dbg & 8)) {
-          __half h0, l0, h1, l1;
-          split_f16(o0 + padd.x, h0, l0);
-          split_f16(o1 + padd.y, h1, l1);
+          uint32_t hw, lw;
+          split2_f16(o0 + padd.x, o1 + padd.y, hw, lw);
           const int64_t pidx = (int64_t)b * de.out_plane_bs + (int64_t)rows[j] * de.out_plane_ld + ocol;
-          *reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(de.out_hi) + pidx) =
-              (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-          *reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(de.out_lo) + pidx) =
-              (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(de.out_hi) + pidx) = hw;
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(de.out_lo) + pidx) = lw;
         }
       } else {
         float o0, o1, o2, o3;
         if (de.act == PTTSPP_ACT_NONE) { o0 = x0; o1 = x1; o2 = x2; o3 = x3; }
         else if (de.act == PTTSPP_ACT_RELU) { o0 = fmaxf(x0, 0.f); o1 = fmaxf(x1, 0.f); o2 = fmaxf(x2, 0.f); o3 = fmaxf(x3, 0.f); }
         else { o0 = act_apply(x0, de.act); o1 = act_apply(x1, de.act); o2 = act_apply(x2, de.act); o3 = act_apply(x3, de.act); }
-        o0 *= am; o1 *= am; o2 *= am; o3 *= am;
+        if (am != 1.f) { o0 *= am; o1 *= am; o2 *= am; o3 *= am; }
         if (de.res) {
           float4 rv = pre[c][j];
           if (kind != 2) rv = *reinterpret_cast<const float4*>(de.res + (int64_t)b * de.res_bs + (int64_t)rows[j] * de.res_ld + ocol);
-          o0 += de.res_scale * rv.x; o1 += de.res_scale * rv.y; o2 += de.res_scale * rv.z; o3 += de.res_scale * rv.w;
+          if (de.res_scale == 1.f) { o0 += rv.x; o1 += rv.y; o2 += rv.z; o3 += rv.w; }
+          else { o0 += de.res_scale * rv.x; o1 += de.res_scale * rv.y; o2 += de.res_scale * rv.z; o3 += de.res_scale * rv.w; }
         }
         if (de.out && de.beta != 0.f) {
           float4 ov = pre[c][j];
           if (kind != 3) ov = *reinterpret_cast<const float4*>(de.out + (int64_t)b * de.out_bs + (int64_t)rows[j] * de.out_ld + ocol);
-          o0 += de.beta * ov.x; o1 += de.beta * ov.y; o2 += de.beta * ov.z; o3 += de.beta * ov.w;
+          if (de.beta == 1.f) { o0 += ov.x; o1 += ov.y; o2 += ov.z; o3 += ov.w; }
+          else { o0 += de.beta * ov.x; o1 += de.beta * ov.y; o2 += de.beta * ov.z; o3 += de.beta * ov.w; }
         }
-        o0 *= inv_div; o1 *= inv_div; o2 *= inv_div; o3 *= inv_div;
+        if (de.out_div != 0.f) { o0 *= inv_div; o1 *= inv_div; o2 *= inv_div; o3 *= inv_div; }
         if (de.out && !(dbg & 8))
           *reinterpret_cast<float4*>(de.out + (int64_t)b * de.out_bs + (int64_t)rows[j] * de.out_ld + ocol) = make_float4(o0, o1, o2, o3);
         if (de.out_hi && !(dbg & 8)) {
-          __half h[4], l[4];
-          split_f16(o0 + padd.x, h[0], l[0]);
-          split_f16(o1 + padd.y, h[1], l[1]);
-          split_f16(o2 + padd.z, h[2], l[2]);
-          split_f16(o3 + padd.w, h[3], l[3]);
+          uint32_t h01, l01, h23, l23;
+          split2_f16(o0 + padd.x, o1 + padd.y, h01, l01);
+          split2_f16(o2 + padd.z, o3 + padd.w, h23, l23);
           const int64_t pidx = (int64_t)b * de.out_plane_bs + (int64_t)rows[j] * de.out_plane_ld + ocol;
-          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(de.out_hi) + pidx) =
-              make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
-                         (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
-          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(de.out_lo) + pidx) =
-              make_uint2((uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
-                         (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(de.out_hi) + pidx) = make_uint2(h01, h23);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(de.out_lo) + pidx) = make_uint2(l01, l23);
         }
       }
     }
   }
 }
 
+// ---- row-per-lane epilogue with 256-bit global accesses ------------------------------------------------------------
+// The accumulator is finished in its TMEM layout (lane = tile row).  Every global access is one full 32-byte sector
+// per lane (LDG/STG.256: 8 floats or 16 halves), so there is no transposition through shared memory: no staging
+// tile (the pair kernel's shared memory goes to more weight stages) and no STS/LDS traffic competing with the
+// tensor core's operand reads, which already take most of the shared-memory bandwidth.
+// Precondition (host: epilogue_rl_ok): 32-byte aligned bases and row strides, Cout % 16 == 0; gate: no residual/beta.
+struct f8 {
+  float v[8];
+};
+__device__ __forceinline__ f8 ldg256(const float* p) {
+  f8 r;
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void stg256u(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
+// operand tile of the row-per-lane epilogue: the 16 floats of (row, 16-column chunk `col`) of the conditioner
+// (kind 1), the residual (kind 2) or the previous output (kind 3); zeros when there is none or the row is outside
+__device__ __forceinline__ void epi_rl_load_operand(const pttspp_conv1d_desc& de, int b, int row, bool ok, int col,
+                                                    f8 (&dst)[2]) {
+  const int kind = conv_epilogue_prefetch_kind(de);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dst[k].v[e] = 0.f;
+  }
+  if (ok && kind != 0 && col < de.Cout) {
+    const float* src = (kind == 1) ? de.addend + (int64_t)b * de.addend_bs + (int64_t)row * de.addend_ld
+                     : (kind == 2) ? de.res + (int64_t)b * de.res_bs + (int64_t)row * de.res_ld
+                                   : de.out + (int64_t)b * de.out_bs + (int64_t)row * de.out_ld;
+    dst[0] = ldg256(src + col);  // kinds 2/3 are excluded for the gate (host check): output column == col
+    dst[1] = ldg256(src + col + 8);
+  }
+}
+// (A rolling prefetch of the NEXT tile's operand chunks into the registers of consumed chunks was tried and measured
+// slower: the longer live ranges spill at the 96-register budget of the 18-warp CTA.)
+template <int BN, int NACC, int EW>
+__device__ __forceinline__ void umma_tile_epilogue_rl(const pttspp_conv1d_desc& de, int n0, int mt, int b, int u,
+                                                      uint32_t tparity, int warp, int lane, uint32_t tmem_base,
+                                                      uint32_t tfull, int n_main, int dbg) {
+  const int q = warp & 3, cgrp = warp >> 2;
+  constexpr int CW = BN / (EW / 4);
+  constexpr int NCH = CW / 16;
+  const int cbeg = cgrp * CW;
+  const bool gate = (de.act == PTTSPP_ACT_GATE);
+  const int kind = conv_epilogue_prefetch_kind(de);
+  const int m = de.m_begin + mt * UM_BM + q * 32 + lane;
+  const int row = m * de.out_mul + de.out_off;
+  const bool ok = (m < de.m_begin + de.M) && row >= 0 && row < de.T_out;
+  float am = de.alpha;
+  if (de.out_len && ok) am = ((long long)row < (long long)de.out_len[b]) ? de.alpha : 0.f;
+  const float inv_div = (de.out_div != 0.f) ? 1.f / de.out_div : 1.f;  // <= 1 ulp from the reference's IEEE division
+  // operand tile (conditioner / residual / previous output): 16 floats per chunk, requested before the accumulator
+  // is complete
+  f8 pre[NCH][2];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) epi_rl_load_operand(de, b, row, ok && !(dbg & 4), n0 + cbeg + 16 * c, pre[c]);
+  mbar_wait(tfull, tparity);
+  tc_fence_after();
+  if (dbg & 64) return;
+  const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * NACC * BN);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col0 = cbeg + 16 * c;
+    if (n0 + col0 >= de.Cout) continue;  // warp-uniform
+    float v[16];
+    {
+      uint32_t acc[NACC][16];
+      tmem_ld16_nowait(tbase + (uint32_t)((NACC - 1) * BN + col0), acc[NACC - 1]);
+#pragma unroll
+      for (int a = 0; a < NACC - 1; ++a)
+        if (a < n_main) tmem_ld16_nowait(tbase + (uint32_t)(a * BN + col0), acc[a]);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(acc[NACC - 1][e]);
+#pragma unroll
+      for (int a = 0; a < NACC - 1; ++a)
+        if (a < n_main) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] += __uint_as_float(acc[a][e]);
+        }
+    }
+    if (ok && !(dbg & 8)) {  // (the TMEM loads above are warp-collective: no divergence before them)
+      const int col = n0 + col0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (de.bias) bz = __ldg(reinterpret_cast<const float4*>(de.bias + col + 4 * k));
+        v[4 * k + 0] = v[4 * k + 0] * de.acc_scale + bz.x;
+        v[4 * k + 1] = v[4 * k + 1] * de.acc_scale + bz.y;
+        v[4 * k + 2] = v[4 * k + 2] * de.acc_scale + bz.z;
+        v[4 * k + 3] = v[4 * k + 3] * de.acc_scale + bz.w;
+      }
+      if (kind == 1) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] += pre[c][e >> 3].v[e & 7];
+      }
+      if (gate) {
+        float o[8];
+#pragma unroll
+        for (int p2 = 0; p2 < 8; ++p2) o[p2] = gate_fast(v[2 * p2], v[2 * p2 + 1]) * am * inv_div;
+        const int ocol = col >> 1;
+        if (de.out) stg256(de.out + (int64_t)b * de.out_bs + (int64_t)row * de.out_ld + ocol, o);
+        if (de.out_hi) {
+          if (de.out_plane_add) {
+            const float4 p0 = __ldg(reinterpret_cast<const float4*>(de.out_plane_add + ocol));
+            const float4 p1 = __ldg(reinterpret_cast<const float4*>(de.out_plane_add + ocol + 4));
+            o[0] += p0.x; o[1] += p0.y; o[2] += p0.z; o[3] += p0.w;
+            o[4] += p1.x; o[5] += p1.y; o[6] += p1.z; o[7] += p1.w;
+          }
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int p2 = 0; p2 < 4; ++p2) split2_f16(o[2 * p2], o[2 * p2 + 1], hw[p2], lw[p2]);
+          const int64_t pidx = (int64_t)b * de.out_plane_bs + (int64_t)row * de.out_plane_ld + ocol;
+          *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(de.out_hi) + pidx) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(de.out_lo) + pidx) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      } else {
+        if (de.act == PTTSPP_ACT_RELU) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+        } else if (de.act != PTTSPP_ACT_NONE) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = act_apply(v[e], de.act);
+        }
+        if (am != 1.f) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] *= am;
+        }
+        if (de.res) {
+          f8 r0 = pre[c][0], r1 = pre[c][1];
+          if (kind != 2) {
+            const float* src = de.res + (int64_t)b * de.res_bs + (int64_t)row * de.res_ld + col;
+            r0 = ldg256(src);
+            r1 = ldg256(src + 8);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            v[e] += de.res_scale * r0.v[e];
+            v[8 + e] += de.res_scale * r1.v[e];
+          }
+        }
+        if (de.out && de.beta != 0.f) {
+          f8 r0 = pre[c][0], r1 = pre[c][1];
+          if (kind != 3) {
+            const float* src = de.out + (int64_t)b * de.out_bs + (int64_t)row * de.out_ld + col;
+            r0 = ldg256(src);
+            r1 = ldg256(src + 8);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            v[e] += de.beta * r0.v[e];
+            v[8 + e] += de.beta * r1.v[e];
+          }
+        }
+        if (de.out_div != 0.f) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] *= inv_div;
+        }
+        if (de.out) {
+          float* dst = de.out + (int64_t)b * de.out_bs + (int64_t)row * de.out_ld + col;
+          stg256(dst, v);
+          stg256(dst + 8, v + 8);
+        }
+        if (de.out_hi) {
+          if (de.out_plane_add) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float4 pz = __ldg(reinterpret_cast<const float4*>(de.out_plane_add + col + 4 * k));
+              v[4 * k + 0] += pz.x; v[4 * k + 1] += pz.y; v[4 * k + 2] += pz.z; v[4 * k + 3] += pz.w;
+            }
+          }
+          uint32_t hw[8], lw[8];
+#pragma unroll
+          for (int p2 = 0; p2 < 8; ++p2) split2_f16(v[2 * p2], v[2 * p2 + 1], hw[p2], lw[p2]);
+          const int64_t pidx = (int64_t)b * de.out_plane_bs + (int64_t)row * de.out_plane_ld + col;
+          stg256u(reinterpret_cast<__half*>(de.out_hi) + pidx, hw);
+          stg256u(reinterpret_cast<__half*>(de.out_lo) + pidx, lw);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // Epilogue of one accumulator tile by one of the 16 epilogue warps (TMEM -> registers -> fused epilogue -> HBM).
 template <int BN, int NACC>
-__device__ __forceinline__ void umma_tile_epilogue(const pttspp_conv1d_desc& d, const pttspp_conv1d_desc& d2, int cout1,
-                                                   int vec_ok, int mt, int nt, int b, int i, int warp, int lane,
-                                                   uint32_t tmem_base, uint32_t tfull, int n_main, const OutMaps* om,
-                                                   const OutMaps* om2, int tma_out, uint8_t* stage, uint32_t stage_u32) {
+__device__ __forceinline__ void umma_tile_epilogue(const pttspp_conv1d_desc& de, int n0, int vec_ok, int mt, int b, int i,
+                                                   int warp, int lane, uint32_t tmem_base, uint32_t tfull, int n_main,
+                                                   const OutMaps* maps, bool tma_st, uint8_t* stage, uint32_t stage_u32) {
+  // `de` is one of the kernel's by-value descriptors, selected by a branch at the call site (immediate constant-bank
+  // operands instead of indexed LDCs, see umma_tile_epilogue_co)
   const int q = warp & 3;      // TMEM lane quarter this warp may access
   const int cgrp = warp >> 2;  // column group (BN / 4 columns each)
   const int u = i & 1;
-  const int m0 = d.m_begin + mt * UM_BM, n0g = nt * BN;
-  const bool second = n0g >= cout1;
-  const pttspp_conv1d_desc& de = second ? d2 : d;  // CTA-uniform
-  const int n0 = second ? n0g - cout1 : n0g;
-  const OutMaps* maps = second ? om2 : om;
-  const bool tma_st = ((tma_out >> (second ? 1 : 0)) & 1) != 0;  // CTA-uniform
+  const int m0 = de.m_begin + mt * UM_BM;
   const int m = m0 + q * 32 + lane;
   const int row = m * de.out_mul + de.out_off;
   const bool row_ok = (m < de.m_begin + de.M) && row >= 0 && row < de.T_out;
@@ -639,17 +843,23 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
         float* stg = reinterpret_cast<float*>(gen_base + STAGES * SM::STAGE_BYTES + 256 + warp * 2048);
         const int nm = n_iter < NACC - 1 ? n_iter : NACC - 1;
         if (nt * BN >= cout1)  // CTA-uniform branch: each side reads its descriptor with immediate constant operands
-          umma_tile_epilogue_co<BN, NACC, UM_EPI_WARPS>(d2, nt * BN - cout1, mt, b, i, warp, lane, tmem_base,
+          umma_tile_epilogue_co<BN, NACC, UM_EPI_WARPS>(d2, nt * BN - cout1, mt, b, i & 1, ((uint32_t)i >> 1) & 1u, warp, lane, tmem_base,
                                                         tfull_bar(i & 1), nm, stg, 0);
         else
-          umma_tile_epilogue_co<BN, NACC, UM_EPI_WARPS>(d, nt * BN, mt, b, i, warp, lane, tmem_base, tfull_bar(i & 1),
+          umma_tile_epilogue_co<BN, NACC, UM_EPI_WARPS>(d, nt * BN, mt, b, i & 1, ((uint32_t)i >> 1) & 1u, warp, lane, tmem_base, tfull_bar(i & 1),
                                                         nm, stg, 0);
       }
-      else
-        umma_tile_epilogue<BN, NACC>(d, d2, cout1, vec_ok, mt, nt, b, i, warp, lane, tmem_base, tfull_bar(i & 1),
-                                     n_iter < NACC - 1 ? n_iter : NACC - 1, &om, &om2, tma_out,
-                                     gen_base + STAGES * SM::STAGE_BYTES + 256 + warp * 2048,
-                                     base + STAGES * SM::STAGE_BYTES + 256 + warp * 2048);
+      else {
+        uint8_t* stg = gen_base + STAGES * SM::STAGE_BYTES + 256 + warp * 2048;
+        const uint32_t stg_u32 = base + STAGES * SM::STAGE_BYTES + 256 + warp * 2048;
+        const int nm = n_iter < NACC - 1 ? n_iter : NACC - 1;
+        if (nt * BN >= cout1)
+          umma_tile_epilogue<BN, NACC>(d2, nt * BN - cout1, vec_ok, mt, b, i, warp, lane, tmem_base, tfull_bar(i & 1), nm,
+                                       &om2, (tma_out & 2) != 0, stg, stg_u32);
+        else
+          umma_tile_epilogue<BN, NACC>(d, nt * BN, vec_ok, mt, b, i, warp, lane, tmem_base, tfull_bar(i & 1), nm, &om,
+                                       (tma_out & 1) != 0, stg, stg_u32);
+      }
       const int u = i & 1;
       tc_fence_before();
       __syncwarp();
@@ -805,8 +1015,12 @@ conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_co
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
       const int mt = unit % n_mt, b = unit / n_mt;
       for (int nt = 0; nt < n_nt; ++nt, ++i) {
-        umma_tile_epilogue<BN, UM_NACC>(d, d2, cout1, vec_ok, mt, nt, b, i, warp, lane, tmem_base, tfull_bar(i & 1), 1,
-                                        nullptr, nullptr, 0, nullptr, 0u);
+        if (nt * BN >= cout1)
+          umma_tile_epilogue<BN, UM_NACC>(d2, nt * BN - cout1, vec_ok, mt, b, i, warp, lane, tmem_base, tfull_bar(i & 1), 1,
+                                          nullptr, false, nullptr, 0u);
+        else
+          umma_tile_epilogue<BN, UM_NACC>(d, nt * BN, vec_ok, mt, b, i, warp, lane, tmem_base, tfull_bar(i & 1), 1,
+                                          nullptr, false, nullptr, 0u);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(i & 1));
@@ -842,13 +1056,18 @@ constexpr int UP_MAX_SLAB = 8;
 
 // EW epilogue warps (4 TMEM lane quarters x EW/4 column groups): 16 drain a tile fastest, 8 leave shared memory for
 // one more weight stage.
-template <int NBST, int EW>
+// NACC = 2: main | cross-term accumulators, two tile buffers.  NACC = 1 (short contractions, K*Cin <= 256: at most 48
+// accumulations, truncation bias < 1e-5 relative): one accumulator per tile and FOUR tile buffers, so the MMA warp
+// runs up to three tiles ahead of a memory-bound epilogue.
+template <int NBST, int EW, int NACC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((EW + 2) * 32, 1)
 conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                         const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                         const pttspp_conv1d_desc d, const pttspp_conv1d_desc d2, const int cout1, const int cout_total,
-                        const int n_mt2, const int n_nt, const int n_tiles, const int rowsA, const int mma_order) {
-  constexpr uint32_t TMEM_COLS = 2 * UM_NACC * UP_BN;
+                        const int n_mt2, const int n_nt, const int n_tiles, const int rowsA, const int mma_order,
+                        const int epi_rl) {
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr int NBUF = 512 / (NACC * UP_BN);  // accumulator tile buffers
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -857,16 +1076,16 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
   const uint32_t a_bytes = (uint32_t)nslab * 2u * a_plane;
   const uint32_t ring = base + a_bytes;
   const uint32_t stg_off = a_bytes + (uint32_t)NBST * UP_BST_BYTES;  // epilogue staging, 2 KB per warp
-  const uint32_t bars_off = stg_off + EW * 2048;
+  const uint32_t bars_off = stg_off + (epi_rl ? 0u : (uint32_t)EW * 2048u);  // the row-per-lane gate epilogue needs no staging
   const uint32_t bars = base + bars_off;
   // fullA[8], emptyA[8], fullB[NBST], emptyB[NBST], tfull[2], tempty[2]
-  constexpr int NBARS = 2 * UP_MAX_SLAB + 2 * NBST + 4;
+  constexpr int NBARS = 2 * UP_MAX_SLAB + 2 * NBST + 8;
   auto fullA = [&](int sl) { return bars + sl * 8; };
   auto emptyA = [&](int sl) { return bars + (UP_MAX_SLAB + sl) * 8; };
   auto fullB = [&](int st) { return bars + (2 * UP_MAX_SLAB + st) * 8; };
   auto emptyB = [&](int st) { return bars + (2 * UP_MAX_SLAB + NBST + st) * 8; };
   auto tfull_bar = [&](int u) { return bars + (2 * UP_MAX_SLAB + 2 * NBST + u) * 8; };
-  auto tempty_bar = [&](int u) { return bars + (2 * UP_MAX_SLAB + 2 * NBST + 2 + u) * 8; };
+  auto tempty_bar = [&](int u) { return bars + (2 * UP_MAX_SLAB + 2 * NBST + 4 + u) * 8; };
   const uint32_t tmem_slot = bars + NBARS * 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + bars_off + NBARS * 8);
 
@@ -885,7 +1104,7 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
       mbar_init(fullB(st), 1);
       mbar_init(emptyB(st), 1);
     }
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < NBUF; ++u) {
       mbar_init(tfull_bar(u), 1);
       mbar_init(tempty_bar(u), 2 * EW);  // epilogue warps of both CTAs
     }
@@ -983,11 +1202,11 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
         const bool new_unit = unit != cur_unit;
         cur_unit = unit;
         const bool last_of_unit = (t + 1 == t_end) || ((t + 1) / n_nt != unit);
-        const int u = i & 1;
-        mbar_wait(tempty_bar(u), (((uint32_t)i >> 1) & 1u) ^ 1u);  // both CTAs' epilogues have drained buffer u
+        const int u = i % NBUF;
+        mbar_wait(tempty_bar(u), (((uint32_t)i / NBUF) & 1u) ^ 1u);  // both CTAs' epilogues have drained buffer u
         tc_fence_after();
-        const uint32_t acc_main = tmem_base + (uint32_t)(u * UM_NACC * UP_BN);
-        const uint32_t acc_cross = acc_main + (uint32_t)UP_BN;
+        const uint32_t acc_main = tmem_base + (uint32_t)(u * NACC * UP_BN);
+        const uint32_t acc_cross = acc_main + (uint32_t)((NACC - 1) * UP_BN);  // NACC == 1: the same accumulator
         uint32_t first = 0;
         for (int slab = 0; slab < nslab; ++slab) {
           if (new_unit) {
@@ -1013,7 +1232,7 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
                   const uint64_t adv = (uint64_t)(kk * 2);
                   umma_f16_pair(acc_cross, dAl + adv, dBh + adv, idesc, kk ? 1u : first);
                   umma_f16_pair(acc_cross, dAh + adv, dBl + adv, idesc, 1u);
-                  umma_f16_pair(acc_main, dAh + adv, dBh + adv, idesc, kk ? 1u : first);
+                  umma_f16_pair(acc_main, dAh + adv, dBh + adv, idesc, (kk || NACC == 1) ? 1u : first);
                 }
               } else if ((mma_order & 3) == 1) {
                 // grouped by accumulator: the destination changes twice per stage instead of after every MMA
@@ -1025,7 +1244,7 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
                   umma_f16_pair(acc_cross, dAh + (uint64_t)(kk * 2), dBl + (uint64_t)(kk * 2), idesc, 1u);
 #pragma unroll
                 for (int kk = 0; kk < UM_BK / 16; ++kk)
-                  umma_f16_pair(acc_main, dAh + (uint64_t)(kk * 2), dBh + (uint64_t)(kk * 2), idesc, kk ? 1u : first);
+                  umma_f16_pair(acc_main, dAh + (uint64_t)(kk * 2), dBh + (uint64_t)(kk * 2), idesc, (kk || NACC == 1) ? 1u : first);
               } else {
                 // timing experiment only (wrong numerics budget): one accumulator, one MMA per product
 #pragma unroll
@@ -1051,17 +1270,29 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
     for (int t = t_begin; t < t_end; ++t, ++i) {
       const int unit = t / n_nt, nt = t - unit * n_nt;
       const int b = unit / n_mt2, mt2 = unit - b * n_mt2;
-      if (nt * UP_BN >= cout1)  // CTA-uniform branch, see umma_tile_epilogue_co
-        umma_tile_epilogue_co<UP_BN, UM_NACC, EW>(d2, nt * UP_BN - cout1, 2 * mt2 + (int)rank, b, i, warp, lane, tmem_base,
-                                                  tfull_bar(i & 1), 1, stage, mma_order);
-      else
-        umma_tile_epilogue_co<UP_BN, UM_NACC, EW>(d, nt * UP_BN, 2 * mt2 + (int)rank, b, i, warp, lane, tmem_base,
-                                                  tfull_bar(i & 1), 1, stage, mma_order);
+      const int mt = 2 * mt2 + (int)rank, ub = i % NBUF;
+      const uint32_t tpar = ((uint32_t)i / NBUF) & 1u;
+      // CTA-uniform branches: each call reads ITS descriptor(s) with immediate constant operands
+      if (epi_rl) {
+        if (nt * UP_BN >= cout1)
+          umma_tile_epilogue_rl<UP_BN, NACC, EW>(d2, nt * UP_BN - cout1, mt, b, ub, tpar, warp, lane, tmem_base, tfull_bar(ub),
+                                                 NACC - 1, mma_order);
+        else
+          umma_tile_epilogue_rl<UP_BN, NACC, EW>(d, nt * UP_BN, mt, b, ub, tpar, warp, lane, tmem_base, tfull_bar(ub), NACC - 1,
+                                                 mma_order);
+      } else {
+        if (nt * UP_BN >= cout1)
+          umma_tile_epilogue_co<UP_BN, NACC, EW>(d2, nt * UP_BN - cout1, mt, b, ub, tpar, warp, lane, tmem_base, tfull_bar(ub),
+                                                 NACC - 1, stage, mma_order);
+        else
+          umma_tile_epilogue_co<UP_BN, NACC, EW>(d, nt * UP_BN, mt, b, ub, tpar, warp, lane, tmem_base, tfull_bar(ub), NACC - 1,
+                                                 stage, mma_order);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (rank == 0) mbar_arrive(tempty_bar(i & 1));
-        else mbar_arrive_cluster(tempty_bar(i & 1), 0);
+        if (rank == 0) mbar_arrive(tempty_bar(i % NBUF));
+        else mbar_arrive_cluster(tempty_bar(i % NBUF), 0);
       }
     }
   }
@@ -1202,6 +1433,17 @@ bool epilogue_co_ok(const pttspp_conv1d_desc& d) {
   return true;
 }
 
+// row-per-lane 256-bit epilogue: 32-byte aligned bases / row strides / batch strides
+bool epilogue_rl_ok(const pttspp_conv1d_desc& d) {
+  if (!epilogue_co_ok(d)) return false;
+  auto a32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
+  auto okf = [&](const void* p, int64_t bs, int ld) { return !p || (a32(p) && bs % 8 == 0 && ld % 8 == 0); };
+  if (!okf(d.addend, d.addend_bs, d.addend_ld) || !okf(d.res, d.res_bs, d.res_ld) || !okf(d.out, d.out_bs, d.out_ld))
+    return false;
+  if (d.out_hi && !(a32(d.out_hi) && a32(d.out_lo) && d.out_plane_bs % 16 == 0 && d.out_plane_ld % 16 == 0)) return false;
+  return true;
+}
+
 // A 1x1 contraction over densely packed [B][T] rows is one [B*T]-row problem: no halo, no per-utterance tile tails.
 bool flatten_batch_ok(const pttspp_conv1d_desc& d) {
   if (d.K != 1 || d.pad != 0 || d.m_begin != 0 || d.M != d.T_out || d.M != d.T_in || d.out_mul != 1 || d.out_off != 0)
@@ -1242,11 +1484,11 @@ int pair_clusters(const void* kern, size_t smem, int threads) {
 }
 
 // one-time setup per kernel instantiation: opt in to 227 KB of dynamic shared memory, query resident clusters
-template <int NBST, int EW>
+template <int NBST, int EW, int NACC>
 int pair_kernel_setup(int num_sms, bool debug) {
   static int max_clusters = -1;
   if (max_clusters < 0) {
-    auto kern = conv1d_umma_pair_kernel<NBST, EW>;
+    auto kern = conv1d_umma_pair_kernel<NBST, EW, NACC>;
     PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int n = pair_clusters((const void*)kern, 227 * 1024, (EW + 2) * 32);
     if (debug) fprintf(stderr, "[pttspp] pair kernel<%d>: cudaOccupancyMaxActiveClusters -> %d\n", NBST, n);
@@ -1271,9 +1513,11 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
   const int rowsA = UM_BM + round_up((d.K - 1) * d.dil, 8);
   if (rowsA > 256) return false;
   const size_t a_bytes = (size_t)nslab * 2 * rowsA * 128;
-  const char* ewe = getenv("PTTSPP_UMMA_EW");
-  const int ew = (ewe && atoi(ewe) == 8) ? 8 : 16;
-  const size_t fixed = a_bytes + (size_t)ew * 2048 + (2 * UP_MAX_SLAB + 2 * 6 + 4) * 8 + 16 + 1024;
+  const int ew = 16;  // epilogue warps (8 measured slower: tools/bench_conv.py history in profiles/)
+  // row-per-lane 256-bit epilogue (no staging tile) whenever the alignment allows it; PTTSPP_UMMA_RL=0: coalescing one
+  const char* rle = getenv("PTTSPP_UMMA_RL");
+  const bool epi_rl = epilogue_rl_ok(d) && (!dual || epilogue_rl_ok(d2)) && !(rle && rle[0] == '0');
+  const size_t fixed = a_bytes + (epi_rl ? 0 : (size_t)ew * 2048) + (2 * UP_MAX_SLAB + 2 * 6 + 8) * 8 + 16 + 1024;
   const size_t cap = 227 * 1024;
   if (fixed + 3 * UP_BST_BYTES > cap) return false;
   const int nbst = (int)std::min<size_t>(6, (cap - fixed) / UP_BST_BYTES);
@@ -1281,7 +1525,8 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
   const long long n_tiles = (long long)n_mt2 * d.B * n_nt;
   if (n_tiles >= (1ll << 30)) return false;
   // worth it only when every pair gets at least a couple of tiles (the activation block is loaded per unit)
-  if (!(env && env[0] == '2') && n_tiles < num_sms) return false;
+  // and when the activation block is reused by at least two N tiles (otherwise the streaming kernel is faster)
+  if (!(env && env[0] == '2') && (n_tiles < num_sms || n_nt < 2)) return false;
 
   const uint64_t wdims[2] = {(uint64_t)d.Cin, (uint64_t)d.K * total_cout};
   const uint64_t wstr[1] = {(uint64_t)d.Cin * 2};
@@ -1301,32 +1546,29 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
     int cout_first = dual ? cout1 : total_cout, cout_all = total_cout, a_n_mt2 = n_mt2, a_n_nt = n_nt, a_tiles = (int)n_tiles,
         a_rowsA = rowsA;
     const char* oe = getenv("PTTSPP_UMMA_ORDER");  // experiments: bits 0-1 MMA order, 4 no operand loads, 8 no stores, 16 no L2 prefetch
-    int a_order = oe ? atoi(oe) : 0;
+    int a_order = oe ? atoi(oe) : 0, a_rl = epi_rl ? 1 : 0;
     void* args[] = {(void*)&mAh, (void*)&mAl, (void*)&mBh, (void*)&mBl, (void*)&d, (void*)&d2, &cout_first, &cout_all,
-                    &a_n_mt2, &a_n_nt, &a_tiles, &a_rowsA, &a_order};
+                    &a_n_mt2, &a_n_nt, &a_tiles, &a_rowsA, &a_order, &a_rl};
     if (debug)
-      fprintf(stderr, "[pttspp] pair launch: clusters %d tiles %lld (units %d x nt %d) rowsA %d nbst %d smem %zu\n",
-              n_clusters, n_tiles, n_mt2 * d.B, n_nt, rowsA, nbst, smem);
+      fprintf(stderr, "[pttspp] pair launch: clusters %d tiles %lld (units %d x nt %d) rowsA %d nbst %d smem %zu rl %d\n",
+              n_clusters, n_tiles, n_mt2 * d.B, n_nt, rowsA, nbst, smem, (int)epi_rl);
     cudaGetLastError();  // a stale error of an earlier call must not be attributed to this launch
     PT_CUDA(cudaLaunchKernel((const void*)kern, dim3(2 * n_clusters), dim3((ew + 2) * 32), args, smem, s));
     ++g_launch_count;
   };
-#define PT_PAIR_CASE(N, E) launch(conv1d_umma_pair_kernel<N, E>, pair_kernel_setup<N, E>(num_sms, debug))
-  if (ew == 8) {
-    switch (nbst) {
-      case 3: PT_PAIR_CASE(3, 8); break;
-      case 4: PT_PAIR_CASE(4, 8); break;
-      case 5: PT_PAIR_CASE(5, 8); break;
-      default: PT_PAIR_CASE(6, 8); break;
-    }
-  } else {
-    switch (nbst) {
-      case 3: PT_PAIR_CASE(3, 16); break;
-      case 4: PT_PAIR_CASE(4, 16); break;
-      case 5: PT_PAIR_CASE(5, 16); break;
-      default: PT_PAIR_CASE(6, 16); break;
-    }
+  // short contractions: one accumulator per tile, four tile buffers (see the kernel)
+  const char* nae = getenv("PTTSPP_UMMA_NACC");
+  const bool one_acc = (d.K * d.Cin <= 256) && !(nae && nae[0] == '2');
+#define PT_PAIR_CASE(N, E, A) launch(conv1d_umma_pair_kernel<N, E, A>, pair_kernel_setup<N, E, A>(num_sms, debug))
+#define PT_PAIR_SWITCH(E, A)               \
+  switch (nbst) {                          \
+    case 3: PT_PAIR_CASE(3, E, A); break;  \
+    case 4: PT_PAIR_CASE(4, E, A); break;  \
+    case 5: PT_PAIR_CASE(5, E, A); break;  \
+    default: PT_PAIR_CASE(6, E, A); break; \
   }
+  if (one_acc) { PT_PAIR_SWITCH(16, 1) } else { PT_PAIR_SWITCH(16, 2) }
+#undef PT_PAIR_SWITCH
 #undef PT_PAIR_CASE
   return true;
 }

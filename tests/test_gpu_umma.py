@@ -67,11 +67,13 @@ VARIANTS = {
     "stream_tma": {"PTTSPP_UMMA_PAIR": "0"},                           # ... TMA bulk-store epilogue (its default)
     "astat": {"PTTSPP_UMMA_PAIR": "0", "PTTSPP_UMMA_AS": "1"},         # single-CTA A-stationary (opt-in)
     "pair": {"PTTSPP_UMMA_PAIR": "2"},                                 # CTA-pair kernel forced wherever it applies
+    # ... gate epilogue through the staging tile, two accumulators even for short contractions
+    "pair_co": {"PTTSPP_UMMA_PAIR": "2", "PTTSPP_UMMA_RL": "0", "PTTSPP_UMMA_NACC": "2"},
 }
 
 
 def _select(monkeypatch, variant):
-    for k in ("PTTSPP_UMMA_PAIR", "PTTSPP_UMMA_EPI", "PTTSPP_UMMA_AS"):
+    for k in ("PTTSPP_UMMA_PAIR", "PTTSPP_UMMA_EPI", "PTTSPP_UMMA_AS", "PTTSPP_UMMA_RL", "PTTSPP_UMMA_NACC"):
         monkeypatch.delenv(k, raising=False)
     for k, v in VARIANTS[variant].items():
         monkeypatch.setenv(k, v)
@@ -97,7 +99,7 @@ def test_conv1d_umma_plain(ops, monkeypatch, Cin, Cout, K, dil, B, T, variant):
     assert err < 1e-5 + 6e-9 * K * Cin, err
 
 
-@pytest.mark.parametrize("variant", ["stream", "stream_tma", "pair"])
+@pytest.mark.parametrize("variant", ["stream", "stream_tma", "pair", "pair_co"])
 def test_conv1d_umma_diffnet_chain(ops, monkeypatch, variant):
     """gate conv -> planes -> 1x1 residual/skip convs, the two tcgen05 launches of a DiffNet layer."""
     _select(monkeypatch, variant)
@@ -140,7 +142,7 @@ def test_conv1d_umma_diffnet_chain(ops, monkeypatch, variant):
     assert float((_bct(sbuf) - skip_ref).abs().max()) < 2e-5
 
 
-@pytest.mark.parametrize("variant", ["stream", "stream_tma", "pair"])
+@pytest.mark.parametrize("variant", ["stream", "stream_tma", "pair", "pair_co"])
 def test_conv1d_umma_dual_epilogue(ops, monkeypatch, variant):
     """residual | skip halves of the DiffNet output projection in ONE launch."""
     _select(monkeypatch, variant)
@@ -165,3 +167,33 @@ def test_conv1d_umma_dual_epilogue(ops, monkeypatch, variant):
     assert float((_bct(sbuf) - skip_ref).abs().max()) < 2e-5
     assert float((_bct(p1[0].float() + p1[1].float()) - (x_ref + nxt[None, :, None])).abs().max()) < 2e-5
     assert float((_bct(p2[0].float() + p2[1].float()) - skip_ref).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("variant", ["stream_tma", "pair", "pair_co"])
+@pytest.mark.parametrize("dil,T", [(1, 2500), (8, 2582)])
+def test_conv1d_umma_gate_large(ops, monkeypatch, variant, dil, T):
+    """DiffNet gated conv at bench-like sizes: fp32 output AND operand planes, ragged out_len mask, plane_add."""
+    _select(monkeypatch, variant)
+    g = torch.Generator().manual_seed(40 + dil)
+    B, C = 4, 256
+    x = torch.randn(B, C, T, generator=g)
+    cond = torch.randn(B, 2 * C, T, generator=g)
+    w1 = torch.randn(2 * C, C, 3, generator=g) / math.sqrt(C * 3)
+    b1 = torch.randn(2 * C, generator=g)
+    padd = torch.randn(C, generator=g)
+    lens = torch.tensor([T, T - 1, T // 2 + 3, 17])
+    y = F.conv1d(x, w1, b1, padding=dil, dilation=dil) + cond
+    gate, filt = torch.chunk(y, 2, dim=1)
+    mask = (torch.arange(T)[None, :] < lens[:, None]).float()[:, None, :]
+    z_ref = torch.sigmoid(gate) * torch.tanh(filt) * mask
+    perm = torch.empty(2 * C, dtype=torch.long)
+    perm[0::2] = torch.arange(C)
+    perm[1::2] = torch.arange(C) + C
+    planes = ops.split_f16(_cl(x))
+    out, zp = ops.conv1d_umma_cl(planes, ops.pack_conv_weight_split(w1, interleave_halves=True, device="cuda"), 2 * C,
+                                 bias=b1[perm].cuda(), K=3, dil=dil, pad=dil, act=ops.ACT_GATE,
+                                 addend=_cl(cond[:, perm]), out_len=lens.cuda(), emit_planes=True,
+                                 plane_add=padd.cuda())
+    assert float((_bct(out) - z_ref).abs().max()) < 2e-5
+    z = zp[0].float() + zp[1].float()
+    assert float((_bct(z) - (z_ref + padd[None, :, None])).abs().max()) < 2e-5

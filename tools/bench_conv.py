@@ -56,11 +56,11 @@ def main():
 
     # experiment bits: 2 one MMA per product, 4 no operand loads, 8 no stores, 32 no TMEM reads, 64 no epilogue
     VARIANTS = (("str", {"PTTSPP_UMMA_PAIR": "0", "PTTSPP_UMMA_EPI": "co"}), ("tma", {"PTTSPP_UMMA_PAIR": "0"}),
-                ("pair", pv()), ("p-1mma", pv(2)), ("p-noLS", pv(12)), ("p-noTM", pv(32)), ("p-noLSTM", pv(44)),
-                ("p-noEpi", pv(64)), ("p-noEpi1", pv(66)), ("p8", pv(None, 8)), ("p8noLSTM", pv(44, 8)))
-    KEYS = ("PTTSPP_UMMA_PAIR", "PTTSPP_UMMA_EPI", "PTTSPP_UMMA_AS", "PTTSPP_UMMA_ORDER", "PTTSPP_UMMA_EW")
+                ("pair", pv()), ("p-co", dict(pv(), PTTSPP_UMMA_RL="0")), ("p-1mma", pv(2)), ("p-noLS", pv(12)),
+                ("p-noEpi", pv(64)))
+    KEYS = ("PTTSPP_UMMA_PAIR", "PTTSPP_UMMA_EPI", "PTTSPP_UMMA_AS", "PTTSPP_UMMA_ORDER", "PTTSPP_UMMA_EW", "PTTSPP_UMMA_RL", "PTTSPP_UMMA_NACC")
     if os.environ.get("BENCH_QUICK"):
-        VARIANTS = VARIANTS[0:1] + VARIANTS[2:]
+        VARIANTS = VARIANTS[1:]
 
     def add(name, fl, fn):
         modes = VARIANTS if name.startswith("umma") else (("    ", {}),)
