@@ -125,6 +125,16 @@ PackedConv load_concat(const TensorStore& st, DeviceBuffers& dev, const std::vec
   }
   c.w = dev.upload(packed);
   if (has_bias) c.bias = dev.upload(bias);
+  if (K == 1 && Cin % 64 == 0) {
+    // split-fp16 planes [Cout][Cin] of the same concatenation for the tcgen05 path (rows already in packed column order)
+    std::vector<float> rows((size_t)c.Cout * Cin);
+    for (int co = 0; co < c.Cout; ++co)
+      for (int ci = 0; ci < Cin; ++ci) rows[(size_t)co * Cin + ci] = packed[(size_t)ci * c.w_ld + co];
+    std::vector<uint16_t> hi(rows.size()), lo(rows.size());
+    pack_conv_weight_split(rows.data(), nullptr, c.Cout, Cin, 1, hi.data(), lo.data(), 0, &c.w_scale_inv);
+    c.w_hi = dev.upload_bytes(hi.data(), hi.size() * 2);
+    c.w_lo = dev.upload_bytes(lo.data(), lo.size() * 2);
+  }
   return c;
 }
 
@@ -352,6 +362,7 @@ extern "C" int pttspp_acoustic_finalize(pttspp_acoustic_t* h, pttspp_stream_t) {
     const std::string p = va + "pitch_predictor.layers." + std::to_string(i) + ".";
     PredLayerW l;
     l.conv = load_conv1d(st, dev, p + "conv", C, C, c.pitch_kernel, 1, c.pitch_kernel / 2);
+    if (C % 64 == 0) attach_split_weights(st, dev, p + "conv", l.conv, false);
     l.norm = load_ln(st, dev, p + "norm.gamma", p + "norm.beta", C);
     h->pitch_layers.push_back(l);
   }
@@ -364,6 +375,7 @@ extern "C" int pttspp_acoustic_finalize(pttspp_acoustic_t* h, pttspp_stream_t) {
     PredLayerW l;
     l.conv = load_conv1d(st, dev, va + "frame_prior_network.convs." + std::to_string(i), C, C, c.fp_kernel, 1,
                          c.fp_kernel / 2);
+    if (C % 64 == 0) attach_split_weights(st, dev, va + "frame_prior_network.convs." + std::to_string(i), l.conv, false);
     const std::string n = va + "frame_prior_network.norms." + std::to_string(i);
     l.norm = load_ln(st, dev, n + ".gamma", n + ".beta", C);
     h->fp_layers.push_back(l);
@@ -554,6 +566,12 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
   const int C = c.channels, DC = c.diff_channels, M = c.mel_dim;
   const int64_t* flen = frame_len;
   const int64_t bsC = (int64_t)Ty * C;
+  // route a conv through the tcgen05 split-fp16 path: operand planes [B][Ty][Cin] + the conv's split weight planes
+  auto tc_in = [&](pttspp_conv1d_desc& q, const uint16_t* hi, const uint16_t* lo, const PackedConv& pc) {
+    q.in_hi = hi; q.in_lo = lo; q.in_bs = (int64_t)Ty * pc.Cin; q.in_ld = pc.Cin;
+    q.w_hi = pc.w_hi; q.w_lo = pc.w_lo; q.w_scale_inv = pc.w_scale_inv;
+    q.impl = 2;
+  };
 
   // length regulator (gather instead of the one-hot matmul of utils/model.py:37-47)
   length_regulate(enc_state, dur, B, Tx, C, Ty, w.xa, nullptr, s);
@@ -566,7 +584,15 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
     for (size_t i = 0; i < h->fp_layers.size(); ++i) {
       const PredLayerW& l = h->fp_layers[i];
       auto d = conv_desc(l.conv, cur, B, Ty, w.tmp);
-      d.in_len = flen; d.act = PTTSPP_ACT_GELU;
+      d.act = PTTSPP_ACT_GELU;
+      if (h->use_umma && l.conv.w_hi) {
+        // frames are known only after the (bit-exact, fp32 CUDA-core) duration path: from here on the contractions run
+        // on the tensor cores.  `x * mask` in front of the conv = zero rows in the operand planes.
+        split_f16_rows(cur, B, Ty, C, flen, w.yh, w.yl, s);
+        tc_in(d, w.yh, w.yl, l.conv);
+      } else {
+        d.in_len = flen;
+      }
       conv1d_cl(d, s);
       const bool last = (i + 1 == h->fp_layers.size());
       run_ln(l.norm, cur, w.tmp, nxt, B, Ty, C, 1e-5f, nullptr, last ? flen : nullptr, 1.f, nullptr, s);
@@ -585,6 +611,10 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
     for (const PredLayerW& l : h->pitch_layers) {
       auto d = conv_desc(l.conv, cur, B, Ty, w.tmp);
       d.act = PTTSPP_ACT_RELU;
+      if (h->use_umma && l.conv.w_hi) {
+        split_f16_rows(cur, B, Ty, C, nullptr, w.yh, w.yl, s);
+        tc_in(d, w.yh, w.yl, l.conv);
+      }
       conv1d_cl(d, s);
       run_ln(l.norm, w.tmp, nullptr, bufs[bi], B, Ty, C, 1e-5f, nullptr, flen, 1.f, nullptr, s);
       cur = bufs[bi];
@@ -603,6 +633,10 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
   const int CP = 2 * DC * c.diff_layers;
   {
     auto d = conv_desc(h->cond_all, cond, B, Ty, w.condp);
+    if (h->use_umma && h->cond_all.w_hi) {
+      split_f16_rows(cond, B, Ty, C, nullptr, w.yh, w.yl, s);
+      tc_in(d, w.yh, w.yl, h->cond_all);
+    }
     conv1d_cl(d, s);
   }
   transpose_bct_to_btc(x_T, w.xt, B, M, Ty, s);

@@ -156,7 +156,7 @@ extern "C" int pttspp_bigvgan_finalize(pttspp_bigvgan_t* h, pttspp_stream_t) {
         AMPLayerW w;
         w.conv1 = load_conv1d(h->store, h->dev, lp + ".conv1", u.Cout, u.Cout, k, dl, (k * dl - dl) / 2);
         w.conv2 = load_conv1d(h->store, h->dev, lp + ".conv2", u.Cout, u.Cout, k, 1, k / 2);
-        if (h->use_umma && u.Cout % 64 == 0) {  // tensor-core path for the dense C -> C contractions
+        if (h->use_umma && (u.Cout % 64 == 0 || u.Cout == 32)) {  // tensor-core path for the dense C -> C contractions
           attach_split_weights(h->store, h->dev, lp + ".conv1", w.conv1, false);
           attach_split_weights(h->store, h->dev, lp + ".conv2", w.conv2, false);
         }

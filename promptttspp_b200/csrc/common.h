@@ -87,6 +87,8 @@ void pack_conv_weight(const float* v, const float* g, int Cout, int Cin, int K, 
 void pack_conv_weight_split(const float* v, const float* g, int Cout, int Cin, int K, void* w_hi, void* w_lo,
                             int interleave_halves, float* scale_inv);
 void split_f16_planes(const float* x, const float* add, int64_t n, int C, void* hi, void* lo, cudaStream_t s);
+// [B][T][C] rows -> planes; rows >= len[b] (len optional) become zeros
+void split_f16_rows(const float* x, int B, int T, int C, const int64_t* len, void* hi, void* lo, cudaStream_t s);
 void pack_convtr_weight(const float* v, const float* g, int Cin, int Cout, int Kt, int stride, float* packed,
                         int w_ld, cudaStream_t s);
 // tcgen05 path, one launch with two epilogues: columns [0, Cout(d1)) follow d1, the next Cout(d2) columns follow d2

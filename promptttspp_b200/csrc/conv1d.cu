@@ -285,6 +285,39 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
 }
 }  // namespace
 
+namespace {
+// rows [B][T][C] -> planes, rows at or beyond len[b] written as zeros (the `x * mask` in front of a conv); 4 elements
+// per thread, 16-byte loads / 8-byte stores
+__global__ void __launch_bounds__(256) split_f16_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ len,
+                                                             int T, int C4, int64_t n4, uint2* __restrict__ hi,
+                                                             uint2* __restrict__ lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int64_t r = i / C4;
+  const int b = (int)(r / T), t = (int)(r - (int64_t)b * T);
+  float4 v = reinterpret_cast<const float4*>(x)[i];
+  if (len && (int64_t)t >= len[b]) v = make_float4(0.f, 0.f, 0.f, 0.f);
+  __half h[4], l[4];
+  split_f16(v.x, h[0], l[0]);
+  split_f16(v.y, h[1], l[1]);
+  split_f16(v.z, h[2], l[2]);
+  split_f16(v.w, h[3], l[3]);
+  hi[i] = make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
+                     (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
+  lo[i] = make_uint2((uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
+                     (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+}
+}  // namespace
+
+void split_f16_rows(const float* x, int B, int T, int C, const int64_t* len, void* hi, void* lo, cudaStream_t s) {
+  PT_CHECK(x && hi && lo && C % 4 == 0 && aligned16(x) && aligned16(hi) && aligned16(lo), "split_f16_rows: bad argument");
+  const int64_t n4 = (int64_t)B * T * (C / 4);
+  if (n4 == 0) return;
+  ProfScope prof(PROF_OTHER, s, 0.0, 8.0 * 4.0 * (double)n4);
+  split_f16_rows_kernel<<<(unsigned)ceil_div64(n4, 256), 256, 0, s>>>(x, len, T, C / 4, n4, (uint2*)hi, (uint2*)lo);
+  PT_LAUNCHED();
+}
+
 void split_f16_planes(const float* x, const float* add, int64_t n, int C, void* hi, void* lo, cudaStream_t s) {
   PT_CHECK(x && hi && lo && C >= 1, "split_f16: bad argument");
   if (n == 0) return;

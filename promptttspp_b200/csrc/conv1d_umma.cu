@@ -1304,6 +1304,169 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
   }
 }
 
+
+// ---- narrow-channel (Cin = Cout = 32) weight-resident kernel -------------------------------------------------------
+// BigVGAN's last stage (32 channels, 245 760 samples per utterance) is HBM bound: 1 GB of activation traffic per conv
+// against 8-88 GFLOP.  All taps' weight planes (K x 32 x 32 halves x 2 planes <= 44 KB) stay resident in shared memory
+// for the whole kernel; per 128-row tile the producer loads ONE halo block (128 + (K-1)*dil rows x 64 B x 2 planes,
+// SWIZZLE_64B K-major) and every tap's MMAs read it through a descriptor advanced by tap*dil rows.  The tensor work per
+// tile is tiny (K x 6 MMAs of 128 x 32 x 16), so the kernel is organised for memory-level parallelism: a deep
+// activation ring, four accumulator buffers, and TWO epilogue groups of 8 warps that alternate tiles, so that one
+// group's residual loads are in flight while the other computes and stores.
+constexpr int US_C = 32;            // channels (Cin == Cout)
+constexpr int US_EW = 8;            // epilogue warps per group
+constexpr int US_GROUPS = 2;
+constexpr int US_THREADS = (US_GROUPS * US_EW + 2) * 32;
+constexpr int US_NBUF = 4;          // accumulator buffers (main | cross, 64 TMEM columns each)
+constexpr int US_MAXK = 11;
+
+// K-major, SWIZZLE_64B shared-memory matrix descriptor: rows of 64 bytes, 8-row groups 512 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;  // SWIZZLE_64B
+  return d;
+}
+
+template <int NST>
+__global__ void __launch_bounds__(US_THREADS, 1)
+conv1d_umma_c32_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                       const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
+                       const pttspp_conv1d_desc d, const int n_mt, const int n_tiles, const int rowsA) {
+  constexpr uint32_t TMEM_COLS = US_NBUF * 2 * US_C;  // 256
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t w_plane = (uint32_t)d.K * US_C * 64u;          // one weight plane: K taps x 32 rows x 64 B
+  const uint32_t w_bytes = 2u * w_plane;
+  const uint32_t a_plane = (uint32_t)rowsA * 64u;
+  const uint32_t a_stage = ((2u * a_plane) + 1023u) & ~1023u;
+  const uint32_t ring = base + ((w_bytes + 1023u) & ~1023u);
+  const uint32_t bars_off = ((w_bytes + 1023u) & ~1023u) + (uint32_t)NST * a_stage;
+  const uint32_t bars = base + bars_off;
+  // fullW, fullA[NST], emptyA[NST], tfull[NBUF], tempty[NBUF]
+  constexpr int NBARS = 1 + 2 * NST + 2 * US_NBUF;
+  const uint32_t fullW = bars;
+  auto fullA = [&](int st) { return bars + (1 + st) * 8; };
+  auto emptyA = [&](int st) { return bars + (1 + NST + st) * 8; };
+  auto tfull_bar = [&](int u) { return bars + (1 + 2 * NST + u) * 8; };
+  auto tempty_bar = [&](int u) { return bars + (1 + 2 * NST + US_NBUF + u) * 8; };
+  const uint32_t tmem_slot = bars + NBARS * 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + bars_off + NBARS * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int W_PROD = US_GROUPS * US_EW, W_MMA = W_PROD + 1;
+  if (threadIdx.x == 0) {
+    mbar_init(fullW, 1);
+    for (int st = 0; st < NST; ++st) {
+      mbar_init(fullA(st), 1);
+      mbar_init(emptyA(st), 1);
+    }
+    for (int u = 0; u < US_NBUF; ++u) {
+      mbar_init(tfull_bar(u), 1);
+      mbar_init(tempty_bar(u), US_EW);
+    }
+    fence_barrier_init();
+  }
+  if (warp == W_PROD && lane == 0) {
+    tma_prefetch_desc(&mapAh);
+    tma_prefetch_desc(&mapAl);
+    tma_prefetch_desc(&mapBh);
+    tma_prefetch_desc(&mapBl);
+  }
+  if (warp == W_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == W_PROD) {
+    // ================= TMA producer =================
+    if (elect_one()) {
+      mbar_expect_tx(fullW, w_bytes);
+      for (int tap = 0; tap < d.K; ++tap) {
+        tma_load_2d(base + (uint32_t)tap * (US_C * 64u), &mapBh, fullW, 0, tap * US_C);
+        tma_load_2d(base + w_plane + (uint32_t)tap * (US_C * 64u), &mapBl, fullW, 0, tap * US_C);
+      }
+    }
+    __syncwarp();
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++g) {
+      const int mt = tile % n_mt, b = tile / n_mt;
+      const int st = g % NST;
+      mbar_wait(emptyA(st), ((g / NST) & 1u) ^ 1u);
+      const int row0 = d.m_begin + mt * UM_BM - d.pad;
+      if (elect_one()) {
+        mbar_expect_tx(fullA(st), 2u * a_plane);
+        tma_load_3d(ring + (uint32_t)st * a_stage, &mapAh, fullA(st), 0, row0, b);
+        tma_load_3d(ring + (uint32_t)st * a_stage + a_plane, &mapAl, fullA(st), 0, row0, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == W_MMA) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = umma_idesc_f16(UM_BM, US_C);
+    const uint64_t descW = umma_desc_k_sw64(base);
+    mbar_wait(fullW, 0);
+    tc_fence_after();
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++g) {
+      const int st = g % NST, u = g % US_NBUF;
+      mbar_wait(tempty_bar(u), ((g / US_NBUF) & 1u) ^ 1u);
+      mbar_wait(fullA(st), (g / NST) & 1u);
+      tc_fence_after();
+      const uint32_t acc_main = tmem_base + (uint32_t)(u * 2 * US_C);
+      const uint32_t acc_cross = acc_main + (uint32_t)US_C;
+      const uint64_t descA = umma_desc_k_sw64(ring + (uint32_t)st * a_stage);
+      if (elect_one()) {
+        for (int tap = 0; tap < d.K; ++tap) {
+          const uint64_t dAh = descA + (uint64_t)(((uint32_t)(tap * d.dil) * 64u) >> 4);  // taps share the halo block
+          const uint64_t dAl = dAh + (uint64_t)(a_plane >> 4);
+          const uint64_t dBh = descW + (uint64_t)(((uint32_t)tap * (US_C * 64u)) >> 4);
+          const uint64_t dBl = dBh + (uint64_t)(w_plane >> 4);
+#pragma unroll
+          for (int kk = 0; kk < US_C / 16; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 2);  // 16 halves = 32 bytes inside the 64-byte swizzle span
+            const uint32_t acc = (tap | kk) ? 1u : 0u;
+            umma_f16(acc_cross, dAl + adv, dBh + adv, idesc, acc);
+            umma_f16(acc_cross, dAh + adv, dBl + adv, idesc, 1u);
+            umma_f16(acc_main, dAh + adv, dBh + adv, idesc, acc);
+          }
+        }
+        umma_commit(emptyA(st));
+        umma_commit(tfull_bar(u));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue: two groups of 8 warps alternate tiles =================
+    const int grp = warp / US_EW, wl = warp % US_EW;
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++g) {
+      if ((int)(g % US_GROUPS) != grp) continue;
+      const int mt = tile % n_mt, b = tile / n_mt;
+      const int u = g % US_NBUF;
+      umma_tile_epilogue_rl<US_C, 2, US_EW>(d, 0, mt, b, u, (g / US_NBUF) & 1u, wl, lane, tmem_base, tfull_bar(u), 1, 0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(u));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---- probe: UMMA shared-memory descriptors whose start row is not a multiple of 8 --------------------------------
 // D[128][128] = A[row_off : row_off + 128][0:64] . B[0:128][0:64]^T with the A tile loaded ONCE (144 rows) and the
 // descriptor start advanced by row_off * 128 bytes.  mode 0: base_offset field 0; mode 1: base_offset =
@@ -1573,9 +1736,57 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
   return true;
 }
 
+
+bool conv1d_umma_c32_ok(const pttspp_conv1d_desc& d) {
+  return d.Cin == US_C && d.Cout == US_C && d.K >= 1 && d.K <= US_MAXK && d.in_hi && d.in_lo && d.w_hi && d.w_lo &&
+         d.in_stride == 1 && !d.in_len && !d.in_add && d.in_ld % 8 == 0 && d.in_bs % 8 == 0 && aligned16(d.in_hi) &&
+         aligned16(d.in_lo) && aligned16(d.w_hi) && aligned16(d.w_lo) && d.w_scale_inv > 0.f &&
+         UM_BM + round_up((d.K - 1) * d.dil, 8) <= 256 && epilogue_rl_ok(d);
+}
+
+void conv1d_umma_c32_launch(const pttspp_conv1d_desc& d_in, cudaStream_t s) {
+  pttspp_conv1d_desc d = d_in;
+  d.acc_scale = d_in.acc_scale * d_in.w_scale_inv;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    PT_CUDA(cudaGetDevice(&dev));
+    PT_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int rowsA = UM_BM + round_up((d.K - 1) * d.dil, 8);
+  const uint64_t wdims[2] = {(uint64_t)US_C, (uint64_t)d.K * US_C};
+  const uint64_t wstr[1] = {(uint64_t)US_C * 2};
+  const uint32_t wbox[2] = {US_C, US_C};
+  const CUtensorMap mBh = make_map(d.w_hi, 2, wdims, wstr, wbox, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
+  const CUtensorMap mBl = make_map(d.w_lo, 2, wdims, wstr, wbox, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
+  const uint64_t adims[3] = {(uint64_t)US_C, (uint64_t)d.T_in, (uint64_t)d.B};
+  const uint64_t astr[2] = {(uint64_t)d.in_ld * 2, (uint64_t)d.in_bs * 2};
+  const uint32_t abox[3] = {US_C, (uint32_t)rowsA, 1};
+  const CUtensorMap mAh = make_map(d.in_hi, 3, adims, astr, abox, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
+  const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
+  constexpr int NST = 6;
+  const size_t w_bytes = round_up(2 * d.K * US_C * 64, 1024);
+  const size_t a_stage = round_up(2 * rowsA * 64, 1024);
+  const size_t smem = w_bytes + NST * a_stage + (1 + 2 * NST + 2 * US_NBUF) * 8 + 16 + 1024;
+  auto kern = conv1d_umma_c32_kernel<NST>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  PT_CHECK(smem <= 227 * 1024, "conv1d c32: shared memory budget exceeded");
+  const int n_mt = ceil_div(d.M, UM_BM);
+  const long long n_tiles = (long long)n_mt * d.B;
+  PT_CHECK(n_tiles < (1ll << 30), "conv1d: too many tiles");
+  const int grid = (int)std::min<long long>(n_tiles, num_sms);
+  kern<<<grid, US_THREADS, smem, s>>>(mAh, mAl, mBh, mBl, d, n_mt, (int)n_tiles, rowsA);
+  PT_LAUNCHED();
+}
+
 }  // namespace
 
 bool conv1d_umma_supported(const pttspp_conv1d_desc& d) {
+  if (conv1d_umma_c32_ok(d)) return true;
   return d.in_hi && d.in_lo && d.w_hi && d.w_lo && d.Cin % UM_BK == 0 && d.in_stride == 1 && !d.in_len && !d.in_add &&
          d.in_ld % 8 == 0 && d.in_bs % 8 == 0 && aligned16(d.in_hi) && aligned16(d.in_lo) && aligned16(d.w_hi) &&
          aligned16(d.w_lo) && d.w_scale_inv > 0.f;
@@ -1718,7 +1929,10 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
   PT_LAUNCHED();
 }
 
-void conv1d_umma_cl(const pttspp_conv1d_desc& d, cudaStream_t s) { conv1d_umma_launch(d, nullptr, s); }
+void conv1d_umma_cl(const pttspp_conv1d_desc& d, cudaStream_t s) {
+  if (conv1d_umma_c32_ok(d)) conv1d_umma_c32_launch(d, s);
+  else conv1d_umma_launch(d, nullptr, s);
+}
 
 void conv1d_umma_dual_cl(const pttspp_conv1d_desc& d1, const pttspp_conv1d_desc& d2, cudaStream_t s) {
   PT_CHECK(conv1d_umma_supported(d1) && conv1d_umma_supported(d2), "conv1d dual launch: unsupported descriptor");

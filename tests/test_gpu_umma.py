@@ -58,6 +58,13 @@ UMMA_CASES = [
     (64, 64, 11, 5, 1, 12000),
     (256, 256, 17, 1, 4, 2500),   # frame-prior shape: halo of 16 rows
     (256, 256, 5, 1, 4, 2500),
+    # 32 channels: weight-resident SWIZZLE_64B kernel (BigVGAN's last stage)
+    (32, 32, 3, 1, 2, 1000),
+    (32, 32, 3, 5, 2, 3001),
+    (32, 32, 7, 3, 1, 5000),
+    (32, 32, 11, 1, 3, 2999),
+    (32, 32, 11, 5, 2, 40000),
+    (32, 32, 1, 1, 1, 77),
 ]
 
 
