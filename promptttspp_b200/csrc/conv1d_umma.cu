@@ -60,6 +60,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// warp-uniform wait for the single-issuer warps: one lane polls, the warp re-converges (32 lanes polling the same
+// barrier serialise in the barrier unit and slowed the short-stage kernels down)
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -295,7 +301,7 @@ __device__ __forceinline__ void umma_tile_epilogue_co(const pttspp_conv1d_desc& 
       }
     }
   }
-  mbar_wait(tfull, tparity);
+  mbar_wait_warp(tfull, tparity);
   tc_fence_after();
   if (dbg & 64) return;  // experiment: mainloop only
   const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * NACC * BN);
@@ -462,7 +468,7 @@ __device__ __forceinline__ void umma_tile_epilogue_rl(const pttspp_conv1d_desc& 
   f8 pre[NCH][2];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) epi_rl_load_operand(de, b, row, ok && !(dbg & 4), n0 + cbeg + 16 * c, pre[c]);
-  mbar_wait(tfull, tparity);
+  mbar_wait_warp(tfull, tparity);
   tc_fence_after();
   if (dbg & 64) return;
   const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * NACC * BN);
@@ -617,7 +623,7 @@ __device__ __forceinline__ void umma_tile_epilogue(const pttspp_conv1d_desc& de,
   const bool v1 = vec && row_ok && n0 + cbeg + 32 <= de.Cout;
   if (v0) conv_epilogue16_load(de, b, row, n0 + cbeg, ops0);
   if (CW == 32 && v1) conv_epilogue16_load(de, b, row, n0 + cbeg + 16, ops1);
-  mbar_wait(tfull, ((uint32_t)i >> 1) & 1u);
+  mbar_wait_warp(tfull, ((uint32_t)i >> 1) & 1u);
   tc_fence_after();
   const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * NACC * BN);
 #pragma unroll
@@ -708,7 +714,10 @@ __device__ __forceinline__ void umma_tile_epilogue(const pttspp_conv1d_desc& de,
 // Persistent, warp-specialised: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA and MMA warps
 // run ahead into the next tile while the eight epilogue warps drain the previous accumulator: TMEM holds two
 // accumulator buffers of (main | cross-term) x BN columns.
-template <int BN, int STAGES, int NACC>
+// EPI: 0 = TMA bulk-store / direct epilogue, 1 = coalescing epilogue.  DUAL: the launch carries a second epilogue
+// descriptor.  Both are compile-time so that a kernel holds exactly one epilogue body per descriptor (with both
+// variants inlined the 96-register budget spilled ~2 KB per thread and the narrow kernel lost 25 %).
+template <int BN, int STAGES, int NACC, int EPI, bool DUAL>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                    const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
@@ -774,7 +783,7 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
         for (int it = 0; it < n_iter; ++it, ++g) {
           const int s = g % STAGES;
           const uint32_t ph = (g / STAGES) & 1u;
-          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_wait_warp(empty_bar(s), ph ^ 1u);
           const int slab = it / d.K, tap = it % d.K;  // taps innermost: the shifted row windows overlap in L2
           const uint32_t st = base + s * SM::STAGE_BYTES;
           const int row = m0 + tap * d.dil - d.pad;
@@ -798,7 +807,7 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
       int i = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
         const int u = i & 1;
-        mbar_wait(tempty_bar(u), (((uint32_t)i >> 1) & 1u) ^ 1u);  // epilogue has drained this buffer
+        mbar_wait_warp(tempty_bar(u), (((uint32_t)i >> 1) & 1u) ^ 1u);  // epilogue has drained this buffer
         tc_fence_after();
         // The tensor core truncates when it adds into the fp32 accumulator, so the error grows linearly with the
         // number of accumulations into one accumulator: the 2^-11 smaller cross terms (hi*lo, lo*hi) get their
@@ -810,7 +819,7 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
         for (int it = 0; it < n_iter; ++it, ++g) {
           const int s = g % STAGES;
           const uint32_t ph = (g / STAGES) & 1u;
-          mbar_wait(full_bar(s), ph);
+          mbar_wait_warp(full_bar(s), ph);
           tc_fence_after();
           // descriptors of this stage: only the 14-bit start-address field differs from the stage-0 descriptor
           const uint64_t dAh = desc0 + (uint64_t)((uint32_t)s * (uint32_t)(SM::STAGE_BYTES >> 4));
@@ -839,21 +848,20 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
     int i = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
       const int nt = tile % n_nt, mt = (tile / n_nt) % n_mt, b = tile / (n_nt * n_mt);
-      if (tma_out & 4) {
+      const int nm = n_iter < NACC - 1 ? n_iter : NACC - 1;
+      const bool second = DUAL && nt * BN >= cout1;  // CTA-uniform branch: each side reads its descriptor with immediates
+      if constexpr (EPI == 1) {
         float* stg = reinterpret_cast<float*>(gen_base + STAGES * SM::STAGE_BYTES + 256 + warp * 2048);
-        const int nm = n_iter < NACC - 1 ? n_iter : NACC - 1;
-        if (nt * BN >= cout1)  // CTA-uniform branch: each side reads its descriptor with immediate constant operands
-          umma_tile_epilogue_co<BN, NACC, UM_EPI_WARPS>(d2, nt * BN - cout1, mt, b, i & 1, ((uint32_t)i >> 1) & 1u, warp, lane, tmem_base,
-                                                        tfull_bar(i & 1), nm, stg, 0);
+        if (second)
+          umma_tile_epilogue_co<BN, NACC, UM_EPI_WARPS>(d2, nt * BN - cout1, mt, b, i & 1, ((uint32_t)i >> 1) & 1u, warp,
+                                                        lane, tmem_base, tfull_bar(i & 1), nm, stg, 0);
         else
-          umma_tile_epilogue_co<BN, NACC, UM_EPI_WARPS>(d, nt * BN, mt, b, i & 1, ((uint32_t)i >> 1) & 1u, warp, lane, tmem_base, tfull_bar(i & 1),
-                                                        nm, stg, 0);
-      }
-      else {
+          umma_tile_epilogue_co<BN, NACC, UM_EPI_WARPS>(d, nt * BN, mt, b, i & 1, ((uint32_t)i >> 1) & 1u, warp, lane,
+                                                        tmem_base, tfull_bar(i & 1), nm, stg, 0);
+      } else {
         uint8_t* stg = gen_base + STAGES * SM::STAGE_BYTES + 256 + warp * 2048;
         const uint32_t stg_u32 = base + STAGES * SM::STAGE_BYTES + 256 + warp * 2048;
-        const int nm = n_iter < NACC - 1 ? n_iter : NACC - 1;
-        if (nt * BN >= cout1)
+        if (second)
           umma_tile_epilogue<BN, NACC>(d2, nt * BN - cout1, vec_ok, mt, b, i, warp, lane, tmem_base, tfull_bar(i & 1), nm,
                                        &om2, (tma_out & 2) != 0, stg, stg_u32);
         else
@@ -1165,7 +1173,7 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
         for (int slab = 0; slab < nslab; ++slab) {
           if (new_unit) {
             // this slab of the previous unit has been consumed (released early in that unit's last tile)
-            mbar_wait(emptyA(slab), ((uint32_t)ablk & 1u) ^ 1u);
+            mbar_wait_warp(emptyA(slab), ((uint32_t)ablk & 1u) ^ 1u);
             if (elect_one()) {
               if (rank == 0) mbar_expect_tx(fullA(slab), 4u * a_plane);
               tma_load_3d_pair(base + (uint32_t)(2 * slab) * a_plane, &mapAh, fullA(slab), slab * UM_BK, row0, b);
@@ -1176,7 +1184,7 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
           for (int tap = 0; tap < d.K; ++tap, ++g) {
             const int st = g % NBST;
             const uint32_t ph = (g / NBST) & 1u;
-            mbar_wait(emptyB(st), ph ^ 1u);
+            mbar_wait_warp(emptyB(st), ph ^ 1u);
             const uint32_t dst = ring + (uint32_t)st * UP_BST_BYTES;
             const int wrow = tap * cout_total + nt * UP_BN + (int)rank * UP_BHALF;
             if (elect_one()) {
@@ -1203,20 +1211,20 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
         cur_unit = unit;
         const bool last_of_unit = (t + 1 == t_end) || ((t + 1) / n_nt != unit);
         const int u = i % NBUF;
-        mbar_wait(tempty_bar(u), (((uint32_t)i / NBUF) & 1u) ^ 1u);  // both CTAs' epilogues have drained buffer u
+        mbar_wait_warp(tempty_bar(u), (((uint32_t)i / NBUF) & 1u) ^ 1u);  // both CTAs' epilogues have drained buffer u
         tc_fence_after();
         const uint32_t acc_main = tmem_base + (uint32_t)(u * NACC * UP_BN);
         const uint32_t acc_cross = acc_main + (uint32_t)((NACC - 1) * UP_BN);  // NACC == 1: the same accumulator
         uint32_t first = 0;
         for (int slab = 0; slab < nslab; ++slab) {
           if (new_unit) {
-            mbar_wait(fullA(slab), (uint32_t)ablk & 1u);
+            mbar_wait_warp(fullA(slab), (uint32_t)ablk & 1u);
             tc_fence_after();
           }
           for (int tap = 0; tap < d.K; ++tap, ++g) {
             const int st = g % NBST;
             const uint32_t ph = (g / NBST) & 1u;
-            mbar_wait(fullB(st), ph);
+            mbar_wait_warp(fullB(st), ph);
             tc_fence_after();
             const uint32_t a_off = (uint32_t)(2 * slab) * a_plane + (uint32_t)(tap * d.dil) * 128u;  // taps share the halo tile
             const uint64_t dAh = desc0 + (uint64_t)(a_off >> 4);
@@ -1401,7 +1409,7 @@ conv1d_umma_c32_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_c
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++g) {
       const int mt = tile % n_mt, b = tile / n_mt;
       const int st = g % NST;
-      mbar_wait(emptyA(st), ((g / NST) & 1u) ^ 1u);
+      mbar_wait_warp(emptyA(st), ((g / NST) & 1u) ^ 1u);
       const int row0 = d.m_begin + mt * UM_BM - d.pad;
       if (elect_one()) {
         mbar_expect_tx(fullA(st), 2u * a_plane);
@@ -1414,13 +1422,13 @@ conv1d_umma_c32_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_c
     // ================= MMA issuer =================
     constexpr uint32_t idesc = umma_idesc_f16(UM_BM, US_C);
     const uint64_t descW = umma_desc_k_sw64(base);
-    mbar_wait(fullW, 0);
+    mbar_wait_warp(fullW, 0);
     tc_fence_after();
     uint32_t g = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++g) {
       const int st = g % NST, u = g % US_NBUF;
-      mbar_wait(tempty_bar(u), ((g / US_NBUF) & 1u) ^ 1u);
-      mbar_wait(fullA(st), (g / NST) & 1u);
+      mbar_wait_warp(tempty_bar(u), ((g / US_NBUF) & 1u) ^ 1u);
+      mbar_wait_warp(fullA(st), (g / NST) & 1u);
       tc_fence_after();
       const uint32_t acc_main = tmem_base + (uint32_t)(u * 2 * US_C);
       const uint32_t acc_cross = acc_main + (uint32_t)US_C;
@@ -1898,10 +1906,11 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
     const CUtensorMap mBh64 = make_map(d.w_hi, 2, wdims, wstr, wbox64);
     const CUtensorMap mBl64 = make_map(d.w_lo, 2, wdims, wstr, wbox64);
     const size_t smem = (size_t)ST * UmmaSmem<BN>::STAGE_BYTES + 256 + UM_EPI_WARPS * 2048 + 1024;
-    auto kern = conv1d_umma_kernel<BN, ST, NA>;
+    auto kern = (tma_out & 4) ? conv1d_umma_kernel<BN, ST, NA, 1, false> : conv1d_umma_kernel<BN, ST, NA, 0, false>;
     static bool attr_set = false;
     if (!attr_set) {
-      PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PT_CUDA(cudaFuncSetAttribute(conv1d_umma_kernel<BN, ST, NA, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PT_CUDA(cudaFuncSetAttribute(conv1d_umma_kernel<BN, ST, NA, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set = true;
     }
     const int nnt = ceil_div(total_cout, BN);
@@ -1915,10 +1924,16 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
   }
   using SM = UmmaSmem<UM_BN>;
   const size_t smem = (size_t)UM_STAGES * SM::STAGE_BYTES + 256 + UM_EPI_WARPS * 2048 + 1024;
-  auto kern = conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC>;
+  auto kern = d2_in ? ((tma_out & 4) ? conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC, 1, true>
+                                     : conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC, 0, true>)
+                    : ((tma_out & 4) ? conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC, 1, false>
+                                     : conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC, 0, false>);
   static bool attr_set = false;
   if (!attr_set) {
-    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PT_CUDA(cudaFuncSetAttribute(conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PT_CUDA(cudaFuncSetAttribute(conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PT_CUDA(cudaFuncSetAttribute(conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PT_CUDA(cudaFuncSetAttribute(conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const long long n_tiles = (long long)n_mt * n_nt * d.B;
