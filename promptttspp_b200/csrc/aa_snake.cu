@@ -20,32 +20,27 @@ constexpr int TT = 16;          // outputs per thread
 constexpr int NX = TT + 10;     // input samples per strip
 constexpr int NS = 2 * TT + 10; // up-sampled samples per strip
 
-// y (fp32) and/or split-fp16 planes y_hi/y_lo (operands of the tcgen05 convs that consume the activation)
-__global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                       __half* __restrict__ y_hi, __half* __restrict__ y_lo, int L,
-                                                       int C, const float* __restrict__ log_alpha,
-                                                       const float* __restrict__ up_f,
-                                                       const float* __restrict__ down_f) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  const int t0 = (blockIdx.y * blockDim.y + threadIdx.y) * TT;
-  const int b = blockIdx.z;
-  if (c >= C || t0 >= L) return;
-  float f[12], g[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) {
-    f[i] = up_f[i];
-    g[i] = down_f[i];
-  }
-  const float alpha = expf(log_alpha[c]);
-  const float inv_alpha = 1.f / (alpha + 1e-9f);
-  const float* xb = x + (int64_t)b * L * C + c;
-
+// y (fp32) and/or split-fp16 planes y_hi/y_lo (operands of the tcgen05 convs that consume the activation).
+// f2 = 2 * up filter (the x2 gain folded in: exact).  EDGE = false: strips whose halo lies inside [0, L) -- no index
+// clamps, no replicate fix-ups (the kernel is instruction bound, ncu: SM 79 % busy at 1.8 TB/s, so every removed
+// instruction is time); EDGE = true: the general path for the first / last strips of an utterance.
+template <bool EDGE>
+__device__ __forceinline__ void aa_snake_strip(const float* __restrict__ xb, float* __restrict__ y,
+                                               __half* __restrict__ y_hi, __half* __restrict__ y_lo, int64_t ob, int t0,
+                                               int L, int C, const float (&f2)[12], const float (&g)[12], float a2,
+                                               float inv_alpha) {
   float xs[NX];
+  if (EDGE) {
 #pragma unroll
-  for (int i = 0; i < NX; ++i) {
-    int l = t0 - 5 + i;
-    l = l < 0 ? 0 : (l > L - 1 ? L - 1 : l);
-    xs[i] = xb[(int64_t)l * C];
+    for (int i = 0; i < NX; ++i) {
+      int l = t0 - 5 + i;
+      l = l < 0 ? 0 : (l > L - 1 ? L - 1 : l);
+      xs[i] = xb[(int64_t)l * C];
+    }
+  } else {
+    const float* xp = xb + (int64_t)(t0 - 5) * C;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xs[i] = xp[(int64_t)i * C];
   }
   // up-sample + snake.  s[i] <-> up-sampled index m = 2*t0 - 5 + i:
   //   i even -> m odd,  j = t0 - 3 + i/2, taps x[j-2+d] = xs[i/2 + d],      filter f[10-2d]
@@ -56,46 +51,71 @@ __global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__
     float u = 0.f;
     if ((i & 1) == 0) {
 #pragma unroll
-      for (int dd = 0; dd < 6; ++dd) u = fmaf(xs[i / 2 + dd], f[10 - 2 * dd], u);
+      for (int dd = 0; dd < 6; ++dd) u = fmaf(xs[i / 2 + dd], f2[10 - 2 * dd], u);
     } else {
 #pragma unroll
-      for (int dd = 0; dd < 6; ++dd) u = fmaf(xs[(i - 1) / 2 + dd], f[11 - 2 * dd], u);
+      for (int dd = 0; dd < 6; ++dd) u = fmaf(xs[(i - 1) / 2 + dd], f2[11 - 2 * dd], u);
     }
-    u *= 2.f;
-    // MUFU sine after an explicit 2*pi range reduction: |error| < 1e-6 over the activations' range, far inside the
-    // 1e-4 RMS waveform bar; the libm sinf slow path made this kernel instruction bound
-    const float arg = u * alpha;
-    const float kq = rintf(arg * 0.15915494309189535f);           // Cody-Waite: 2*pi = hi + lo, two FMAs
-    float red = fmaf(-kq, 6.28318548202514648f, arg);              // fp32(2*pi)
-    red = fmaf(-kq, -1.74845553146951715e-07f, red);               // 2*pi - fp32(2*pi)
-    const float sn = __sinf(red);
-    sv[i] = u + inv_alpha * (sn * sn);
+    // sin(alpha*u) with the argument reduced in REVOLUTIONS: r = u * alpha/(2*pi), frac = r - rint(r) is exact, and
+    // the MUFU sine of 2*pi*frac in [-pi, pi] is accurate to 2^-21 -- |error| < 1e-6 over the activations' range, far
+    // inside the 1e-4 RMS waveform bar (libm sinf's slow path made this kernel instruction bound)
+    const float r = u * a2;
+    const float frac = r - rintf(r);
+    const float sn = __sinf(frac * 6.28318530717958648f);
+    sv[i] = fmaf(inv_alpha * sn, sn, u);
   }
-  // replicate padding of the up-sampled signal: indices below 0 / above 2L-1 repeat the edge value
+  if (EDGE) {
+    // replicate padding of the up-sampled signal: indices below 0 / above 2L-1 repeat the edge value
 #pragma unroll
-  for (int i = 4; i >= 0; --i)
-    if (2 * t0 - 5 + i < 0) sv[i] = sv[i + 1];
-  const int imax = 2 * (L - t0) + 4;  // strip index of up-sampled sample 2L-1
+    for (int i = 4; i >= 0; --i)
+      if (2 * t0 - 5 + i < 0) sv[i] = sv[i + 1];
+    const int imax = 2 * (L - t0) + 4;  // strip index of up-sampled sample 2L-1
 #pragma unroll
-  for (int i = 1; i < NS; ++i)
-    if (i > imax) sv[i] = sv[i - 1];
-
-  const int64_t ob = (int64_t)b * L * C + c;
+    for (int i = 1; i < NS; ++i)
+      if (i > imax) sv[i] = sv[i - 1];
+  }
+  float* yp = y ? y + ob : nullptr;
+  __half* hp = y_hi ? y_hi + ob : nullptr;
+  __half* lp = y_hi ? y_lo + ob : nullptr;
 #pragma unroll
   for (int t = 0; t < TT; ++t) {
-    if (t0 + t < L) {
+    if (!EDGE || t0 + t < L) {
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < 12; ++k) acc = fmaf(sv[2 * t + k], g[k], acc);
-      const int64_t o = ob + (int64_t)(t0 + t) * C;
-      if (y) y[o] = acc;
-      if (y_hi) {
+      if (yp) yp[(int64_t)t * C] = acc;
+      if (hp) {
         const __half h = __float2half_rn(acc);
-        y_hi[o] = h;
-        y_lo[o] = __float2half_rn(acc - __half2float(h));
+        hp[(int64_t)t * C] = h;
+        lp[(int64_t)t * C] = __float2half_rn(acc - __half2float(h));
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                       __half* __restrict__ y_hi, __half* __restrict__ y_lo, int L,
+                                                       int C, const float* __restrict__ log_alpha,
+                                                       const float* __restrict__ up_f,
+                                                       const float* __restrict__ down_f) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int t0 = (blockIdx.y * blockDim.y + threadIdx.y) * TT;
+  const int b = blockIdx.z;
+  if (c >= C || t0 >= L) return;
+  float f2[12], g[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    f2[i] = 2.f * up_f[i];
+    g[i] = down_f[i];
+  }
+  const float alpha = expf(log_alpha[c]);
+  const float inv_alpha = 1.f / (alpha + 1e-9f);
+  const float a2 = alpha * 0.15915494309189535f;
+  const float* xb = x + (int64_t)b * L * C + c;
+  const int64_t ob = (int64_t)b * L * C + c + (int64_t)t0 * C;
+  // warp-uniform: a warp spans 32 channels of ONE strip
+  if (t0 >= 5 && t0 + TT + 5 <= L) aa_snake_strip<false>(xb, y, y_hi, y_lo, ob, t0, L, C, f2, g, a2, inv_alpha);
+  else aa_snake_strip<true>(xb, y, y_hi, y_lo, ob, t0, L, C, f2, g, a2, inv_alpha);
 }
 
 }  // namespace

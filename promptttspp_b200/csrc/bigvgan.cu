@@ -25,6 +25,9 @@ struct UpsampleW {
   float* w = nullptr;  // [stride][J][Cin][w_ld]
   float* bias = nullptr;
   int Cin = 0, Cout = 0, Kt = 0, stride = 0, pad = 0, out_pad = 0, J = 0, w_ld = 0;
+  // tcgen05 path: per phase r the 2-tap conv's split-fp16 weight planes [J][Cout][Cin] (+ its power-of-two scale)
+  std::vector<void*> w_hi, w_lo;
+  std::vector<float> w_scale_inv;
 };
 
 }  // namespace pttspp
@@ -39,6 +42,7 @@ struct pttspp_bigvgan {
   std::vector<pttspp::UpsampleW> ups;
   std::vector<std::vector<std::vector<pttspp::AMPLayerW>>> mrfs;  // [stage][kernel][layer]
   pttspp::AAParams act_post;
+  float* post_w = nullptr;  // conv_post weight as [K][C] for the dedicated C -> 1 kernel
 };
 
 namespace pttspp {
@@ -70,6 +74,61 @@ int64_t max_stage_elems(const pttspp_bigvgan_config& c, int B, int T) {
     mx = std::max(mx, L * stage_channels(c, i + 1));
   }
   return mx * B;
+}
+
+
+// conv_post (C = 32 -> 1, k taps) + tanh, HBM bound (reads C floats per output sample): a warp owns a strip of
+// output samples, lane = channel, the k-row window slides through registers, one shuffle reduction per sample and
+// one coalesced 128-byte store per 32 samples.  Replaces bigvgan.py:129-131 for the 32-channel last stage; the generic
+// implicit-GEMM kernel spent 1.7 ms on this N = 1 contraction (ncu launch list, profiles/).
+constexpr int POST_STRIP = 128;  // outputs per warp
+template <int K>
+__global__ void __launch_bounds__(256) conv_post_tanh_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ out,
+                                                             int L, int strips_per_row) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int b = warp / strips_per_row, t0 = (warp - b * strips_per_row) * POST_STRIP;
+  if (t0 >= L) return;
+  constexpr int P = K / 2;
+  float wk[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) wk[k] = w[k * 32 + lane];
+  const float bz = bias ? bias[0] : 0.f;
+  const float* xb = x + (int64_t)b * L * 32 + lane;
+  float win[K];  // win[k] = x[t + k - P] for the current output t
+#pragma unroll
+  for (int k = 0; k < K - 1; ++k) {
+    const int l = t0 + k - P;
+    win[k + 1] = (l >= 0 && l < L) ? xb[(int64_t)l * 32] : 0.f;
+  }
+  float keep = 0.f;
+  for (int tt = 0; tt < POST_STRIP; ++tt) {
+    const int t = t0 + tt;
+#pragma unroll
+    for (int k = 0; k < K - 1; ++k) win[k] = win[k + 1];
+    const int l = t + P;
+    win[K - 1] = (l < L) ? xb[(int64_t)l * 32] : 0.f;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc = fmaf(win[k], wk[k], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((tt & 31) == lane) keep = acc;
+    if ((tt & 31) == 31) {
+      const int to = t - 31 + lane;
+      if (to < L) out[(int64_t)b * L + to] = tanhf(keep + bz);
+    }
+  }
+}
+
+void conv_post_tanh(const float* x, const float* w, const float* bias, float* out, int B, int L, int K, cudaStream_t s) {
+  const int strips = ceil_div(L, POST_STRIP);
+  const long long warps = (long long)B * strips;
+  ProfScope prof(PROF_OTHER, s, 0.0, 4.0 * B * (double)L * 33);
+  const unsigned blocks = (unsigned)ceil_div64(warps * 32, 256);
+  PT_CHECK(K == 7, "conv_post kernel is instantiated for k = 7");
+  conv_post_tanh_kernel<7><<<blocks, 256, 0, s>>>(x, w, bias, out, L, strips);
+  PT_LAUNCHED();
 }
 
 }  // namespace
@@ -144,6 +203,22 @@ extern "C" int pttspp_bigvgan_finalize(pttspp_bigvgan_t* h, pttspp_stream_t) {
                          u.Cin, u.Cout, u.Kt, u.stride, packed.data(), u.w_ld, 0);
     u.w = h->dev.upload(packed);
     u.bias = h->dev.upload(h->store.get(p + ".bias", u.Cout).data);
+    if (h->use_umma && u.Cin % 64 == 0 && u.Cout % 16 == 0) {
+      // per phase: the [J][Cin][Cout] taps as a torch-layout conv weight [Cout][Cin][J] -> split-fp16 planes
+      std::vector<float> wt((size_t)u.Cout * u.Cin * u.J);
+      std::vector<uint16_t> hi(wt.size()), lo(wt.size());
+      for (int r = 0; r < u.stride; ++r) {
+        for (int kp = 0; kp < u.J; ++kp)
+          for (int ci = 0; ci < u.Cin; ++ci)
+            for (int co = 0; co < u.Cout; ++co)
+              wt[((size_t)co * u.Cin + ci) * u.J + kp] = packed[(((size_t)r * u.J + kp) * u.Cin + ci) * u.w_ld + co];
+        float sc = 0.f;
+        pack_conv_weight_split(wt.data(), nullptr, u.Cout, u.Cin, u.J, hi.data(), lo.data(), 0, &sc);
+        u.w_hi.push_back(h->dev.upload_bytes(hi.data(), hi.size() * 2));
+        u.w_lo.push_back(h->dev.upload_bytes(lo.data(), lo.size() * 2));
+        u.w_scale_inv.push_back(sc);
+      }
+    }
     h->ups.push_back(u);
 
     std::vector<std::vector<AMPLayerW>> stage;
@@ -171,6 +246,15 @@ extern "C" int pttspp_bigvgan_finalize(pttspp_bigvgan_t* h, pttspp_stream_t) {
   const int Cl = C0 >> c.num_upsamples;
   h->act_post = load_aa(h->store, h->dev, "act_post", Cl);
   h->conv_post = load_conv1d(h->store, h->dev, "conv_post", 1, Cl, 7, 1, 3);
+  h->post_w = nullptr;
+  if (Cl == 32) {  // [1][C][7] (weight or weight-norm pair, folded by load_conv1d into packed [K][C][w_ld]) -> [K][C]
+    std::vector<float> host((size_t)7 * h->conv_post.Cin * h->conv_post.w_ld);
+    PT_CUDA(cudaMemcpy(host.data(), h->conv_post.w, host.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    std::vector<float> kc((size_t)7 * 32);
+    for (int k = 0; k < 7; ++k)
+      for (int ci = 0; ci < 32; ++ci) kc[(size_t)k * 32 + ci] = host[((size_t)k * 32 + ci) * h->conv_post.w_ld];
+    h->post_w = h->dev.upload(kc);
+  }
   h->finalized = true;
   PT_API_END
 }
@@ -198,8 +282,19 @@ extern "C" int pttspp_bigvgan_forward(pttspp_bigvgan_t* h, const float* mel, int
 
   // mel [B][C][T] -> [B][T][C]; conv_pre
   transpose_bct_to_btc(mel, t1, B, c.in_channel, T, s);
+  // operand planes of the current stage input (for the tensor-core transposed convs) live in the t2 region, which
+  // is free whenever a stage's last conv or conv_pre runs: hi = first half, lo = second half
+  auto stage_planes = [&](int64_t n_elems, uint16_t*& ph, uint16_t*& pl) {
+    ph = reinterpret_cast<uint16_t*>(t2);
+    pl = ph + n_elems;
+  };
   {
     auto d = conv_desc(h->conv_pre, t1, B, T, bxs);
+    if (!h->ups[0].w_hi.empty()) {
+      uint16_t *ph, *pl;
+      stage_planes((int64_t)B * T * h->conv_pre.Cout, ph, pl);
+      d.out_hi = ph; d.out_lo = pl; d.out_plane_bs = (int64_t)T * h->conv_pre.Cout; d.out_plane_ld = h->conv_pre.Cout;
+    }
     conv1d_cl(d, s);
   }
   int L = T;
@@ -221,6 +316,11 @@ extern "C" int pttspp_bigvgan_forward(pttspp_bigvgan_t* h, const float* mel, int
       d.M = m_end - d.m_begin + 1;
       d.out_mul = u.stride; d.out_off = off;
       d.acc_scale = 1.f; d.res_scale = 1.f; d.alpha = 1.f; d.beta = 0.f; d.B = B;
+      if (!u.w_hi.empty()) {
+        uint16_t *ph, *pl;
+        stage_planes((int64_t)B * L * u.Cin, ph, pl);
+        d.in_hi = ph; d.in_lo = pl; d.w_hi = u.w_hi[r]; d.w_lo = u.w_lo[r]; d.w_scale_inv = u.w_scale_inv[r]; d.impl = 2;
+      }
       conv1d_cl(d, s);
     }
     L = Lout;
@@ -253,7 +353,15 @@ extern "C" int pttspp_bigvgan_forward(pttspp_bigvgan_t* h, const float* mel, int
         d.res = cur; d.res_bs = (int64_t)L * C; d.res_ld = C;
         if (last) {  // xs = (j ? xs : 0) + (x + y); the last block divides by num_kernels (bigvgan.py:124-127)
           d.beta = (j == 0) ? 0.f : 1.f;
-          if (j == c.num_kernels - 1) d.out_div = (float)c.num_kernels;
+          if (j == c.num_kernels - 1) {
+            d.out_div = (float)c.num_kernels;
+            if (i + 1 < c.num_upsamples && !h->ups[i + 1].w_hi.empty()) {
+              // the finished stage output also leaves as operand planes for the next transposed conv
+              uint16_t *oh, *ol;
+              stage_planes((int64_t)B * L * C, oh, ol);
+              d.out_hi = oh; d.out_lo = ol; d.out_plane_bs = (int64_t)L * C; d.out_plane_ld = C;
+            }
+          }
         }
         conv1d_cl(d, s);
         cur = dst;
@@ -264,7 +372,9 @@ extern "C" int pttspp_bigvgan_forward(pttspp_bigvgan_t* h, const float* mel, int
   }
   const int Cl = c.upsample_initial_channel >> c.num_upsamples;
   aa_snake_cl(hcur, t1, B, L, Cl, h->act_post.log_alpha, h->act_post.up_f, h->act_post.down_f, s);
-  {
+  if (h->post_w && Cl == 32) {
+    conv_post_tanh(t1, h->post_w, h->conv_post.bias, wav, B, L, 7, s);
+  } else {
     auto d = conv_desc(h->conv_post, t1, B, L, wav);
     d.act = PTTSPP_ACT_TANH;
     conv1d_cl(d, s);

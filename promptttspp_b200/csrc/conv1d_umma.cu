@@ -445,6 +445,25 @@ __device__ __forceinline__ void epi_rl_load_operand(const pttspp_conv1d_desc& de
     dst[1] = ldg256(src + col + 8);
   }
 }
+// L2 prefetch of the NEXT tile's operand rows by the epilogue warps themselves (one 128-byte line per lane and
+// 32-column slice: no registers, no TMA queue), so that DRAM latency is paid one tile ahead
+template <int BN, int EW>
+__device__ __forceinline__ void epi_rl_prefetch_tile(const pttspp_conv1d_desc& de, int n0, int mt, int b, int warp, int lane) {
+  const int kind = conv_epilogue_prefetch_kind(de);
+  if (kind == 0) return;
+  constexpr int CW = BN / (EW / 4);
+  const int q = warp & 3, cbeg = (warp >> 2) * CW;
+  const int m = de.m_begin + mt * UM_BM + q * 32 + lane;
+  const int row = m * de.out_mul + de.out_off;
+  if (!((m < de.m_begin + de.M) && row >= 0 && row < de.T_out)) return;
+  const float* src = (kind == 1) ? de.addend + (int64_t)b * de.addend_bs + (int64_t)row * de.addend_ld
+                   : (kind == 2) ? de.res + (int64_t)b * de.res_bs + (int64_t)row * de.res_ld
+                                 : de.out + (int64_t)b * de.out_bs + (int64_t)row * de.out_ld;
+#pragma unroll
+  for (int c = 0; c < CW; c += 32)
+    if (n0 + cbeg + c < de.Cout) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + n0 + cbeg + c));
+}
+
 // (A rolling prefetch of the NEXT tile's operand chunks into the registers of consumed chunks was tried and measured
 // slower: the longer live ranges spill at the 96-register budget of the 18-warp CTA.)
 template <int BN, int NACC, int EW>
@@ -1146,7 +1165,7 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
         cur_unit = unit;
         const int b = unit / n_mt2, mt2 = unit - b * n_mt2;
         const int row0 = d.m_begin + mt2 * (2 * UM_BM) + (int)rank * UM_BM - d.pad;
-        if (mma_order & 16) {  // experiment (measured harmful: the bulk prefetches queue in front of the TMA loads)
+        if (mma_order & 128) {  // experiment (measured harmful: the bulk prefetches queue in front of the TMA loads)
           // The producer runs one to two tiles ahead of the epilogue: pull the epilogue's operand tile (conditioner /
           // residual / previous output, 128 rows x 512 B) into L2 now, so that the epilogue's loads are L2 hits.
           const bool second = nt * UP_BN >= cout1;
@@ -1282,6 +1301,12 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
       const uint32_t tpar = ((uint32_t)i / NBUF) & 1u;
       // CTA-uniform branches: each call reads ITS descriptor(s) with immediate constant operands
       if (epi_rl) {
+        if (t + 1 < t_end && !(mma_order & 16)) {
+          const int tn = t + 1, unit_n = tn / n_nt, nt_n = tn - unit_n * n_nt;
+          const int b_n = unit_n / n_mt2, mt_n = 2 * (unit_n - b_n * n_mt2) + (int)rank;
+          if (nt_n * UP_BN >= cout1) epi_rl_prefetch_tile<UP_BN, EW>(d2, nt_n * UP_BN - cout1, mt_n, b_n, warp, lane);
+          else epi_rl_prefetch_tile<UP_BN, EW>(d, nt_n * UP_BN, mt_n, b_n, warp, lane);
+        }
         if (nt * UP_BN >= cout1)
           umma_tile_epilogue_rl<UP_BN, NACC, EW>(d2, nt * UP_BN - cout1, mt, b, ub, tpar, warp, lane, tmem_base, tfull_bar(ub),
                                                  NACC - 1, mma_order);
