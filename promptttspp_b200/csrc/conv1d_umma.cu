@@ -1346,7 +1346,6 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
 // tile is tiny (K x 6 MMAs of 128 x 32 x 16), so the kernel is organised for memory-level parallelism: a deep
 // activation ring, four accumulator buffers, and TWO epilogue groups of 8 warps that alternate tiles, so that one
 // group's residual loads are in flight while the other computes and stores.
-constexpr int US_C = 32;            // channels (Cin == Cout)
 constexpr int US_EW = 8;            // epilogue warps per group
 constexpr int US_GROUPS = 2;
 constexpr int US_THREADS = (US_GROUPS * US_EW + 2) * 32;
@@ -1364,18 +1363,21 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t saddr) {
   return d;
 }
 
-template <int NST>
+// US_C = 32: 64-byte rows, SWIZZLE_64B; US_C = 64: 128-byte rows, SWIZZLE_128B (BigVGAN's 64-channel stage, taps <= 7:
+// K x 64 x 64 x 2 planes <= 112 KB resident).
+template <int US_C, int NST>
 __global__ void __launch_bounds__(US_THREADS, 1)
 conv1d_umma_c32_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                        const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                        const pttspp_conv1d_desc d, const int n_mt, const int n_tiles, const int rowsA) {
-  constexpr uint32_t TMEM_COLS = US_NBUF * 2 * US_C;  // 256
+  constexpr uint32_t TMEM_COLS = US_NBUF * 2 * US_C;  // 256 / 512
+  constexpr uint32_t ROWB = US_C * 2;                 // bytes per operand row
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t w_plane = (uint32_t)d.K * US_C * 64u;          // one weight plane: K taps x 32 rows x 64 B
+  const uint32_t w_plane = (uint32_t)d.K * US_C * ROWB;         // one weight plane: K taps x C rows x ROWB
   const uint32_t w_bytes = 2u * w_plane;
-  const uint32_t a_plane = (uint32_t)rowsA * 64u;
+  const uint32_t a_plane = (uint32_t)rowsA * ROWB;
   const uint32_t a_stage = ((2u * a_plane) + 1023u) & ~1023u;
   const uint32_t ring = base + ((w_bytes + 1023u) & ~1023u);
   const uint32_t bars_off = ((w_bytes + 1023u) & ~1023u) + (uint32_t)NST * a_stage;
@@ -1425,8 +1427,8 @@ conv1d_umma_c32_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_c
     if (elect_one()) {
       mbar_expect_tx(fullW, w_bytes);
       for (int tap = 0; tap < d.K; ++tap) {
-        tma_load_2d(base + (uint32_t)tap * (US_C * 64u), &mapBh, fullW, 0, tap * US_C);
-        tma_load_2d(base + w_plane + (uint32_t)tap * (US_C * 64u), &mapBl, fullW, 0, tap * US_C);
+        tma_load_2d(base + (uint32_t)tap * (US_C * ROWB), &mapBh, fullW, 0, tap * US_C);
+        tma_load_2d(base + w_plane + (uint32_t)tap * (US_C * ROWB), &mapBl, fullW, 0, tap * US_C);
       }
     }
     __syncwarp();
@@ -1446,7 +1448,7 @@ conv1d_umma_c32_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_c
   } else if (warp == W_MMA) {
     // ================= MMA issuer =================
     constexpr uint32_t idesc = umma_idesc_f16(UM_BM, US_C);
-    const uint64_t descW = umma_desc_k_sw64(base);
+    const uint64_t descW = (US_C == 32) ? umma_desc_k_sw64(base) : umma_desc_k_sw128(base);
     mbar_wait_warp(fullW, 0);
     tc_fence_after();
     uint32_t g = 0;
@@ -1457,16 +1459,17 @@ conv1d_umma_c32_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_c
       tc_fence_after();
       const uint32_t acc_main = tmem_base + (uint32_t)(u * 2 * US_C);
       const uint32_t acc_cross = acc_main + (uint32_t)US_C;
-      const uint64_t descA = umma_desc_k_sw64(ring + (uint32_t)st * a_stage);
+      const uint64_t descA = (US_C == 32) ? umma_desc_k_sw64(ring + (uint32_t)st * a_stage)
+                                          : umma_desc_k_sw128(ring + (uint32_t)st * a_stage);
       if (elect_one()) {
         for (int tap = 0; tap < d.K; ++tap) {
-          const uint64_t dAh = descA + (uint64_t)(((uint32_t)(tap * d.dil) * 64u) >> 4);  // taps share the halo block
+          const uint64_t dAh = descA + (uint64_t)(((uint32_t)(tap * d.dil) * ROWB) >> 4);  // taps share the halo block
           const uint64_t dAl = dAh + (uint64_t)(a_plane >> 4);
-          const uint64_t dBh = descW + (uint64_t)(((uint32_t)tap * (US_C * 64u)) >> 4);
+          const uint64_t dBh = descW + (uint64_t)(((uint32_t)tap * (US_C * ROWB)) >> 4);
           const uint64_t dBl = dBh + (uint64_t)(w_plane >> 4);
 #pragma unroll
           for (int kk = 0; kk < US_C / 16; ++kk) {
-            const uint64_t adv = (uint64_t)(kk * 2);  // 16 halves = 32 bytes inside the 64-byte swizzle span
+            const uint64_t adv = (uint64_t)(kk * 2);  // 16 halves = 32 bytes inside the swizzle span
             const uint32_t acc = (tap | kk) ? 1u : 0u;
             umma_f16(acc_cross, dAl + adv, dBh + adv, idesc, acc);
             umma_f16(acc_cross, dAh + adv, dBl + adv, idesc, 1u);
@@ -1770,11 +1773,31 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
 }
 
 
+// weight-resident kernel: 32 channels with up to 11 taps, 64 channels with up to 7 (weights + >= 2 halo stages fit)
 bool conv1d_umma_c32_ok(const pttspp_conv1d_desc& d) {
-  return d.Cin == US_C && d.Cout == US_C && d.K >= 1 && d.K <= US_MAXK && d.in_hi && d.in_lo && d.w_hi && d.w_lo &&
-         d.in_stride == 1 && !d.in_len && !d.in_add && d.in_ld % 8 == 0 && d.in_bs % 8 == 0 && aligned16(d.in_hi) &&
-         aligned16(d.in_lo) && aligned16(d.w_hi) && aligned16(d.w_lo) && d.w_scale_inv > 0.f &&
-         UM_BM + round_up((d.K - 1) * d.dil, 8) <= 256 && epilogue_rl_ok(d);
+  if (!((d.Cin == 32 && d.Cout == 32 && d.K <= US_MAXK) || (d.Cin == 64 && d.Cout == 64 && d.K <= 7))) return false;
+  if (d.Cin == 64 && getenv("PTTSPP_UMMA_NO_WRES64")) return false;
+  return d.K >= 1 && d.in_hi && d.in_lo && d.w_hi && d.w_lo && d.in_stride == 1 && !d.in_len && !d.in_add &&
+         d.in_ld % 8 == 0 && d.in_bs % 8 == 0 && aligned16(d.in_hi) && aligned16(d.in_lo) && aligned16(d.w_hi) &&
+         aligned16(d.w_lo) && d.w_scale_inv > 0.f && UM_BM + round_up((d.K - 1) * d.dil, 8) <= 256 && epilogue_rl_ok(d);
+}
+
+template <int C, int NST>
+void conv1d_umma_wres_launch_t(const pttspp_conv1d_desc& d, const CUtensorMap& mAh, const CUtensorMap& mAl,
+                               const CUtensorMap& mBh, const CUtensorMap& mBl, int rowsA, size_t smem, int num_sms,
+                               cudaStream_t s) {
+  auto kern = conv1d_umma_c32_kernel<C, NST>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int n_mt = ceil_div(d.M, UM_BM);
+  const long long n_tiles = (long long)n_mt * d.B;
+  PT_CHECK(n_tiles < (1ll << 30), "conv1d: too many tiles");
+  const int grid = (int)std::min<long long>(n_tiles, num_sms);
+  kern<<<grid, US_THREADS, smem, s>>>(mAh, mAl, mBh, mBl, d, n_mt, (int)n_tiles, rowsA);
+  PT_LAUNCHED();
 }
 
 void conv1d_umma_c32_launch(const pttspp_conv1d_desc& d_in, cudaStream_t s) {
@@ -1786,34 +1809,40 @@ void conv1d_umma_c32_launch(const pttspp_conv1d_desc& d_in, cudaStream_t s) {
     PT_CUDA(cudaGetDevice(&dev));
     PT_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  const int C = d.Cin;
+  const int rowb = C * 2;
+  const CUtensorMapSwizzle swz = (C == 32) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   const int rowsA = UM_BM + round_up((d.K - 1) * d.dil, 8);
-  const uint64_t wdims[2] = {(uint64_t)US_C, (uint64_t)d.K * US_C};
-  const uint64_t wstr[1] = {(uint64_t)US_C * 2};
-  const uint32_t wbox[2] = {US_C, US_C};
-  const CUtensorMap mBh = make_map(d.w_hi, 2, wdims, wstr, wbox, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
-  const CUtensorMap mBl = make_map(d.w_lo, 2, wdims, wstr, wbox, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
-  const uint64_t adims[3] = {(uint64_t)US_C, (uint64_t)d.T_in, (uint64_t)d.B};
+  const uint64_t wdims[2] = {(uint64_t)C, (uint64_t)d.K * C};
+  const uint64_t wstr[1] = {(uint64_t)C * 2};
+  const uint32_t wbox[2] = {(uint32_t)C, (uint32_t)C};
+  const CUtensorMap mBh = make_map(d.w_hi, 2, wdims, wstr, wbox, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, swz);
+  const CUtensorMap mBl = make_map(d.w_lo, 2, wdims, wstr, wbox, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, swz);
+  const uint64_t adims[3] = {(uint64_t)C, (uint64_t)d.T_in, (uint64_t)d.B};
   const uint64_t astr[2] = {(uint64_t)d.in_ld * 2, (uint64_t)d.in_bs * 2};
-  const uint32_t abox[3] = {US_C, (uint32_t)rowsA, 1};
-  const CUtensorMap mAh = make_map(d.in_hi, 3, adims, astr, abox, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
-  const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
-  constexpr int NST = 6;
-  const size_t w_bytes = round_up(2 * d.K * US_C * 64, 1024);
-  const size_t a_stage = round_up(2 * rowsA * 64, 1024);
-  const size_t smem = w_bytes + NST * a_stage + (1 + 2 * NST + 2 * US_NBUF) * 8 + 16 + 1024;
-  auto kern = conv1d_umma_c32_kernel<NST>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+  const uint32_t abox[3] = {(uint32_t)C, (uint32_t)rowsA, 1};
+  const CUtensorMap mAh = make_map(d.in_hi, 3, adims, astr, abox, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, swz);
+  const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, swz);
+  const size_t w_bytes = round_up(2 * d.K * C * rowb, 1024);
+  const size_t a_stage = round_up(2 * rowsA * rowb, 1024);
+  const size_t misc = (1 + 2 * 6 + 2 * US_NBUF) * 8 + 16 + 1024;
+  const size_t cap = 227 * 1024;
+  PT_CHECK(w_bytes + 2 * a_stage + misc <= cap, "conv1d weight-resident kernel: shared memory budget exceeded");
+  int nst = (int)std::min<size_t>(6, (cap - w_bytes - misc) / a_stage);
+  if (nst == 5) nst = 4;  // instantiated ring depths: 2, 3, 4, 6
+  const size_t smem = w_bytes + (size_t)nst * a_stage + misc;
+#define PT_WRES(CC, N) conv1d_umma_wres_launch_t<CC, N>(d, mAh, mAl, mBh, mBl, rowsA, smem, num_sms, s)
+  if (C == 32) {
+    PT_WRES(32, 6);  // always fits: 44 KB of weights + 6 x 23.5 KB
+  } else {
+    switch (nst) {
+      case 2: PT_WRES(64, 2); break;
+      case 3: PT_WRES(64, 3); break;
+      case 4: PT_WRES(64, 4); break;
+      default: PT_WRES(64, 6); break;
+    }
   }
-  PT_CHECK(smem <= 227 * 1024, "conv1d c32: shared memory budget exceeded");
-  const int n_mt = ceil_div(d.M, UM_BM);
-  const long long n_tiles = (long long)n_mt * d.B;
-  PT_CHECK(n_tiles < (1ll << 30), "conv1d: too many tiles");
-  const int grid = (int)std::min<long long>(n_tiles, num_sms);
-  kern<<<grid, US_THREADS, smem, s>>>(mAh, mAl, mBh, mBl, d, n_mt, (int)n_tiles, rowsA);
-  PT_LAUNCHED();
+#undef PT_WRES
 }
 
 }  // namespace

@@ -65,6 +65,11 @@ UMMA_CASES = [
     (32, 32, 11, 1, 3, 2999),
     (32, 32, 11, 5, 2, 40000),
     (32, 32, 1, 1, 1, 77),
+    # 64 channels, <= 7 taps: the same weight-resident kernel with SWIZZLE_128B rows
+    (64, 64, 3, 1, 2, 1000),
+    (64, 64, 3, 5, 2, 3001),
+    (64, 64, 7, 5, 2, 20000),
+    (64, 64, 7, 1, 3, 2999),
 ]
 
 
