@@ -232,6 +232,22 @@ size_t pttspp_bigvgan_workspace_bytes(const pttspp_bigvgan_t* h, int B, int T);
 int pttspp_bigvgan_forward(pttspp_bigvgan_t* h, const float* mel, int B, int T, float* wav, void* workspace,
                            size_t workspace_bytes, pttspp_stream_t stream);
 
+/* F0-aware generator (promptttspp/vocoders/bigvgan_f0.py:98-115): the handle must have received the
+ * `noise_convs.{i}.{weight,bias}` tensors; har_source: [B][T*prod(rates)] from pttspp_nsf_source.  Per stage
+ * x = up(x) + noise_conv(har_source) (:104-106), everything else as pttspp_bigvgan_forward. */
+int pttspp_bigvgan_forward_f0(pttspp_bigvgan_t* h, const float* mel, const float* har_source, int B, int T, float* wav,
+                              void* workspace, size_t workspace_bytes, pttspp_stream_t stream);
+/* Harmonic-plus-noise source: nn.Upsample(scale_factor=hop) of f0 [B][T] (bigvgan_f0.py:99), SineGen
+ * (promptttspp/vocoders/nsf.py:55-85 phase accumulation with torch's double-accumulated cumsum, :116-148 voiced /
+ * unvoiced mix) and SourceModuleHnNSF's Linear(H -> 1) + tanh (:193-206).  The random draws of the reference are
+ * INPUTS (device): rand_ini [B][H] (torch.rand, column 0 zeroed, nsf.py:64-67) and noise [B][L][H] (randn_like, :143);
+ * H = harmonic_num + 1 <= 16, L = T*hop.  har_source: [B][L]. */
+size_t pttspp_nsf_source_workspace_bytes(int B, int T, int hop, int harmonic_num);
+int pttspp_nsf_source(const float* f0, int B, int T, int hop, float sampling_rate, int harmonic_num, float sine_amp,
+                      float noise_std, float voiced_threshold, const float* rand_ini, const float* noise,
+                      const float* lin_w, const float* lin_b, float* har_source, void* workspace, size_t workspace_bytes,
+                      pttspp_stream_t stream);
+
 /* ---- model level: acoustic model (PromptTTSMDNDurCFG inference) --------------------- */
 
 typedef struct pttspp_acoustic pttspp_acoustic_t;

@@ -14,6 +14,7 @@ Layouts follow the reference: activations [B, C, T] unless stated otherwise.
 """
 import math
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -99,6 +100,68 @@ def bigvgan_forward(sd, cfg, mel):
         p = f"upsamples.{i}"
         x = F.conv_transpose1d(x, _conv_weight(sd, p), sd[p + ".bias"], stride=u, padding=u // 2 + u % 2,
                                output_padding=u % 2)
+        xs = 0
+        for j, (rk, rd) in enumerate(zip(rks, rds)):
+            y = x
+            for l, d in enumerate(rd):
+                lp = f"mrfs.{i}.{j}.layers.{l}"
+                h = _aa(sd, lp + ".act1", y)
+                h = F.conv1d(h, _conv_weight(sd, lp + ".conv1"), sd[lp + ".conv1.bias"],
+                             padding=(rk * d - d) // 2, dilation=d)
+                h = _aa(sd, lp + ".act2", h)
+                h = F.conv1d(h, _conv_weight(sd, lp + ".conv2"), sd[lp + ".conv2.bias"], padding=rk // 2)
+                y = y + h
+            xs = xs + y
+        x = xs / len(rks)
+    x = _aa(sd, "act_post", x)
+    x = F.conv1d(x, _conv_weight(sd, "conv_post"), sd["conv_post.bias"], padding=3)
+    return torch.tanh(x)
+
+
+def nsf_source(sd, f0_up, rand_ini, noise, sampling_rate=24000.0, harmonic_num=8, sine_amp=0.1, noise_std=0.003,
+               voiced_threshold=0.0):
+    """SourceModuleHnNSF.forward (vocoders/nsf.py:193-206) over SineGen.forward (:116-148) and SineGen._f02sine
+    (:55-85, the non-pulse branch), with the reference's random draws injected: rand_ini [B, H] (:64-67, column 0
+    zeroed), noise [B, L, H] (:143).  f0_up: [B, L, 1] -> har_source [B, L, 1]."""
+    H = harmonic_num + 1
+    f0_buf = torch.zeros(f0_up.shape[0], f0_up.shape[1], H)
+    f0_buf[:, :, 0] = f0_up[:, :, 0]
+    for idx in range(harmonic_num):
+        f0_buf[:, :, idx + 1] = f0_buf[:, :, 0] * (idx + 2)
+    rad = (f0_buf / sampling_rate) % 1
+    ini = rand_ini.clone()
+    ini[:, 0] = 0
+    rad[:, 0, :] = rad[:, 0, :] + ini
+    over = torch.cumsum(rad, 1) % 1
+    wrap = (over[:, 1:, :] - over[:, :-1, :]) < 0
+    shift = torch.zeros_like(rad)
+    shift[:, 1:, :] = wrap * -1.0
+    sines = torch.sin(torch.cumsum(rad + shift, dim=1) * 2 * np.pi)
+    sine_waves = sines * sine_amp
+    uv = torch.ones_like(f0_up) * (f0_up > voiced_threshold)
+    noise_amp = uv * noise_std + (1 - uv) * sine_amp / 3
+    sine_waves = sine_waves * uv + noise_amp * noise
+    return torch.tanh(F.linear(sine_waves, sd["m_source.l_linear.weight"], sd["m_source.l_linear.bias"]))
+
+
+def bigvgan_f0_forward(sd, cfg, mel, f0, rand_ini, noise, sampling_rate=24000.0, harmonic_num=8):
+    """F0AwareBigVGAN.forward (vocoders/bigvgan_f0.py:98-115).  mel [B, 80, T], f0 [B, 1, T]; nn.Upsample(nearest,
+    scale_factor=prod(rates)) of f0 (:99), the source (:100-101), then per stage x = up(x) + noise_conv(har) (:104-106)."""
+    rates, ksz = cfg["upsample_rates"], cfg["upsample_kernel_sizes"]
+    rks, rds = cfg["resblock_kernel_sizes"], cfg["resblock_dilations"]
+    hop = int(np.prod(rates))
+    f0_up = F.interpolate(f0, scale_factor=float(hop)).transpose(-1, -2)
+    har = nsf_source(sd, f0_up, rand_ini, noise, sampling_rate, harmonic_num).transpose(-1, -2)
+    x = F.conv1d(mel, _conv_weight(sd, "conv_pre"), sd["conv_pre.bias"], padding=3)
+    for i, (u, k) in enumerate(zip(rates, ksz)):
+        p = f"upsamples.{i}"
+        x = F.conv_transpose1d(x, _conv_weight(sd, p), sd[p + ".bias"], stride=u, padding=u // 2 + u % 2,
+                               output_padding=u % 2)
+        if i + 1 < len(rates):
+            sf = int(np.prod(rates[i + 1:]))
+            x = x + F.conv1d(har, sd[f"noise_convs.{i}.weight"], sd[f"noise_convs.{i}.bias"], stride=sf, padding=sf // 2)
+        else:
+            x = x + F.conv1d(har, sd[f"noise_convs.{i}.weight"], sd[f"noise_convs.{i}.bias"])
         xs = 0
         for j, (rk, rd) in enumerate(zip(rks, rds)):
             y = x

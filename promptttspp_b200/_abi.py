@@ -111,6 +111,12 @@ SIGNATURES = {
     "pttspp_bigvgan_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "pttspp_bigvgan_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_size_t, C.c_void_p]),
+    "pttspp_bigvgan_forward_f0": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_size_t, C.c_void_p]),
+    "pttspp_nsf_source_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "pttspp_nsf_source": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float,
+                                    C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_size_t, C.c_void_p]),
     "pttspp_acoustic_create": (C.c_int, [C.POINTER(AcousticConfig), C.POINTER(C.c_void_p)]),
     "pttspp_acoustic_destroy": (None, [C.c_void_p]),
     "pttspp_acoustic_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, c_i64p, C.c_int, C.c_void_p]),

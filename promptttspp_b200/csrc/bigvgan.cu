@@ -43,6 +43,13 @@ struct pttspp_bigvgan {
   std::vector<std::vector<std::vector<pttspp::AMPLayerW>>> mrfs;  // [stage][kernel][layer]
   pttspp::AAParams act_post;
   float* post_w = nullptr;  // conv_post weight as [K][C] for the dedicated C -> 1 kernel
+  // F0-aware variant (vocoders/bigvgan_f0.py): per stage the Conv1d(1 -> C_i, k, stride) applied to the harmonic source
+  struct NoiseConv {
+    float* w = nullptr;  // [K][C]
+    float* bias = nullptr;
+    int K = 1, stride = 1, pad = 0, C = 0;
+  };
+  std::vector<NoiseConv> noise_convs;  // empty for the plain BigVGAN
 };
 
 namespace pttspp {
@@ -129,6 +136,139 @@ void conv_post_tanh(const float* x, const float* w, const float* bias, float* ou
   PT_CHECK(K == 7, "conv_post kernel is instantiated for k = 7");
   conv_post_tanh_kernel<7><<<blocks, 256, 0, s>>>(x, w, bias, out, L, strips);
   PT_LAUNCHED();
+}
+
+// ---- F0-aware BigVGAN: harmonic-plus-noise source (vocoders/nsf.py) ------------------------------------------------
+// SineGen._f02sine (:55-85) is two prefix sums over the sample axis per harmonic:
+//   rad[t]   = ((h+1) * f0[t] / sr) mod 1            (+ rand_ini[h] at t = 0)
+//   c1       = cumsum(rad); wrap[t] = (c1[t] mod 1) < (c1[t-1] mod 1)      (the "-1 whenever the sum passes 1" trick)
+//   phase    = cumsum(rad - wrap);  sine = sin(2*pi*phase)
+// torch's CPU cumsum accumulates in double and rounds every output to float; the kernels below do the same
+// (chunked: per-chunk double sums, a tiny sequential scan of the chunk sums, then the in-chunk pass), so the result
+// does not depend on the chunking beyond 1e-16.  One thread owns (utterance, chunk) and all harmonics.
+constexpr int NSF_CHUNK = 256;
+constexpr int NSF_MAXH = 16;
+
+__device__ __forceinline__ float nsf_rad(float f0, int h, float sr, float ini, bool first) {
+  const float fh = (h == 0) ? f0 : f0 * (float)(h + 1);  // f0_buf[:, :, idx+1] = f0_buf[:, :, 0] * (idx + 2)
+  float r = fh / sr;
+  r = r - floorf(r);  // python-style % 1 (non-negative operands)
+  if (first) r = r + ini;
+  return r;
+}
+__device__ __forceinline__ float nsf_mod1(float x) { return x - floorf(x); }
+
+// pass 1 / 3: chunk sums.  shifted == 0: sum of rad; shifted == 1: sum of (rad + wrap shift), needs off1 (exclusive
+// double prefix of pass 1).  sums / off: [B][nchunk][H]
+__global__ void __launch_bounds__(128) nsf_chunk_sums_kernel(const float* __restrict__ f0, const float* __restrict__ rand_ini,
+                                                             const double* __restrict__ off1, double* __restrict__ sums,
+                                                             int B, int T, int hop, int H, float sr, int nchunk,
+                                                             int shifted) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * nchunk) return;
+  const int b = idx / nchunk, ch = idx - b * nchunk;
+  const int L = T * hop, t0 = ch * NSF_CHUNK, t1 = min(L, t0 + NSF_CHUNK);
+  for (int h = 0; h < H; ++h) {
+    const float ini = rand_ini[b * H + h];
+    double acc = 0.0, c1 = shifted ? off1[(size_t)idx * H + h] : 0.0;
+    float prev = shifted ? nsf_mod1((float)c1) : 0.f;  // (c1[t0-1] mod 1); unused at t0 == 0
+    for (int t = t0; t < t1; ++t) {
+      const float r = nsf_rad(f0[b * T + t / hop], h, sr, ini, t == 0);
+      if (!shifted) {
+        acc += (double)r;
+      } else {
+        c1 += (double)r;
+        const float cur = nsf_mod1((float)c1);
+        const float sh = (t > 0 && (cur - prev) < 0.f) ? -1.f : 0.f;
+        prev = cur;
+        acc += (double)(r + sh);
+      }
+    }
+    sums[(size_t)idx * H + h] = acc;
+  }
+}
+// exclusive prefix of the chunk sums along the chunk axis (one thread per (b, h); nchunk is ~1000)
+__global__ void nsf_chunk_scan_kernel(const double* __restrict__ sums, double* __restrict__ off, int B, int H, int nchunk) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  const int b = idx / H, h = idx - b * H;
+  double acc = 0.0;
+  for (int ch = 0; ch < nchunk; ++ch) {
+    const size_t i = ((size_t)b * nchunk + ch) * H + h;
+    off[i] = acc;
+    acc += sums[i];
+  }
+}
+// pass 5: sines, voiced/unvoiced mix with the injected noise (SineGen.forward :116-148), Linear(H -> 1) + tanh
+// (SourceModuleHnNSF.forward :193-206) -> har_source [B][L]
+__global__ void __launch_bounds__(128) nsf_source_kernel(const float* __restrict__ f0, const float* __restrict__ rand_ini,
+                                                         const float* __restrict__ noise /*[B][L][H]*/,
+                                                         const double* __restrict__ off1, const double* __restrict__ off2,
+                                                         const float* __restrict__ lin_w, const float* __restrict__ lin_b,
+                                                         float* __restrict__ har, int B, int T, int hop, int H, float sr,
+                                                         float sine_amp, float noise_std, float voiced_thr, int nchunk) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * nchunk) return;
+  const int b = idx / nchunk, ch = idx - b * nchunk;
+  const int L = T * hop, t0 = ch * NSF_CHUNK, t1 = min(L, t0 + NSF_CHUNK);
+  double c1[NSF_MAXH], c2[NSF_MAXH];
+  float prev[NSF_MAXH], ini[NSF_MAXH], lw[NSF_MAXH];
+#pragma unroll
+  for (int h = 0; h < NSF_MAXH; ++h) {
+    if (h < H) {
+      c1[h] = off1[(size_t)idx * H + h];
+      c2[h] = off2[(size_t)idx * H + h];
+      prev[h] = nsf_mod1((float)c1[h]);
+      ini[h] = rand_ini[b * H + h];
+      lw[h] = lin_w[h];
+    }
+  }
+  const float two = 2.f, pi = 3.14159265358979323846f;  // `cumsum * 2 * np.pi`: two fp32 multiplications
+  for (int t = t0; t < t1; ++t) {
+    const float f = f0[b * T + t / hop];
+    const float uv = (f > voiced_thr) ? 1.f : 0.f;
+    const float namp = uv * noise_std + (1.f - uv) * sine_amp / 3.f;
+    float acc = 0.f;
+#pragma unroll
+    for (int h = 0; h < NSF_MAXH; ++h) {
+      if (h < H) {
+        const float r = nsf_rad(f, h, sr, ini[h], t == 0);
+        c1[h] += (double)r;
+        const float cur = nsf_mod1((float)c1[h]);
+        const float sh = (t > 0 && (cur - prev[h]) < 0.f) ? -1.f : 0.f;
+        prev[h] = cur;
+        c2[h] += (double)(r + sh);
+        const float sine = sinf(((float)c2[h] * two) * pi) * sine_amp;
+        const float sw = sine * uv + namp * noise[((size_t)b * L + t) * H + h];
+        acc = fmaf(sw, lw[h], acc);  // F.linear: dot product over the harmonics
+      }
+    }
+    har[(size_t)b * L + t] = tanhf(acc + lin_b[0]);
+  }
+}
+
+// x_source = Conv1d(1 -> C, K, stride, pad)(har_source) written channels-last into the stage buffer, to which the
+// transposed conv then ACCUMULATES (x = up(x) + noise_conv(har_source), bigvgan_f0.py:104-106)
+__global__ void __launch_bounds__(256) noise_conv_kernel(const float* __restrict__ har, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ out, int L,
+                                                         int Lout, int C, int K, int stride, int pad) {
+  extern __shared__ float win[];  // (rows-1)*stride + K samples
+  constexpr int ROWS = 32;
+  const int b = blockIdx.y, l0 = blockIdx.x * ROWS;
+  const int span = (ROWS - 1) * stride + K;
+  const int s0 = l0 * stride - pad;
+  for (int i = threadIdx.x; i < span; i += blockDim.x) {
+    const int t = s0 + i;
+    win[i] = (t >= 0 && t < L) ? har[(size_t)b * L + t] : 0.f;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < ROWS * C; o += blockDim.x) {
+    const int r = o / C, c = o - r * C;
+    if (l0 + r >= Lout) continue;
+    float acc = bias[c];
+    for (int k = 0; k < K; ++k) acc = fmaf(win[r * stride + k], w[k * C + c], acc);
+    out[((size_t)b * Lout + l0 + r) * C + c] = acc;
+  }
 }
 
 }  // namespace
@@ -243,6 +383,25 @@ extern "C" int pttspp_bigvgan_finalize(pttspp_bigvgan_t* h, pttspp_stream_t) {
     }
     h->mrfs.push_back(stage);
   }
+  h->noise_convs.clear();
+  if (h->store.has("noise_convs.0.weight")) {  // F0-aware generator (bigvgan_f0.py:66-79)
+    for (int i = 0; i < c.num_upsamples; ++i) {
+      pttspp_bigvgan::NoiseConv nc;
+      nc.C = C0 >> (i + 1);
+      int sf = 1;
+      for (int q = i + 1; q < c.num_upsamples; ++q) sf *= c.upsample_rates[q];
+      if (i + 1 < c.num_upsamples) { nc.K = 2 * sf; nc.stride = sf; nc.pad = sf / 2; }
+      else { nc.K = 1; nc.stride = 1; nc.pad = 0; }
+      const std::string p = "noise_convs." + std::to_string(i);
+      const auto& wt = h->store.get(p + ".weight", (int64_t)nc.C * nc.K).data;  // [C][1][K]
+      std::vector<float> kc((size_t)nc.K * nc.C);
+      for (int co = 0; co < nc.C; ++co)
+        for (int k = 0; k < nc.K; ++k) kc[(size_t)k * nc.C + co] = wt[(size_t)co * nc.K + k];
+      nc.w = h->dev.upload(kc);
+      nc.bias = h->dev.upload(h->store.get(p + ".bias", nc.C).data);
+      h->noise_convs.push_back(nc);
+    }
+  }
   const int Cl = C0 >> c.num_upsamples;
   h->act_post = load_aa(h->store, h->dev, "act_post", Cl);
   h->conv_post = load_conv1d(h->store, h->dev, "conv_post", 1, Cl, 7, 1, 3);
@@ -265,10 +424,12 @@ extern "C" size_t pttspp_bigvgan_workspace_bytes(const pttspp_bigvgan_t* h, int 
   return (size_t)el * 6 * sizeof(float) + 256;
 }
 
-extern "C" int pttspp_bigvgan_forward(pttspp_bigvgan_t* h, const float* mel, int B, int T, float* wav, void* workspace,
-                                      size_t workspace_bytes, pttspp_stream_t stream) {
-  PT_API_BEGIN
+static void bigvgan_forward_impl(pttspp_bigvgan_t* h, const float* mel, const float* har_source, int B, int T, float* wav,
+                                 void* workspace, size_t workspace_bytes, pttspp_stream_t stream) {
+  {
   PT_CHECK(h && mel && wav, "null argument");
+  PT_CHECK((har_source != nullptr) == !h->noise_convs.empty(),
+           "bigvgan: the F0-aware generator needs a harmonic source (forward_f0), the plain one must not get one");
   PT_CHECK(h->finalized, "bigvgan: finalize() has not been called after the last set_tensor()");
   PT_CHECK(B >= 1 && T >= 1, "bigvgan: empty input (B=%d, T=%d)", B, T);
   PT_CHECK(workspace && workspace_bytes >= pttspp_bigvgan_workspace_bytes(h, B, T), "bigvgan: workspace too small");
@@ -302,6 +463,15 @@ extern "C" int pttspp_bigvgan_forward(pttspp_bigvgan_t* h, const float* mel, int
   for (int i = 0; i < c.num_upsamples; ++i) {
     const UpsampleW& u = h->ups[i];
     const int Lout = (L - 1) * u.stride - 2 * u.pad + u.Kt + u.out_pad;
+    const bool f0_aware = har_source != nullptr;
+    if (f0_aware) {
+      const auto& nc = h->noise_convs[i];
+      const int Lh = T * total_upsample(c);
+      dim3 grid(ceil_div(Lout, 32), B);
+      const size_t sm = ((size_t)31 * nc.stride + nc.K) * sizeof(float);
+      noise_conv_kernel<<<grid, 256, sm, s>>>(har_source, nc.w, nc.bias, bx, Lh, Lout, nc.C, nc.K, nc.stride, nc.pad);
+      PT_LAUNCHED();
+    }
     // polyphase transposed conv: phase r writes rows m*stride + r - pad
     for (int r = 0; r < u.stride; ++r) {
       pttspp_conv1d_desc d;
@@ -315,7 +485,7 @@ extern "C" int pttspp_bigvgan_forward(pttspp_bigvgan_t* h, const float* mel, int
       const int m_end = (Lout - 1 - off) / u.stride;  // last m with m*stride + off <= Lout-1
       d.M = m_end - d.m_begin + 1;
       d.out_mul = u.stride; d.out_off = off;
-      d.acc_scale = 1.f; d.res_scale = 1.f; d.alpha = 1.f; d.beta = 0.f; d.B = B;
+      d.acc_scale = 1.f; d.res_scale = 1.f; d.alpha = 1.f; d.beta = f0_aware ? 1.f : 0.f; d.B = B;
       if (!u.w_hi.empty()) {
         uint16_t *ph, *pl;
         stage_planes((int64_t)B * L * u.Cin, ph, pl);
@@ -379,5 +549,59 @@ extern "C" int pttspp_bigvgan_forward(pttspp_bigvgan_t* h, const float* mel, int
     d.act = PTTSPP_ACT_TANH;
     conv1d_cl(d, s);
   }
+  }
+}
+
+extern "C" int pttspp_bigvgan_forward(pttspp_bigvgan_t* h, const float* mel, int B, int T, float* wav, void* workspace,
+                                      size_t workspace_bytes, pttspp_stream_t stream) {
+  PT_API_BEGIN
+  bigvgan_forward_impl(h, mel, nullptr, B, T, wav, workspace, workspace_bytes, stream);
+  PT_API_END
+}
+
+extern "C" int pttspp_bigvgan_forward_f0(pttspp_bigvgan_t* h, const float* mel, const float* har_source, int B, int T,
+                                         float* wav, void* workspace, size_t workspace_bytes, pttspp_stream_t stream) {
+  PT_API_BEGIN
+  PT_CHECK(har_source, "null harmonic source");
+  bigvgan_forward_impl(h, mel, har_source, B, T, wav, workspace, workspace_bytes, stream);
+  PT_API_END
+}
+
+extern "C" size_t pttspp_nsf_source_workspace_bytes(int B, int T, int hop, int harmonic_num) {
+  if (B <= 0 || T <= 0 || hop <= 0 || harmonic_num < 0) return 0;
+  const size_t nchunk = ((size_t)T * hop + NSF_CHUNK - 1) / NSF_CHUNK;
+  return 4 * (size_t)B * nchunk * (harmonic_num + 1) * sizeof(double) + 256;
+}
+
+extern "C" int pttspp_nsf_source(const float* f0, int B, int T, int hop, float sampling_rate, int harmonic_num,
+                                 float sine_amp, float noise_std, float voiced_threshold, const float* rand_ini,
+                                 const float* noise, const float* lin_w, const float* lin_b, float* har_source,
+                                 void* workspace, size_t workspace_bytes, pttspp_stream_t stream) {
+  PT_API_BEGIN
+  PT_CHECK(f0 && rand_ini && noise && lin_w && lin_b && har_source && workspace, "null argument");
+  const int H = harmonic_num + 1;
+  PT_CHECK(B >= 1 && T >= 1 && hop >= 1 && H >= 1 && H <= NSF_MAXH, "nsf_source: bad shape (harmonics <= %d)", NSF_MAXH - 1);
+  PT_CHECK(workspace_bytes >= pttspp_nsf_source_workspace_bytes(B, T, hop, harmonic_num), "nsf_source: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nchunk = ceil_div(T * hop, NSF_CHUNK);
+  const size_t n = (size_t)B * nchunk * H;
+  double* sums1 = (double*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  double *off1 = sums1 + n, *sums2 = off1 + n, *off2 = sums2 + n;
+  const int threads = B * nchunk;
+  ProfScope prof(PROF_OTHER, s, 0.0, 4.0 * B * (double)T * hop * (H + 1));
+  nsf_chunk_sums_kernel<<<ceil_div(threads, 128), 128, 0, s>>>(f0, rand_ini, nullptr, sums1, B, T, hop, H, sampling_rate,
+                                                                nchunk, 0);
+  PT_LAUNCHED();
+  nsf_chunk_scan_kernel<<<ceil_div(B * H, 64), 64, 0, s>>>(sums1, off1, B, H, nchunk);
+  PT_LAUNCHED();
+  nsf_chunk_sums_kernel<<<ceil_div(threads, 128), 128, 0, s>>>(f0, rand_ini, off1, sums2, B, T, hop, H, sampling_rate,
+                                                                nchunk, 1);
+  PT_LAUNCHED();
+  nsf_chunk_scan_kernel<<<ceil_div(B * H, 64), 64, 0, s>>>(sums2, off2, B, H, nchunk);
+  PT_LAUNCHED();
+  nsf_source_kernel<<<ceil_div(threads, 128), 128, 0, s>>>(f0, rand_ini, noise, off1, off2, lin_w, lin_b, har_source, B, T,
+                                                            hop, H, sampling_rate, sine_amp, noise_std, voiced_threshold,
+                                                            nchunk);
+  PT_LAUNCHED();
   PT_API_END
 }

@@ -34,6 +34,15 @@ def build_vocoder(ns=None, **overrides):
     return ns.BigVGAN(**kw)
 
 
+def build_vocoder_f0(ns=None, sampling_rate=24000, harmonic_num=8, **overrides):
+    """F0AwareBigVGAN with conf/vocoder/bigvgan_f0.yaml kwargs; `ns` = module namespace providing the class."""
+    if ns is None:
+        from .. import vocoders as ns
+    kw = dict(VOCODER_KWARGS)
+    kw.update(overrides)
+    return ns.F0AwareBigVGAN(sampling_rate=sampling_rate, harmonic_num=harmonic_num, **kw)
+
+
 def build_acoustic(rel_pos_type="legacy", bert=None, K_step=100, ns=None):
     """PromptTTSMDNDurCFG with the kwargs of prompttts_mdn_v2_wo_erg_final[_demo].yaml.
 

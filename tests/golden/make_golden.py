@@ -170,6 +170,46 @@ def make_vocoder():
         np.savez_compressed(OUT / f"vocoder_{name}.npz", **out)
 
 
+def make_vocoder_f0():
+    """Reference F0AwareBigVGAN with its three random draws (nsf.py:64 torch.rand, :143 and :205 torch.randn_like)
+    replaced by the seeded tensors of tests/golden_cases.py."""
+    sys.path.insert(0, str(REF))
+    import promptttspp.vocoders as ref_voc
+    from golden_cases import F0_KWARGS, VOCODER_F0_CASES, vocoder_f0_inputs
+    from promptttspp_b200.utils.synthetic import build_vocoder_f0
+
+    for name, case in VOCODER_F0_CASES.items():
+        print("vocoder_f0", name, case)
+        voc = build_vocoder_f0(ns=ref_voc, **F0_KWARGS).eval()
+        sd = synthetic_state_dict(build_vocoder_f0(**F0_KWARGS), seed=case["weight_seed"])
+        voc.load_state_dict(sd, strict=True)
+        mel, f0, rand_ini, noise = vocoder_f0_inputs(case)
+        real_rand, real_randn_like = torch.rand, torch.randn_like
+        calls = []
+
+        def fake_rand(*shape, **k):
+            calls.append(("rand", tuple(shape)))
+            assert tuple(shape) == tuple(rand_ini.shape), shape
+            return rand_ini.clone()
+
+        def fake_randn_like(t, *a, **k):
+            calls.append(("randn_like", tuple(t.shape)))
+            if tuple(t.shape) == tuple(noise.shape):
+                return noise.clone()
+            return torch.zeros_like(t)  # nsf.py:205: the noise-branch source, unused by the vocoder
+
+        torch.rand, torch.randn_like = fake_rand, fake_randn_like
+        try:
+            with torch.no_grad():
+                wav = voc(mel, f0)
+                f0_up = voc.f0_up(f0).transpose(-1, -2)
+                har, _, _ = voc.m_source(f0_up)
+        finally:
+            torch.rand, torch.randn_like = real_rand, real_randn_like
+        print("   calls", calls[:3], "wav", tuple(wav.shape), "rms", float(wav.pow(2).mean().sqrt()))
+        np.savez_compressed(OUT / f"vocoder_f0_{name}.npz", wav=wav.numpy(), har=har.numpy())
+
+
 def make_ops():
     """Op-level vectors from the reference layers: pin the closed forms used by the kernels."""
     sys.path.insert(0, str(REF))
@@ -214,11 +254,13 @@ def make_ops():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops", "vocoder", "acoustic"]
+    which = sys.argv[1:] or ["ops", "vocoder", "vocoder_f0", "acoustic"]
     if "ops" in which:
         make_ops()
     if "vocoder" in which:
         make_vocoder()
+    if "vocoder_f0" in which:
+        make_vocoder_f0()
     if "acoustic" in which:
         make_acoustic(reference_namespace())
     print("done")

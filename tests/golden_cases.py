@@ -26,6 +26,13 @@ VOCODER_CASES = {
     "b1_t33": dict(weight_seed=4321, input_seed=4, B=1, T=33),
 }
 
+# F0-aware vocoder (conf/vocoder/bigvgan_f0.yaml): mel + frame-level f0 with unvoiced stretches + injected source noise
+VOCODER_F0_CASES = {
+    "b2_t12": dict(weight_seed=4322, input_seed=5, noise_seed=205, B=2, T=12),
+    "b1_t40": dict(weight_seed=4322, input_seed=6, noise_seed=206, B=1, T=40),
+}
+F0_KWARGS = dict(sampling_rate=24000, harmonic_num=8)
+
 AA_CASES = {"c4_l37": (2, 4, 37), "c32_l3": (1, 32, 3), "c3_l1": (1, 3, 1), "c8_l64": (1, 8, 64)}
 
 
@@ -58,3 +65,17 @@ def vocoder_inputs(case):
     g = torch.Generator().manual_seed(case["input_seed"])
     mel = torch.randn(case["B"], 80, case["T"], generator=g) * 2.0 - 5.0
     return mel.clamp(-11.5, 2.0)
+
+
+def vocoder_f0_inputs(case, hop=240):
+    """mel, f0 [B, 1, T] (Hz; about a third of the frames unvoiced = 0), rand_ini [B, 9], noise [B, L, 9]."""
+    mel = vocoder_inputs(case)
+    g = torch.Generator().manual_seed(case["input_seed"] + 1000)
+    B, T = case["B"], case["T"]
+    f0 = 80.0 + 320.0 * torch.rand(B, 1, T, generator=g)
+    f0 = f0 * (torch.rand(B, 1, T, generator=g) > 0.33).float()
+    gn = torch.Generator().manual_seed(case["noise_seed"])
+    H = F0_KWARGS["harmonic_num"] + 1
+    rand_ini = torch.rand(B, H, generator=gn)
+    noise = _randn(B, T * hop, H, generator=gn)
+    return mel, f0, rand_ini, noise

@@ -134,3 +134,68 @@ def test_acoustic_default_rng_and_shapes():
         n = int(flen[b])
         assert torch.count_nonzero(mel[b, :, n:]) == 0 and torch.count_nonzero(log_cf0[b, :, n:]) == 0
     assert isinstance(model.infer(phoneme[:1, :10].cuda(), style_prompt="one"), torch.Tensor)
+
+
+# ---- F0-aware vocoder (the vocoder app.py / synthesize.py instantiate by default) ----
+
+@pytest.fixture(scope="module")
+def vocoder_f0():
+    from golden_cases import F0_KWARGS
+    from promptttspp_b200.utils.synthetic import build_vocoder_f0
+
+    voc = build_vocoder_f0(**F0_KWARGS)
+    voc.load_state_dict(synthetic_state_dict(voc, seed=4322), strict=True)
+    return voc.cuda().eval()
+
+
+@pytest.mark.parametrize("name", ["b2_t12", "b1_t40"])
+def test_bigvgan_f0_matches_reference_golden(golden_dir, vocoder_f0, name):
+    from golden_cases import VOCODER_F0_CASES, vocoder_f0_inputs
+    from promptttspp_b200.vocoders.nsf import SourceNoise
+
+    case = VOCODER_F0_CASES[name]
+    gold = np.load(golden_dir / f"vocoder_f0_{name}.npz")
+    mel, f0, rand_ini, noise = vocoder_f0_inputs(case)
+    sn = SourceNoise(rand_ini.cuda(), noise.cuda())
+    har = vocoder_f0.m_source(f0[:, 0, :].cuda(), 240, sn).cpu()
+    ref_har = torch.from_numpy(gold["har"])[:, :, 0]
+    err_h = float((har - ref_har).abs().max())
+    print(f"nsf source {name}: max-abs err {err_h:.3e}")
+    assert err_h < 2e-5  # fp32 sin of a phase whose double-accumulated prefix sums are reproduced exactly
+    wav = vocoder_f0(mel.cuda(), f0.cuda(), source_noise=sn).cpu()
+    ref = torch.from_numpy(gold["wav"])
+    assert wav.shape == ref.shape
+    err = _rms(wav, ref)
+    print(f"bigvgan_f0 {name}: rms err {err:.3e}, max-abs {float((wav - ref).abs().max()):.3e}")
+    assert err < WAV_TOL
+
+
+def test_bigvgan_f0_long_against_oracle_and_api(vocoder_f0):
+    """Phase accumulation over a longer utterance (several 256-sample scan chunks per voiced stretch, harmonics that
+    wrap many times), unvoiced-only rows, the default noise path and the argument checks."""
+    from promptttspp_b200.vocoders.nsf import SourceNoise
+
+    sd = {k: v.cpu() for k, v in vocoder_f0.state_dict().items()}
+    g = torch.Generator().manual_seed(31)
+    B, T = 2, 150
+    mel = (torch.randn(B, 80, T, generator=g) * 2 - 5).clamp(-11.5, 2)
+    f0 = 60.0 + 500.0 * torch.rand(B, 1, T, generator=g)
+    f0[:, :, 40:70] = 0
+    f0[1] = 0  # a fully unvoiced utterance
+    rand_ini = torch.rand(B, 9, generator=g)
+    noise = torch.randn(B, T * 240, 9, generator=g)
+    f0_up = torch.nn.functional.interpolate(f0, scale_factor=240.0).transpose(-1, -2)
+    ref_har = oracle.nsf_source(sd, f0_up, rand_ini, noise)[:, :, 0]
+    sn = SourceNoise(rand_ini.cuda(), noise.cuda())
+    har = vocoder_f0.m_source(f0[:, 0, :].cuda(), 240, sn).cpu()
+    assert float((har - ref_har).abs().max()) < 5e-5
+    ref = oracle.bigvgan_f0_forward(sd, oracle.VOCODER_CFG, mel, f0, rand_ini, noise)
+    wav = vocoder_f0(mel.cuda(), f0.cuda(), source_noise=sn).cpu()
+    assert _rms(wav, ref) < WAV_TOL
+    torch.manual_seed(0)
+    w1 = vocoder_f0(mel.cuda(), f0.cuda())
+    torch.manual_seed(0)
+    w2 = vocoder_f0(mel.cuda(), f0.cuda())
+    assert w1.shape == (B, 1, 240 * T) and torch.equal(w1, w2) and torch.isfinite(w1).all()
+    with pytest.raises(ValueError):
+        vocoder_f0(mel.cuda(), f0[:, :, :-1].cuda())

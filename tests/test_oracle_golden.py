@@ -93,3 +93,24 @@ def test_acoustic_oracle_matches_reference(golden_dir, name):
     sat = float((gold["mel"].abs() >= 5.999).float().mean())
     print(f"{name}: mel max-abs err {float(err):.3e}, saturated fraction {sat:.3f}")
     assert float(err) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["b2_t12", "b1_t40"])
+def test_bigvgan_f0_oracle_matches_reference(golden_dir, name):
+    """F0-aware vocoder (bigvgan_f0.py + nsf.py): the oracle restatement against the reference's own output with the
+    reference's three random draws replaced by seeded tensors (tests/golden/make_golden.py: make_vocoder_f0)."""
+    from golden_cases import F0_KWARGS, VOCODER_F0_CASES, vocoder_f0_inputs
+    from promptttspp_b200.utils.synthetic import build_vocoder_f0
+
+    case = VOCODER_F0_CASES[name]
+    gold = np.load(golden_dir / f"vocoder_f0_{name}.npz")
+    voc = build_vocoder_f0(**F0_KWARGS)
+    assert len(voc.state_dict()) == 463  # 453 BigVGAN keys + m_source.l_linear.{weight,bias} + 4 x noise_convs.{weight,bias}
+    sd = synthetic_state_dict(voc, seed=case["weight_seed"])
+    mel, f0, rand_ini, noise = vocoder_f0_inputs(case)
+    hop = 240
+    f0_up = torch.nn.functional.interpolate(f0, scale_factor=float(hop)).transpose(-1, -2)
+    har = oracle.nsf_source(sd, f0_up, rand_ini, noise)
+    assert float((har - torch.from_numpy(gold["har"])).abs().max()) < 1e-6
+    wav = oracle.bigvgan_f0_forward(sd, oracle.VOCODER_CFG, mel, f0, rand_ini, noise)
+    assert float((wav - torch.from_numpy(gold["wav"])).pow(2).mean().sqrt()) < 2e-6
