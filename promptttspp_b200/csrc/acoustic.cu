@@ -72,7 +72,7 @@ struct pttspp_acoustic {
   pttspp::LNW fp_norm_emb;
   std::vector<pttspp::PredLayerW> fp_layers;
   // diffusion
-  pttspp::PackedConv in_proj, cond_all, skip_proj, out_proj;
+  pttspp::PackedConv in_proj, in_proj_tc, cond_all, skip_proj, out_proj;
   std::vector<pttspp::DiffLayerW> diff;
   float* step_table = nullptr;  // [K_step][layers][C]
   bool use_umma = true;         // tcgen05 split-fp16 path for the DiffNet contractions (PTTSPP_DISABLE_UMMA=1: off)
@@ -219,6 +219,7 @@ EncodeWs carve_encode(const pttspp_acoustic_config& c, int B, int Tx, int Tp, Ca
 struct DecodeWs {
   float *xa, *xb, *tmp, *lcf0, *vuv, *condp, *xt, *h, *z, *skip, *s, *eps;
   uint16_t *yh, *yl, *zh, *zl, *sh, *sl, *ph, *pl;  // split-fp16 operand planes [B][Ty][DC]
+  uint16_t *xh, *xl;                                // x_t planes [B][Ty][round_up(mel, 64)]
 };
 
 DecodeWs carve_decode(const pttspp_acoustic_config& c, int B, int Ty, Carver& cv) {
@@ -241,6 +242,7 @@ DecodeWs carve_decode(const pttspp_acoustic_config& c, int B, int Ty, Carver& cv
   w.zh = cv.take<uint16_t>(n * DC); w.zl = cv.take<uint16_t>(n * DC);
   w.sh = cv.take<uint16_t>(n * DC); w.sl = cv.take<uint16_t>(n * DC);
   w.ph = cv.take<uint16_t>(n * DC); w.pl = cv.take<uint16_t>(n * DC);
+  w.xh = cv.take<uint16_t>(n * round_up(c.mel_dim, 64)); w.xl = cv.take<uint16_t>(n * round_up(c.mel_dim, 64));
   return w;
 }
 
@@ -385,6 +387,21 @@ extern "C" int pttspp_acoustic_finalize(pttspp_acoustic_t* h, pttspp_stream_t) {
   const std::string dn = "decoder.denoise_fn.";
   const int DC = c.diff_channels;
   h->in_proj = load_conv1d(st, dev, dn + "input_projection", DC, c.mel_dim, 1, 1, 0);
+  {
+    // tensor-core copy with the mel axis zero-padded to a multiple of 64 (80 -> 128): x_t travels as padded planes
+    const int Mp = round_up(c.mel_dim, 64);
+    const auto& wt = st.get(dn + "input_projection.weight", (int64_t)DC * c.mel_dim).data;  // [DC][mel][1]
+    std::vector<float> wp((size_t)DC * Mp, 0.f);
+    for (int co = 0; co < DC; ++co)
+      for (int ci = 0; ci < c.mel_dim; ++ci) wp[(size_t)co * Mp + ci] = wt[(size_t)co * c.mel_dim + ci];
+    std::vector<uint16_t> hi(wp.size()), lo(wp.size());
+    pack_conv_weight_split(wp.data(), nullptr, DC, Mp, 1, hi.data(), lo.data(), 0, &h->in_proj_tc.w_scale_inv);
+    h->in_proj_tc = h->in_proj;
+    h->in_proj_tc.Cin = Mp;
+    pack_conv_weight_split(wp.data(), nullptr, DC, Mp, 1, hi.data(), lo.data(), 0, &h->in_proj_tc.w_scale_inv);
+    h->in_proj_tc.w_hi = dev.upload_bytes(hi.data(), hi.size() * 2);
+    h->in_proj_tc.w_lo = dev.upload_bytes(lo.data(), lo.size() * 2);
+  }
   std::vector<std::string> cond_names;
   for (int l = 0; l < c.diff_layers; ++l) {
     const std::string p = dn + "residual_layers." + std::to_string(l) + ".";
@@ -640,6 +657,9 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
     conv1d_cl(d, s);
   }
   transpose_bct_to_btc(x_T, w.xt, B, M, Ty, s);
+  const int Mp = round_up(M, 64);
+  const bool tc_inproj = h->use_umma && h->in_proj_tc.w_hi != nullptr;
+  if (tc_inproj) split_f16_pad(w.xt, (int64_t)B * Ty, M, Mp, w.xh, w.xl, s);  // later steps: written by ddpm_update
   const float sqrt2 = sqrtf(2.f);
   const float inv_sqrt_layers = 1.f / sqrtf((float)c.diff_layers);
   const int64_t bsD = (int64_t)Ty * DC;
@@ -657,8 +677,9 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
   for (int step = c.K_step - 1; step >= 0; --step) {
     const float* step_emb = h->step_table + (size_t)step * c.diff_layers * DC;
     {
-      auto d = conv_desc(h->in_proj, w.xt, B, Ty, w.h);
+      auto d = conv_desc(tc_inproj ? h->in_proj_tc : h->in_proj, w.xt, B, Ty, w.h);
       d.act = PTTSPP_ACT_RELU;
+      if (tc_inproj) tc_in(d, w.xh, w.xl, h->in_proj_tc);
       if (um) planes_out(d, w.yh, w.yl, step_emb);  // y_0 = h + step_emb[0] as operand planes
       conv1d_cl(d, s);
     }
@@ -715,7 +736,8 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
     }
     const float sigma = (step > 0) ? expf(0.5f * h->logvar[step]) : 0.f;
     ddpm_update(w.xt, w.eps, z + (size_t)(c.K_step - 1 - step) * B * M * Ty, B, Ty, M, h->c_recip[step],
-                h->c_recipm1[step], h->coef1[step], h->coef2[step], sigma, s);
+                h->c_recipm1[step], h->coef1[step], h->coef2[step], sigma, s, tc_inproj ? w.xh : nullptr,
+                tc_inproj ? w.xl : nullptr, Mp);
   }
   // de-normalise, mask, back to [B][mel][Ty]  (diffusion.py:170-173, model.py:319-320)
   if (c.norm_scale > 0.f)

@@ -2,6 +2,8 @@
 // regulator), MDN heads, the Conformer conv-module middle (GLU -> depthwise -> BatchNorm -> Swish),
 // pitch embedding and the DDPM posterior update.  All use one thread per output element with the
 // channel index fastest (coalesced 128-byte rows) or one warp per row with shuffle reductions.
+#include <cuda_fp16.h>
+
 #include "common.h"
 
 namespace pttspp {
@@ -347,9 +349,12 @@ __global__ void __launch_bounds__(256) pitch_embed_add_kernel(float* __restrict_
 
 // ---- DDPM ancestral step (diffusion.py:181-221) -------------------------------------------
 // x, eps: [B][T][M] channels-last; z: [B][M][T] (the layout torch.randn drew it in).
+// xp_hi/xp_lo (optional): split-fp16 planes [B][T][Mp] of the updated x for the tensor-core input projection of the
+// next step (columns >= M stay zero: the planes are cleared once per call)
 __global__ void __launch_bounds__(256) ddpm_update_kernel(float* __restrict__ x, const float* __restrict__ eps,
                                                           const float* __restrict__ z, int T, int M, float c_recip,
-                                                          float c_recipm1, float coef1, float coef2, float sigma) {
+                                                          float c_recipm1, float coef1, float coef2, float sigma,
+                                                          __half* __restrict__ xp_hi, __half* __restrict__ xp_lo, int Mp) {
   __shared__ float zt[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
@@ -368,7 +373,14 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(float* __restrict__ x,
       float x0 = c_recip * xv - c_recipm1 * eps[idx];
       x0 = fminf(fmaxf(x0, -1.f), 1.f);
       const float mean = coef1 * x0 + coef2 * xv;
-      x[idx] = mean + sigma * zt[tx][i];
+      const float xn = mean + sigma * zt[tx][i];
+      x[idx] = xn;
+      if (xp_hi) {
+        const int64_t pidx = ((int64_t)b * T + t) * Mp + m;
+        const __half hh = __float2half_rn(xn);
+        xp_hi[pidx] = hh;
+        xp_lo[pidx] = __float2half_rn(xn - __half2float(hh));
+      }
     }
   }
 }
@@ -489,10 +501,11 @@ void pitch_embed_add(float* x, const float* log_cf0, const float* w, const float
 }
 
 void ddpm_update(float* x, const float* eps, const float* z, int B, int T, int M, float c_recip, float c_recipm1,
-                 float coef1, float coef2, float sigma, cudaStream_t s) {
+                 float coef1, float coef2, float sigma, cudaStream_t s, void* xp_hi, void* xp_lo, int Mp) {
   if (B == 0 || T == 0) return;
   dim3 grid(ceil_div(T, 32), ceil_div(M, 32), B);
-  ddpm_update_kernel<<<grid, 256, 0, s>>>(x, eps, z, T, M, c_recip, c_recipm1, coef1, coef2, sigma);
+  ddpm_update_kernel<<<grid, 256, 0, s>>>(x, eps, z, T, M, c_recip, c_recipm1, coef1, coef2, sigma, (__half*)xp_hi,
+                                          (__half*)xp_lo, Mp);
   PT_LAUNCHED();
 }
 

@@ -129,7 +129,9 @@ void pitch_embed_add(float* x, const float* log_cf0, const float* w, const float
                      int T, int C, cudaStream_t s);
 void ddpm_update(float* x /*[B][T][M]*/, const float* eps /*[B][T][M]*/, const float* z /*[B][M][T]*/, int B,
                  int T, int M, float c_recip, float c_recipm1, float coef1, float coef2, float sigma,
-                 cudaStream_t s);
+                 cudaStream_t s, void* xp_hi = nullptr, void* xp_lo = nullptr, int Mp = 0);
+// [rows][C] fp32 -> split-fp16 planes [rows][Cp] (Cp >= C, columns >= C written as zeros)
+void split_f16_pad(const float* x, int64_t rows, int C, int Cp, void* hi, void* lo, cudaStream_t s);
 
 
 // ---- host-side tensor store + device buffers shared by the model-level handles -------------

@@ -169,7 +169,10 @@ void conv1d_cl(const pttspp_conv1d_desc& d, cudaStream_t s) {
   PT_CHECK(d.in && d.w, "conv1d: the CUDA-core path needs fp32 `in` and packed fp32 weights `w`");
   PT_CHECK(d.in_ld % 4 == 0 && aligned16(d.in), "conv1d: input must be 16-byte aligned, ld %% 4 == 0");
   PT_CHECK(d.w_ld % 4 == 0 && d.w_ld >= d.Cout && aligned16(d.w), "conv1d: packed weight ld=%d invalid", d.w_ld);
-  if (d.Cout > 64)
+  // few large tiles leave SMs idle on short sequences (the encoder's 1024 -> 256 k9 conv at Tx = 256 ran 64 CTAs):
+  // take the 64-column tile when the 128-column grid would not fill the machine
+  const long long ctas128 = (long long)ceil_div(d.M, 128) * ceil_div(d.Cout, 128) * d.B;
+  if (d.Cout > 64 && ctas128 >= 120)
     launch_simt<128, 128, 8, 8>(d, s);
   else if (d.Cout > 32)
     launch_simt<128, 64, 8, 4>(d, s);
@@ -308,6 +311,29 @@ __global__ void __launch_bounds__(256) split_f16_rows_kernel(const float* __rest
                      (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
 }
 }  // namespace
+
+namespace {
+__global__ void __launch_bounds__(256) split_f16_pad_kernel(const float* __restrict__ x, int64_t rows, int C, int Cp,
+                                                            __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * Cp) return;
+  const int64_t r = i / Cp;
+  const int c = (int)(i - r * Cp);
+  const float v = (c < C) ? x[r * C + c] : 0.f;
+  __half h, l;
+  split_f16(v, h, l);
+  hi[i] = h;
+  lo[i] = l;
+}
+}  // namespace
+
+void split_f16_pad(const float* x, int64_t rows, int C, int Cp, void* hi, void* lo, cudaStream_t s) {
+  PT_CHECK(x && hi && lo && C >= 1 && Cp >= C, "split_f16_pad: bad argument");
+  if (rows == 0) return;
+  ProfScope prof(PROF_OTHER, s, 0.0, 4.0 * (double)rows * (C + Cp));
+  split_f16_pad_kernel<<<(unsigned)ceil_div64(rows * Cp, 256), 256, 0, s>>>(x, rows, C, Cp, (__half*)hi, (__half*)lo);
+  PT_LAUNCHED();
+}
 
 void split_f16_rows(const float* x, int B, int T, int C, const int64_t* len, void* hi, void* lo, cudaStream_t s) {
   PT_CHECK(x && hi && lo && C % 4 == 0 && aligned16(x) && aligned16(hi) && aligned16(lo), "split_f16_rows: bad argument");
