@@ -129,24 +129,43 @@ def prof_report(lib):
     return [dict(kernel=TAGS[i], ms=ms[i], flops=fl[i], bytes=by[i], calls=calls[i]) for i in range(n)]
 
 
-def roofline_from(report, pk, in_long_step):
+def ncu_traffic(kernel, rows):
+    """DRAM bytes per launch of `kernel`'s family from the committed ncu --set full capture (profiles/), scaled from
+    the capture's row count to this run's; None when no capture covers the family."""
+    p = ROOT / "profiles" / "r01_ncu_traffic.json"
+    if not p.exists():
+        return None, None
+    t = json.loads(p.read_text())
+    if kernel == "conv1d_tcgen05_splitfp16" and "pair_dilated_gate" in t and "pair_dual_1x1" in t and rows:
+        per = 0.5 * (t["pair_dilated_gate"]["dram_bytes_per_launch"] + t["pair_dual_1x1"]["dram_bytes_per_launch"])
+        return per * rows / t["_rows"], ("profiles/r01_ncu_traffic.json: mean of the two DiffNet CTA-pair kernels "
+                                         f"(dilated+gate, dual 1x1), scaled {t['_rows']} -> {int(rows)} rows")
+    if kernel == "aa_snake" and "aa_snake" in t:
+        return t["aa_snake"]["dram_bytes_per_launch"], "profiles/r01_ncu_traffic.json (captured launch, not rescaled)"
+    return None, None
+
+
+def roofline_from(report, pk, in_long_step, rows=None):
     """Dominant kernel family of one profiled step -> the `roofline` object."""
     top = max(report, key=lambda r: r["ms"])
     if top["ms"] <= 0 or top["calls"] == 0:
         return None
+    traffic, traffic_src = ncu_traffic(top["kernel"], rows)
     if top["flops"] > 0:
         peak = pk["tf_sustained"] if in_long_step else pk["tf_burst"]
         ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
         return {"bound": "tensor", "kernel": top["kernel"], "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": None, "launches": top["calls"],
+                "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "launches": top["calls"],
                 "avg_launch_ms": top["ms"] / top["calls"], "share_of_step": top["ms"] / sum(r["ms"] for r in report),
+                "mma_frac": (3.0 * ach / peak) if top["kernel"] == TAGS[1] else None,
                 "peak_source": pk["source"] + (", bf16 dense sustained" if in_long_step else ", bf16 dense burst"),
                 "note": ("fp32 CUDA-core FFMA path; the tensor peak is the contract's denominator"
                          if top["kernel"] == TAGS[0] else
-                         "split-fp16 (3 tcgen05 MMAs per fp32 product): ceiling = 1/3 of the bf16 peak")}
+                         "split-fp16 (3 tcgen05 MMAs per fp32 product): ceiling = 1/3 of the bf16 peak; mma_frac = "
+                         "issued fp16 MMA FLOPs / peak")}
     ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": top["kernel"], "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-            "frac": ach / pk["hbm"], "traffic": None, "launches": top["calls"],
+            "frac": ach / pk["hbm"], "traffic": traffic, "traffic_source": traffic_src, "launches": top["calls"],
             "avg_launch_ms": top["ms"] / top["calls"], "share_of_step": top["ms"] / sum(r["ms"] for r in report),
             "peak_source": pk["source"]}
 
@@ -325,7 +344,7 @@ def run_native(args, rank, local_rank, world):
     if rank == 0:
         cpu_ac, _ = cpu_acoustic_sample(1, 0) if world == 1 and not args.no_cpu else (None, None)
         cpu_voc = cpu_bigvgan_sample(1, 0) if world == 1 and not args.no_cpu else None
-        roof_ac = roofline_from(rep_ac, pk, in_long_step=True)
+        roof_ac = roofline_from(rep_ac, pk, in_long_step=True, rows=float(padded) / world)
         roof_voc = roofline_from(rep_voc, pk, in_long_step=True)
         frames_s = float(valid) / (ms_dev * 1e-3)
         line = {
