@@ -191,6 +191,13 @@ int pttspp_duration_quantize(const float* log_d, const int64_t* phone_len, int B
 int pttspp_length_regulate(const float* x, const int64_t* dur, int B, int Tx, int C, int Ty, float* out,
                            int32_t* idx_out /* optional [B][Ty], -1 on padding */, pttspp_stream_t stream);
 
+/* Zero-phase IIR filter of rows x[rows][T] -> y (scratch: rows*T floats): torchaudio.functional.filtfilt(x, a, b,
+ * clamp=False), i.e. lfilter forward, flip, lfilter, flip, zero initial state, coefficients normalised by a[0]; b/a:
+ * ntaps (<= 8) device floats.  Replaces the torch branch of promptttspp/utils/model.py:164-196 (the 5th-order
+ * Butterworth low-pass app.py:77 applies to log-f0 between the acoustic model and the vocoder). */
+int pttspp_iir_filtfilt(const float* x, float* y, float* scratch, int rows, int T, const float* b_coeffs,
+                        const float* a_coeffs, int ntaps, pttspp_stream_t stream);
+
 /* Relative-position multi-head self-attention (Transformer-XL style), both ESPnet variants.
  *   scores = ((q+u) k^T + rel_shift((q+v) p^T)) / sqrt(d_k); masked softmax; . v
  * q,k,v,out: [B][T][H*d_k]; p: [Tp][H*d_k] with Tp = T (legacy) or 2T-1 (new);

@@ -118,6 +118,19 @@ def bigvgan_forward(sd, cfg, mel):
     return torch.tanh(x)
 
 
+def lowpass_filter(x, fs=100, cutoff=20, N=5):
+    """utils/model.py:164-196, the torch branch (app.py:77 applies it to log-f0): scipy.signal.butter coefficients,
+    short-input pass-through, torchaudio.functional.filtfilt(x, a, b, clamp=False)."""
+    from scipy import signal
+    from torchaudio.functional import filtfilt
+
+    nyquist = fs // 2
+    b, a = signal.butter(N, [cutoff / nyquist], "lowpass")
+    if x.shape[-1] <= max(len(a), len(b)) * (N // 2 + 1):
+        return x
+    return filtfilt(x, torch.from_numpy(a).float(), torch.from_numpy(b).float(), clamp=False)
+
+
 def nsf_source(sd, f0_up, rand_ini, noise, sampling_rate=24000.0, harmonic_num=8, sine_amp=0.1, noise_std=0.003,
                voiced_threshold=0.0):
     """SourceModuleHnNSF.forward (vocoders/nsf.py:193-206) over SineGen.forward (:116-148) and SineGen._f02sine

@@ -104,6 +104,8 @@ SIGNATURES = {
     "pttspp_length_regulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
     "pttspp_relpos_attention": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pttspp_iir_filtfilt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_void_p]),
     "pttspp_bigvgan_create": (C.c_int, [C.POINTER(BigVGANConfig), C.POINTER(C.c_void_p)]),
     "pttspp_bigvgan_destroy": (None, [C.c_void_p]),
     "pttspp_bigvgan_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, c_i64p, C.c_int, C.c_void_p]),

@@ -385,6 +385,53 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(float* __restrict__ x,
   }
 }
 
+
+// ---- zero-phase IIR filter of the f0 contour (utils/model.py:164-196 -> torchaudio.functional.filtfilt) -------------
+// filtfilt(x, a, b, clamp=False) = flip(lfilter(flip(lfilter(x)))) with zero initial state and no edge padding
+// (torchaudio's, not scipy's, convention).  The recursion is sequential in time; rows (utterances) are independent and
+// short (a few thousand 10-ms frames), so one thread owns one row and a ring of the last NT-1 inputs / outputs.
+constexpr int IIR_MAX_TAPS = 8;
+__global__ void __launch_bounds__(64) iir_filtfilt_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                          float* __restrict__ tmp, int rows, int T,
+                                                          const float* __restrict__ bc, const float* __restrict__ ac, int nt) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float b[IIR_MAX_TAPS], a[IIR_MAX_TAPS];
+  const float a0 = ac[0];
+#pragma unroll
+  for (int k = 0; k < IIR_MAX_TAPS; ++k) {
+    b[k] = (k < nt) ? bc[k] / a0 : 0.f;  // lfilter normalises both coefficient sets by a[0]
+    a[k] = (k < nt) ? ac[k] / a0 : 0.f;
+  }
+  const float* xr = x + (int64_t)r * T;
+  float* t1 = tmp + (int64_t)r * T;
+  float* yr = y + (int64_t)r * T;
+  for (int pass = 0; pass < 2; ++pass) {
+    // pass 0: forward over x -> t1; pass 1: backward over t1 -> y (a forward filter of the flipped signal)
+    float xin[IIR_MAX_TAPS], yo[IIR_MAX_TAPS];
+#pragma unroll
+    for (int k = 0; k < IIR_MAX_TAPS; ++k) xin[k] = yo[k] = 0.f;
+    for (int n = 0; n < T; ++n) {
+      const int idx = pass ? (T - 1 - n) : n;
+      const float v = pass ? t1[idx] : xr[idx];
+#pragma unroll
+      for (int k = IIR_MAX_TAPS - 1; k > 0; --k) {
+        xin[k] = xin[k - 1];
+        yo[k] = yo[k - 1];
+      }
+      xin[0] = v;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < IIR_MAX_TAPS; ++k) acc = fmaf(b[k], xin[k], acc);
+#pragma unroll
+      for (int k = 1; k < IIR_MAX_TAPS; ++k) acc = fmaf(-a[k], yo[k], acc);
+      yo[0] = acc;
+      if (pass) yr[idx] = acc;
+      else t1[idx] = acc;
+    }
+  }
+}
+
 }  // namespace
 
 static inline unsigned blocks_for(int64_t n, int per) { return (unsigned)ceil_div64(n, per); }
@@ -522,5 +569,23 @@ extern "C" int pttspp_length_regulate(const float* x, const int64_t* dur, int B,
                                       int32_t* idx_out, pttspp_stream_t stream) {
   PT_API_BEGIN
   pttspp::length_regulate(x, dur, B, Tx, C, Ty, out, idx_out, (cudaStream_t)stream);
+  PT_API_END
+}
+
+namespace pttspp {
+void iir_filtfilt(const float* x, float* y, float* tmp, int rows, int T, const float* b, const float* a, int ntaps,
+                  cudaStream_t s) {
+  PT_CHECK(x && y && tmp && b && a, "iir_filtfilt: null pointer");
+  PT_CHECK(ntaps >= 1 && ntaps <= IIR_MAX_TAPS, "iir_filtfilt: 1..%d coefficients supported", IIR_MAX_TAPS);
+  if (rows <= 0 || T <= 0) return;
+  iir_filtfilt_kernel<<<ceil_div(rows, 64), 64, 0, s>>>(x, y, tmp, rows, T, b, a, ntaps);
+  PT_LAUNCHED();
+}
+}  // namespace pttspp
+
+extern "C" int pttspp_iir_filtfilt(const float* x, float* y, float* scratch, int rows, int T, const float* b_coeffs,
+                                   const float* a_coeffs, int ntaps, pttspp_stream_t stream) {
+  PT_API_BEGIN
+  pttspp::iir_filtfilt(x, y, scratch, rows, T, b_coeffs, a_coeffs, ntaps, (cudaStream_t)stream);
   PT_API_END
 }

@@ -210,6 +210,19 @@ def make_vocoder_f0():
         np.savez_compressed(OUT / f"vocoder_f0_{name}.npz", wav=wav.numpy(), har=har.numpy())
 
 
+def make_lowpass():
+    """promptttspp.utils.model.lowpass_filter (the reference's own function) on seeded log-f0-like contours."""
+    sys.path.insert(0, str(REF))
+    from promptttspp.utils.model import lowpass_filter as ref_lowpass
+    from golden_cases import lowpass_inputs
+
+    out = {}
+    for i, x in enumerate(lowpass_inputs()):
+        out[f"y{i}"] = ref_lowpass(x, 100, cutoff=20).numpy()
+    np.savez_compressed(OUT / "lowpass.npz", **out)
+    print("lowpass", {k: v.shape for k, v in out.items()})
+
+
 def make_ops():
     """Op-level vectors from the reference layers: pin the closed forms used by the kernels."""
     sys.path.insert(0, str(REF))
@@ -254,13 +267,15 @@ def make_ops():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops", "vocoder", "vocoder_f0", "acoustic"]
+    which = sys.argv[1:] or ["ops", "vocoder", "vocoder_f0", "lowpass", "acoustic"]
     if "ops" in which:
         make_ops()
     if "vocoder" in which:
         make_vocoder()
     if "vocoder_f0" in which:
         make_vocoder_f0()
+    if "lowpass" in which:
+        make_lowpass()
     if "acoustic" in which:
         make_acoustic(reference_namespace())
     print("done")

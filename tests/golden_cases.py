@@ -79,3 +79,10 @@ def vocoder_f0_inputs(case, hop=240):
     rand_ini = torch.rand(B, H, generator=gn)
     noise = _randn(B, T * hop, H, generator=gn)
     return mel, f0, rand_ini, noise
+
+
+def lowpass_inputs():
+    """log-f0-like contours [B, 1, T]: a long ragged batch, a single row, and one short enough for the pass-through."""
+    g = torch.Generator().manual_seed(77)
+    return [5.0 + 0.5 * torch.randn(3, 1, 400, generator=g).cumsum(-1) * 0.1, 4.0 + torch.randn(1, 1, 57, generator=g),
+            torch.randn(2, 1, 17, generator=g)]

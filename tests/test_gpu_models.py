@@ -199,3 +199,30 @@ def test_bigvgan_f0_long_against_oracle_and_api(vocoder_f0):
     assert w1.shape == (B, 1, 240 * T) and torch.equal(w1, w2) and torch.isfinite(w1).all()
     with pytest.raises(ValueError):
         vocoder_f0(mel.cuda(), f0[:, :, :-1].cuda())
+
+
+def test_app_py_flow_acoustic_to_f0_vocoder(vocoder_f0):
+    """The sequence app.py:56-81 runs: infer(return_f0) -> lowpass_filter(log_cf0) -> exp, vuv mask -> de-normalise ->
+    vocoder(mel, f0).  Stage parity is covered above on identical inputs; here the stages are chained through the public
+    API (shapes, finiteness, determinism under a fixed seed)."""
+    from promptttspp_b200.utils.model import lowpass_filter
+
+    case = dict(ACOUSTIC_CASES["legacy_infer"], K_step=8)
+    phoneme, lengths, cls_emb = acoustic_inputs(case)
+    model = build_acoustic(bert=FixedPromptEmbedding(cls_emb), K_step=case["K_step"])
+    model.load_state_dict(synthetic_state_dict(model, seed=case["weight_seed"], frames_per_phoneme=3.0), strict=True)
+    model = model.cuda().eval()
+
+    def run():
+        torch.manual_seed(5)
+        dec, log_cf0, vuv = model.infer(phoneme.cuda(), style_prompt=["a calm voice"], use_max=True, noise_scale=0.5,
+                                        return_f0=True)
+        log_cf0 = lowpass_filter(log_cf0, int(1.0 / (10 * 0.001)), cutoff=20)
+        f0 = log_cf0.exp()
+        f0[vuv < 0.5] = 0
+        dec = dec * 2.0 + (-5.0)
+        return vocoder_f0(dec, f0).squeeze(1).cpu()
+
+    w1, w2 = run(), run()
+    assert w1.dim() == 2 and w1.shape[1] % 240 == 0 and torch.isfinite(w1).all()
+    assert torch.equal(w1, w2)

@@ -244,3 +244,21 @@ def test_relpos_attention(ops, legacy, T, lens):
     ref = torch.matmul(attn, vh).transpose(1, 2).reshape(B, T, H * dk)
     out = ops.relpos_attention(q.cuda(), k.cuda(), v.cuda(), p.cuda(), bu.cuda(), bv.cuda(), lens.cuda(), H, legacy)
     assert torch.allclose(out.cpu(), ref, atol=5e-5), float((out.cpu() - ref).abs().max())
+
+
+def test_lowpass_filter_matches_reference_golden(golden_dir):
+    """pttspp_iir_filtfilt behind utils.model.lowpass_filter vs the reference function's output (app.py:77 path)."""
+    import numpy as np
+    from golden_cases import lowpass_inputs
+    from promptttspp_b200.utils.model import lowpass_filter
+
+    gold = np.load(golden_dir / "lowpass.npz")
+    for i, x in enumerate(lowpass_inputs()):
+        y = lowpass_filter(x.cuda(), 100, cutoff=20).cpu()
+        ref = torch.from_numpy(gold[f"y{i}"])
+        assert y.shape == ref.shape
+        err = float((y - ref).abs().max())
+        print(f"lowpass case {i}: max-abs err {err:.2e}")
+        assert err < 2e-5
+    with pytest.raises(RuntimeError):
+        lowpass_filter(torch.zeros(1, 1, 100))  # CPU tensor: no host fallback

@@ -114,3 +114,21 @@ def test_bigvgan_f0_oracle_matches_reference(golden_dir, name):
     assert float((har - torch.from_numpy(gold["har"])).abs().max()) < 1e-6
     wav = oracle.bigvgan_f0_forward(sd, oracle.VOCODER_CFG, mel, f0, rand_ini, noise)
     assert float((wav - torch.from_numpy(gold["wav"])).pow(2).mean().sqrt()) < 2e-6
+
+
+def test_lowpass_oracle_and_butterworth_match_reference(golden_dir):
+    """f0 smoothing between acoustic model and vocoder (utils/model.py:164-196): oracle vs the reference's own output,
+    and the package's scipy-free Butterworth design vs scipy.signal.butter."""
+    from golden_cases import lowpass_inputs
+    from promptttspp_b200.utils.model import butter_lowpass
+    from scipy import signal
+
+    gold = np.load(golden_dir / "lowpass.npz")
+    for i, x in enumerate(lowpass_inputs()):
+        y = oracle.lowpass_filter(x, 100, cutoff=20)
+        assert float((y - torch.from_numpy(gold[f"y{i}"])).abs().max()) < 1e-6
+    assert torch.equal(oracle.lowpass_filter(lowpass_inputs()[2]), lowpass_inputs()[2])  # too short: returned as is
+    for N, Wn in ((5, 0.4), (3, 0.2), (5, 0.1)):
+        b, a = butter_lowpass(N, Wn)
+        bs, as_ = signal.butter(N, [Wn], "lowpass")
+        assert np.abs(b - bs).max() < 1e-12 and np.abs(a - as_).max() < 1e-12
