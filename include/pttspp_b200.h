@@ -118,6 +118,16 @@ typedef struct {
   const float* out_plane_add; /* optional [output columns] */
   int64_t out_plane_bs;
   int32_t out_plane_ld;
+  /* Residual taken from split-fp16 planes instead of `res` (which must then be NULL):
+   *   r[row, c] = float(res_hi[row, c]) + float(res_lo[row, c]) - res_plane_sub[c]
+   * DiffNet's residual stream h travels only as the operand planes y = h + step_emb[l] of the next dilated conv; the
+   * 1x1 output projection recovers h from them (denoiser.py:79-83) and no fp32 copy of h is stored.  Supported by the
+   * CTA-pair tcgen05 kernel (which such a launch always takes). */
+  const void* res_hi;
+  const void* res_lo;
+  const float* res_plane_sub; /* optional [output columns] */
+  int64_t res_plane_bs;
+  int32_t res_plane_ld;
 } pttspp_conv1d_desc;
 
 int pttspp_conv1d_cl(const pttspp_conv1d_desc* d, pttspp_stream_t stream);

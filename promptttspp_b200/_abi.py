@@ -35,6 +35,8 @@ class Conv1dDesc(C.Structure):
         ("in_hi", C.c_void_p), ("in_lo", C.c_void_p), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p),
         ("w_scale_inv", C.c_float), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_plane_add", C.c_void_p),
         ("out_plane_bs", C.c_int64), ("out_plane_ld", C.c_int32),
+        ("res_hi", C.c_void_p), ("res_lo", C.c_void_p), ("res_plane_sub", C.c_void_p), ("res_plane_bs", C.c_int64),
+        ("res_plane_ld", C.c_int32),
     ]
 
 

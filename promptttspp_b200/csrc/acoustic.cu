@@ -664,6 +664,8 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
   const float inv_sqrt_layers = 1.f / sqrtf((float)c.diff_layers);
   const int64_t bsD = (int64_t)Ty * DC;
   const bool um = h->use_umma;
+  // PTTSPP_H_FP32=1 keeps an fp32 copy of the residual stream (the pre-planes behaviour, for A/B measurements)
+  const bool h_planes = um && tc_inproj && DC % 16 == 0 && getenv("PTTSPP_H_FP32") == nullptr;
   auto planes_in = [&](pttspp_conv1d_desc& q, const uint16_t* hi, const uint16_t* lo, const PackedConv& pc, int row_off) {
     q.in_hi = hi; q.in_lo = lo; q.in_bs = bsD; q.in_ld = DC;
     q.w_hi = (const uint16_t*)pc.w_hi + (size_t)row_off * pc.Cin;
@@ -680,7 +682,10 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
       auto d = conv_desc(tc_inproj ? h->in_proj_tc : h->in_proj, w.xt, B, Ty, w.h);
       d.act = PTTSPP_ACT_RELU;
       if (tc_inproj) tc_in(d, w.xh, w.xl, h->in_proj_tc);
-      if (um) planes_out(d, w.yh, w.yl, step_emb);  // y_0 = h + step_emb[0] as operand planes
+      if (um) {
+        planes_out(d, w.yh, w.yl, step_emb);  // y_0 = h + step_emb[0] as operand planes
+        if (h_planes) d.out = nullptr;        // the residual stream travels only as those planes
+      }
       conv1d_cl(d, s);
     }
     for (int l = 0; l < c.diff_layers; ++l) {
@@ -706,6 +711,12 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
       if (um) {
         planes_in(r, w.zh, w.zl, lw.outp, 0);
         if (!last) planes_out(r, w.yh, w.yl, step_emb + (size_t)(l + 1) * DC);  // next layer's conv input
+        if (h_planes) {
+          // h = y - step_emb[l] from the planes (in place: every element is read and rewritten by the same thread)
+          r.res = nullptr; r.out = nullptr;
+          r.res_hi = w.yh; r.res_lo = w.yl; r.res_plane_sub = step_emb + (size_t)l * DC;
+          r.res_plane_bs = bsD; r.res_plane_ld = DC;
+        }
       } else {
         conv1d_cl(r, s);
       }
@@ -716,7 +727,8 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
       if (um) {
         planes_in(k, w.zh, w.zl, lw.outp, DC);
         if (last) planes_out(k, w.sh, w.sl, nullptr);  // operand planes of the skip sum
-        conv1d_umma_dual_cl(r, k, s);                   // one launch, two epilogues (residual | skip)
+        if (last && h_planes) conv1d_cl(k, s);          // the last layer's residual half has no consumer
+        else conv1d_umma_dual_cl(r, k, s);              // one launch, two epilogues (residual | skip)
       } else {
         conv1d_cl(k, s);
       }

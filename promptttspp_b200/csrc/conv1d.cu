@@ -148,6 +148,8 @@ bool conv1d_umma_supported(const pttspp_conv1d_desc& d);
 void conv1d_cl(const pttspp_conv1d_desc& d, cudaStream_t s) {
   PT_CHECK(d.out || d.out_hi, "conv1d: no output (out and out_hi are NULL)");
   PT_CHECK(!d.out_hi || d.out_lo, "conv1d: out_hi without out_lo");
+  PT_CHECK(!d.res_hi || (d.res_lo && !d.res && (d.impl == 2 || (d.impl == 0 && conv1d_umma_supported(d)))),
+           "conv1d: res_hi needs res_lo, no fp32 res, and the tcgen05 path");
   PT_CHECK(d.Cin > 0 && d.Cin % BK == 0, "conv1d: Cin=%d must be a positive multiple of %d", d.Cin, BK);
   PT_CHECK(!d.in_add || aligned16(d.in_add), "conv1d: in_add must be 16-byte aligned");
   PT_CHECK(d.K >= 1 && d.dil >= 1 && d.in_stride >= 1 && d.out_mul >= 1, "conv1d: bad geometry");

@@ -437,7 +437,12 @@ __device__ __forceinline__ void epi_rl_load_operand(const pttspp_conv1d_desc& de
 #pragma unroll
     for (int e = 0; e < 8; ++e) dst[k].v[e] = 0.f;
   }
-  if (ok && kind != 0 && col < de.Cout) {
+  if (ok && kind == 4 && col < de.Cout) {
+    // 16 halves of each plane = one 256-bit load each; kept as raw bits, decoded by the consumer
+    const int64_t pidx = (int64_t)b * de.res_plane_bs + (int64_t)row * de.res_plane_ld + col;
+    dst[0] = ldg256(reinterpret_cast<const float*>(reinterpret_cast<const __half*>(de.res_hi) + pidx));
+    dst[1] = ldg256(reinterpret_cast<const float*>(reinterpret_cast<const __half*>(de.res_lo) + pidx));
+  } else if (ok && kind != 0 && col < de.Cout) {
     const float* src = (kind == 1) ? de.addend + (int64_t)b * de.addend_bs + (int64_t)row * de.addend_ld
                      : (kind == 2) ? de.res + (int64_t)b * de.res_bs + (int64_t)row * de.res_ld
                                    : de.out + (int64_t)b * de.out_bs + (int64_t)row * de.out_ld;
@@ -456,6 +461,16 @@ __device__ __forceinline__ void epi_rl_prefetch_tile(const pttspp_conv1d_desc& d
   const int m = de.m_begin + mt * UM_BM + q * 32 + lane;
   const int row = m * de.out_mul + de.out_off;
   if (!((m < de.m_begin + de.M) && row >= 0 && row < de.T_out)) return;
+  if (kind == 4) {  // residual planes: 32 columns = 64 bytes of each plane
+    const int64_t pidx = (int64_t)b * de.res_plane_bs + (int64_t)row * de.res_plane_ld + n0 + cbeg;
+#pragma unroll
+    for (int c = 0; c < CW; c += 32)
+      if (n0 + cbeg + c < de.Cout) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const __half*>(de.res_hi) + pidx + c));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const __half*>(de.res_lo) + pidx + c));
+      }
+    return;
+  }
   const float* src = (kind == 1) ? de.addend + (int64_t)b * de.addend_bs + (int64_t)row * de.addend_ld
                    : (kind == 2) ? de.res + (int64_t)b * de.res_bs + (int64_t)row * de.res_ld
                                  : de.out + (int64_t)b * de.out_bs + (int64_t)row * de.out_ld;
@@ -570,6 +585,22 @@ __device__ __forceinline__ void umma_tile_epilogue_rl(const pttspp_conv1d_desc& 
           for (int e = 0; e < 8; ++e) {
             v[e] += de.res_scale * r0.v[e];
             v[8 + e] += de.res_scale * r1.v[e];
+          }
+        } else if (kind == 4) {
+          // residual from operand planes: r = hi + lo - sub  (pre[c][0] = 16 hi halves, pre[c][1] = 16 lo halves)
+#pragma unroll
+          for (int p2 = 0; p2 < 8; ++p2) {
+            const uint32_t hb = __float_as_uint(pre[c][0].v[p2]), lb = __float_as_uint(pre[c][1].v[p2]);
+            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hb));
+            const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lb));
+            float r0 = hf.x + lf.x, r1 = hf.y + lf.y;
+            if (de.res_plane_sub) {
+              const float2 sb = __ldg(reinterpret_cast<const float2*>(de.res_plane_sub + col + 2 * p2));
+              r0 -= sb.x;
+              r1 -= sb.y;
+            }
+            v[2 * p2] += de.res_scale * r0;
+            v[2 * p2 + 1] += de.res_scale * r1;
           }
         }
         if (de.out && de.beta != 0.f) {
@@ -1640,6 +1671,9 @@ bool epilogue_rl_ok(const pttspp_conv1d_desc& d) {
   if (!okf(d.addend, d.addend_bs, d.addend_ld) || !okf(d.res, d.res_bs, d.res_ld) || !okf(d.out, d.out_bs, d.out_ld))
     return false;
   if (d.out_hi && !(a32(d.out_hi) && a32(d.out_lo) && d.out_plane_bs % 16 == 0 && d.out_plane_ld % 16 == 0)) return false;
+  if (d.res_hi && !(d.res_lo && !d.res && a32(d.res_hi) && a32(d.res_lo) && d.res_plane_bs % 16 == 0 &&
+                    d.res_plane_ld % 16 == 0 && (!d.res_plane_sub || aligned16(d.res_plane_sub))))
+    return false;
   return true;
 }
 
@@ -1653,6 +1687,7 @@ bool flatten_batch_ok(const pttspp_conv1d_desc& d) {
   if (d.res && d.res_bs != (int64_t)d.T_out * d.res_ld) return false;
   if (d.addend && d.addend_bs != (int64_t)d.T_out * d.addend_ld) return false;
   if (d.out_hi && d.out_plane_bs != (int64_t)d.T_out * d.out_plane_ld) return false;
+  if (d.res_hi && d.res_plane_bs != (int64_t)d.T_out * d.res_plane_ld) return false;
   return (int64_t)d.B * d.T_in < (1ll << 30);
 }
 void flatten_batch(pttspp_conv1d_desc& d) {
@@ -1700,7 +1735,8 @@ int pair_kernel_setup(int num_sms, bool debug) {
 bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool dual, int cout1, int total_cout,
                              cudaStream_t s, int num_sms) {
   const char* env = getenv("PTTSPP_UMMA_PAIR");
-  if (env && env[0] == '0') return false;
+  const bool needs_pair = d.res_hi != nullptr || (dual && d2.res_hi != nullptr);  // only this kernel's epilogue reads it
+  if (env && env[0] == '0' && !needs_pair) return false;
   if (!epilogue_co_ok(d) || (dual && !epilogue_co_ok(d2))) return false;
   if (total_cout % UP_BN != 0 || d.Cin % UM_BK != 0 || d.Cin / UM_BK > UP_MAX_SLAB) return false;
   if (d.K * d.Cin / 16 > 64) return false;  // long contractions keep the multi-accumulator streaming kernel
@@ -1715,7 +1751,8 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
   const int ew = 16;  // epilogue warps (8 measured slower: tools/bench_conv.py history in profiles/)
   // row-per-lane 256-bit epilogue (no staging tile) whenever the alignment allows it; PTTSPP_UMMA_RL=0: coalescing one
   const char* rle = getenv("PTTSPP_UMMA_RL");
-  const bool epi_rl = epilogue_rl_ok(d) && (!dual || epilogue_rl_ok(d2)) && !(rle && rle[0] == '0');
+  const bool epi_rl = epilogue_rl_ok(d) && (!dual || epilogue_rl_ok(d2)) && (needs_pair || !(rle && rle[0] == '0'));
+  PT_CHECK(!needs_pair || epi_rl, "conv1d: a residual from operand planes needs 32-byte aligned tensors (row-per-lane epilogue)");
   const size_t fixed = a_bytes + (epi_rl ? 0 : (size_t)ew * 2048) + (2 * UP_MAX_SLAB + 2 * 6 + 8) * 8 + 16 + 1024;
   const size_t cap = 227 * 1024;
   if (fixed + 3 * UP_BST_BYTES > cap) return false;
@@ -1725,7 +1762,7 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
   if (n_tiles >= (1ll << 30)) return false;
   // worth it only when every pair gets at least a couple of tiles (the activation block is loaded per unit)
   // and when the activation block is reused by at least two N tiles (otherwise the streaming kernel is faster)
-  if (!(env && env[0] == '2') && (n_tiles < num_sms || n_nt < 2)) return false;
+  if (!(env && env[0] == '2') && !needs_pair && (n_tiles < num_sms || n_nt < 2)) return false;
 
   const uint64_t wdims[2] = {(uint64_t)d.Cin, (uint64_t)d.K * total_cout};
   const uint64_t wstr[1] = {(uint64_t)d.Cin * 2};
@@ -1884,6 +1921,9 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
   const int total_cout = d.Cout;
   if (d2_in) d.Cout = cout1;  // the epilogue of the first half sees its own column count again
   if (conv1d_umma_pair_launch(d, d2, d2_in != nullptr, cout1, total_cout, s, num_sms)) return;
+  PT_CHECK(!d.res_hi && !(d2_in && d2.res_hi),
+           "conv1d: a residual from operand planes (res_hi) is only supported by the CTA-pair kernel, which this shape "
+           "does not qualify for");
   const int n_mt = ceil_div(d.M, UM_BM), n_nt = ceil_div(total_cout, UM_BN);
   const int nslab = d.Cin / UM_BK;
   // weight planes [K*Cout][Cin]

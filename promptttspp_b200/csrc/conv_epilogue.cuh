@@ -106,8 +106,9 @@ struct EpiOps16 {
   float4 p[4];
 };
 
+// 1 conditioner addend, 2 fp32 residual, 3 previous output (beta), 4 residual from split-fp16 planes
 __device__ __forceinline__ int conv_epilogue_prefetch_kind(const pttspp_conv1d_desc& d) {
-  return d.addend ? 1 : (d.res ? 2 : ((d.out && d.beta != 0.f) ? 3 : 0));
+  return d.addend ? 1 : (d.res ? 2 : (d.res_hi ? 4 : ((d.out && d.beta != 0.f) ? 3 : 0)));
 }
 
 __device__ __forceinline__ void conv_epilogue16_load(const pttspp_conv1d_desc& d, int b, int row, int col, EpiOps16& o) {

@@ -56,8 +56,8 @@ def main():
 
     # experiment bits: 2 one MMA per product, 4 no operand loads, 8 no stores, 32 no TMEM reads, 64 no epilogue
     VARIANTS = (("str", {"PTTSPP_UMMA_PAIR": "0", "PTTSPP_UMMA_EPI": "co"}), ("tma", {"PTTSPP_UMMA_PAIR": "0"}),
-                ("pair", pv()), ("p-noPF", pv(16)), ("p-1mma", pv(2)), ("p-noLS", pv(12)),
-                ("p-noEpi", pv(64)))
+                ("pair", pv()), ("p-noLD", pv(4)), ("p-noST", pv(8)), ("p-noLS", pv(12)), ("p-noEpi", pv(64)),
+                ("p-1mma", pv(2)))
     KEYS = ("PTTSPP_UMMA_PAIR", "PTTSPP_UMMA_EPI", "PTTSPP_UMMA_AS", "PTTSPP_UMMA_ORDER", "PTTSPP_UMMA_EW", "PTTSPP_UMMA_RL", "PTTSPP_UMMA_NACC")
     if os.environ.get("BENCH_QUICK"):
         VARIANTS = VARIANTS[1:]
