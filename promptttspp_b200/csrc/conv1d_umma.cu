@@ -1122,7 +1122,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((EW + 2) * 32, 1)
 conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                         const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                         const pttspp_conv1d_desc d, const pttspp_conv1d_desc d2, const int cout1, const int cout_total,
-                        const int n_mt2, const int n_nt, const int n_tiles, const int rowsA, const int mma_order,
+                        const int n_mt, const int n_nt, const int n_tiles, const int rowsA, const int mma_order,
                         const int epi_rl) {
   constexpr uint32_t TMEM_COLS = 512;
   constexpr int NBUF = 512 / (NACC * UP_BN);  // accumulator tile buffers
@@ -1194,8 +1194,11 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
         const int unit = t / n_nt, nt = t - unit * n_nt;
         const bool new_unit = unit != cur_unit;
         cur_unit = unit;
-        const int b = unit / n_mt2, mt2 = unit - b * n_mt2;
-        const int row0 = d.m_begin + mt2 * (2 * UM_BM) + (int)rank * UM_BM - d.pad;
+        // a unit is TWO independent 128-row blocks (one per CTA) of the flat (utterance, block) list: the pair's CTAs
+        // may work on different utterances, so only the very last unit can be half empty
+        const int q = 2 * unit + (int)rank;
+        const int b = min(q / n_mt, d.B - 1), mt = (q / n_mt < d.B) ? q - (q / n_mt) * n_mt : n_mt;  // past the end: no rows
+        const int row0 = d.m_begin + mt * UM_BM - d.pad;
         if (mma_order & 128) {  // experiment (measured harmful: the bulk prefetches queue in front of the TMA loads)
           // The producer runs one to two tiles ahead of the epilogue: pull the epilogue's operand tile (conditioner /
           // residual / previous output, 128 rows x 512 B) into L2 now, so that the epilogue's loads are L2 hits.
@@ -1212,7 +1215,7 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
             const uint32_t bytes = (kind == 1 || !gate) ? UP_BN * 4 : UP_BN * 2;
 #pragma unroll
             for (int rr = 0; rr < UM_BM / 32; ++rr) {
-              const int m = d.m_begin + mt2 * (2 * UM_BM) + (int)rank * UM_BM + rr * 32 + lane;
+              const int m = d.m_begin + mt * UM_BM + rr * 32 + lane;
               const int row = m * de.out_mul + de.out_off;
               if (m < de.m_begin + de.M && row >= 0 && row < de.T_out)
                 l2_prefetch_bulk(src + (int64_t)b * bs + (int64_t)row * ld + c0, bytes);
@@ -1327,14 +1330,16 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
     float* stage = reinterpret_cast<float*>(gen_base + stg_off + warp * 2048);
     for (int t = t_begin; t < t_end; ++t, ++i) {
       const int unit = t / n_nt, nt = t - unit * n_nt;
-      const int b = unit / n_mt2, mt2 = unit - b * n_mt2;
-      const int mt = 2 * mt2 + (int)rank, ub = i % NBUF;
+      const int q = 2 * unit + (int)rank;
+      const int b = min(q / n_mt, d.B - 1), mt = (q / n_mt < d.B) ? q - (q / n_mt) * n_mt : n_mt;
+      const int ub = i % NBUF;
       const uint32_t tpar = ((uint32_t)i / NBUF) & 1u;
       // CTA-uniform branches: each call reads ITS descriptor(s) with immediate constant operands
       if (epi_rl) {
         if (t + 1 < t_end && !(mma_order & 16)) {
           const int tn = t + 1, unit_n = tn / n_nt, nt_n = tn - unit_n * n_nt;
-          const int b_n = unit_n / n_mt2, mt_n = 2 * (unit_n - b_n * n_mt2) + (int)rank;
+          const int q_n = 2 * unit_n + (int)rank;
+          const int b_n = min(q_n / n_mt, d.B - 1), mt_n = (q_n / n_mt < d.B) ? q_n - (q_n / n_mt) * n_mt : n_mt;
           if (nt_n * UP_BN >= cout1) epi_rl_prefetch_tile<UP_BN, EW>(d2, nt_n * UP_BN - cout1, mt_n, b_n, warp, lane);
           else epi_rl_prefetch_tile<UP_BN, EW>(d, nt_n * UP_BN, mt_n, b_n, warp, lane);
         }
@@ -1757,8 +1762,9 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
   const size_t cap = 227 * 1024;
   if (fixed + 3 * UP_BST_BYTES > cap) return false;
   const int nbst = (int)std::min<size_t>(6, (cap - fixed) / UP_BST_BYTES);
-  const int n_mt2 = ceil_div(d.M, 2 * UM_BM), n_nt = total_cout / UP_BN;
-  const long long n_tiles = (long long)n_mt2 * d.B * n_nt;
+  const int n_mt = ceil_div(d.M, UM_BM), n_nt = total_cout / UP_BN;  // 128-row blocks per utterance
+  const long long n_units = ceil_div64((long long)n_mt * d.B, 2);      // pairs of blocks
+  const long long n_tiles = n_units * n_nt;
   if (n_tiles >= (1ll << 30)) return false;
   // worth it only when every pair gets at least a couple of tiles (the activation block is loaded per unit)
   // and when the activation block is reused by at least two N tiles (otherwise the streaming kernel is faster)
@@ -1779,7 +1785,7 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
   const bool debug = getenv("PTTSPP_UMMA_DEBUG") != nullptr;
   auto launch = [&](auto kern, int max_clusters) {
     const int n_clusters = (int)std::min<long long>(n_tiles, std::min(max_clusters, num_sms / 2));
-    int cout_first = dual ? cout1 : total_cout, cout_all = total_cout, a_n_mt2 = n_mt2, a_n_nt = n_nt, a_tiles = (int)n_tiles,
+    int cout_first = dual ? cout1 : total_cout, cout_all = total_cout, a_n_mt2 = n_mt, a_n_nt = n_nt, a_tiles = (int)n_tiles,
         a_rowsA = rowsA;
     const char* oe = getenv("PTTSPP_UMMA_ORDER");  // experiments: bits 0-1 MMA order, 4 no operand loads, 8 no stores, 16 no L2 prefetch
     int a_order = oe ? atoi(oe) : 0, a_rl = epi_rl ? 1 : 0;
@@ -1787,7 +1793,7 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
                     &a_n_mt2, &a_n_nt, &a_tiles, &a_rowsA, &a_order, &a_rl};
     if (debug)
       fprintf(stderr, "[pttspp] pair launch: clusters %d tiles %lld (units %d x nt %d) rowsA %d nbst %d smem %zu rl %d\n",
-              n_clusters, n_tiles, n_mt2 * d.B, n_nt, rowsA, nbst, smem, (int)epi_rl);
+              n_clusters, n_tiles, (int)n_units, n_nt, rowsA, nbst, smem, (int)epi_rl);
     cudaGetLastError();  // a stale error of an earlier call must not be attributed to this launch
     PT_CUDA(cudaLaunchKernel((const void*)kern, dim3(2 * n_clusters), dim3((ew + 2) * 32), args, smem, s));
     ++g_launch_count;

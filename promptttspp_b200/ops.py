@@ -160,7 +160,8 @@ def pack_conv_weight_split(weight, g=None, interleave_halves=False, device=None)
 
 def conv1d_umma_cl(x_planes, w_split, Cout, bias=None, K=1, dil=1, pad=0, act=ACT_NONE, out_len=None, addend=None,
                    res=None, res_scale=1.0, alpha=1.0, beta=0.0, out=None, acc_scale=1.0, out_div=0.0,
-                   emit_planes=False, plane_add=None, write_f32=True, _desc_only=False):
+                   emit_planes=False, plane_add=None, write_f32=True, _desc_only=False, res_planes=None,
+                   res_plane_sub=None, out_planes=None):
     """tcgen05 path on pre-split operands.  x_planes = (hi, lo) [B, T, Cin] fp16; w_split from
     pack_conv_weight_split.  Returns out (fp32) and/or (out_hi, out_lo)."""
     xh, xl = x_planes
@@ -185,12 +186,19 @@ def conv1d_umma_cl(x_planes, w_split, Cout, bias=None, K=1, dil=1, pad=0, act=AC
     d.act = act; d.acc_scale = acc_scale
     if res is not None:
         d.res = res.data_ptr(); d.res_bs = res.stride(0); d.res_ld = res.stride(1)
+    if res_planes is not None:  # residual = hi + lo - sub, read from operand planes (CTA-pair kernel only)
+        d.res_hi = res_planes[0].data_ptr(); d.res_lo = res_planes[1].data_ptr()
+        d.res_plane_bs = res_planes[0].stride(0); d.res_plane_ld = res_planes[0].stride(1)
+        d.res_plane_sub = None if res_plane_sub is None else res_plane_sub.data_ptr()
     d.res_scale = res_scale; d.alpha = alpha; d.beta = beta; d.out_div = out_div
     d.B = B; d.impl = 2
     planes = None
     if emit_planes:
-        oh = torch.empty(B, T, out_cols, dtype=torch.float16, device=xh.device)
-        ol = torch.empty(B, T, out_cols, dtype=torch.float16, device=xh.device)
+        if out_planes is not None:  # caller-provided (e.g. in place over the residual planes)
+            oh, ol = out_planes
+        else:
+            oh = torch.empty(B, T, out_cols, dtype=torch.float16, device=xh.device)
+            ol = torch.empty(B, T, out_cols, dtype=torch.float16, device=xh.device)
         d.out_hi = oh.data_ptr(); d.out_lo = ol.data_ptr(); d.out_plane_bs = oh.stride(0); d.out_plane_ld = oh.stride(1)
         d.out_plane_add = None if plane_add is None else plane_add.data_ptr()
         planes = (oh, ol)

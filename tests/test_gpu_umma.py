@@ -209,3 +209,34 @@ def test_conv1d_umma_gate_large(ops, monkeypatch, variant, dil, T):
     assert float((_bct(out) - z_ref).abs().max()) < 2e-5
     z = zp[0].float() + zp[1].float()
     assert float((_bct(z) - (z_ref + padd[None, :, None])).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("B,T", [(2, 333), (4, 2600)])
+def test_conv1d_umma_dual_residual_from_planes(ops, monkeypatch, B, T):
+    """DiffNet output projection with the residual stream kept ONLY as operand planes: h = hi + lo - step_emb[l] is
+    recovered in the epilogue, (h + W_r z)/sqrt(2) + step_emb[l+1] is written back over the same planes (no fp32 h),
+    the skip half accumulates as before.  Always takes the CTA-pair kernel."""
+    _select(monkeypatch, "stream_tma")  # even with the pair kernel disabled by env this launch must take it
+    g = torch.Generator().manual_seed(21)
+    C = 256
+    z = torch.rand(B, C, T, generator=g) * 2 - 1
+    h = torch.randn(B, C, T, generator=g)
+    emb, nxt = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    skip_old = torch.randn(B, C, T, generator=g)
+    w2 = torch.randn(2 * C, C, 1, generator=g) / math.sqrt(C)
+    b2 = torch.randn(2 * C, generator=g)
+    o = F.conv1d(z, w2, b2)
+    h_ref = (h + o[:, :C]) / math.sqrt(2.0)
+    skip_ref = skip_old + o[:, C:]
+    zp = ops.split_f16(_cl(z))
+    yp = ops.split_f16(_cl(h), emb.cuda())  # y = h + step_emb[l]
+    sbuf = _cl(skip_old)
+    (o1, p1), _ = ops.conv1d_umma_dual_cl(
+        zp, ops.pack_conv_weight_split(w2, device="cuda"), C,
+        dict(bias=b2[:C].cuda(), res_planes=yp, res_plane_sub=emb.cuda(), out_div=math.sqrt(2.0), write_f32=False,
+             emit_planes=True, out_planes=yp, plane_add=nxt.cuda()),
+        dict(bias=b2[C:].cuda(), out=sbuf, beta=1.0))
+    assert o1 is None and p1[0].data_ptr() == yp[0].data_ptr()
+    y_next = yp[0].float() + yp[1].float()
+    assert float((_bct(y_next) - (h_ref + nxt[None, :, None])).abs().max()) < 3e-5
+    assert float((_bct(sbuf) - skip_ref).abs().max()) < 2e-5
