@@ -208,6 +208,21 @@ int pttspp_length_regulate(const float* x, const int64_t* dur, int B, int Tx, in
 int pttspp_iir_filtfilt(const float* x, float* y, float* scratch, int rows, int T, const float* b_coeffs,
                         const float* a_coeffs, int ntaps, pttspp_stream_t stream);
 
+/* Reference-mel style path (promptttspp/modules/reference_encoder.py:95-124, style_encoder.py:82-171).
+ * conv2d_bn_relu: one [Conv2d KxK stride pad (no bias) -> BatchNorm2d(eval, folded to scale/shift) -> ReLU] block on
+ *   NCHW tensors x [B][Cin][H][W] -> out [B][Cout][Ho][Wo] (reference_encoder.py:66-81).
+ * gru_last_state: torch.nn.GRU(I, Hn, 1, batch_first) over x [B][T][I]; out [B][Hn] = hidden state after the last valid
+ *   step t < lens[b] (pack_padded_sequence + `_, ref_embs = self.gru(hs)`, :112-121); lens NULL = T; gates (r, z, n).
+ * style_token_attention: q = Linear(ref [B][R]); k, v = Linear(tanh(gst_embs [Tk][Dk])); `heads` heads over Fdim
+ *   features, scores / sqrt(Fdim), softmax over tokens, linear_out -> out [B][Fdim] (style_encoder.py:123-171). */
+int pttspp_conv2d_bn_relu(const float* x, const float* w, const float* bn_scale, const float* bn_shift, float* out, int B,
+                          int Cin, int H, int W, int Cout, int K, int stride, int pad, pttspp_stream_t stream);
+int pttspp_gru_last_state(const float* x, const int64_t* lens, int B, int T, int I, int Hn, const float* w_ih,
+                          const float* w_hh, const float* b_ih, const float* b_hh, float* out, pttspp_stream_t stream);
+int pttspp_style_token_attention(const float* ref, int B, int R, const float* gst_embs, int Tk, int Dk, int heads, int Fdim,
+                                 const float* wq, const float* bq, const float* wk, const float* bk, const float* wv,
+                                 const float* bv, const float* wo, const float* bo, float* out, pttspp_stream_t stream);
+
 /* Relative-position multi-head self-attention (Transformer-XL style), both ESPnet variants.
  *   scores = ((q+u) k^T + rel_shift((q+v) p^T)) / sqrt(d_k); masked softmax; . v
  * q,k,v,out: [B][T][H*d_k]; p: [Tp][H*d_k] with Tp = T (legacy) or 2T-1 (new);
@@ -308,6 +323,13 @@ int pttspp_acoustic_encode(pttspp_acoustic_t* h, const int64_t* phoneme, const i
                            float noise_scale, int use_max, float* enc_state, int64_t* dur,
                            int64_t* frame_len, float* log_dur, float* style_emb, void* workspace,
                            size_t workspace_bytes, pttspp_stream_t stream);
+
+/* The same text side with the style vector given instead of derived from a prompt: style_in [B][C] is the output of
+ * the reference-mel style encoder (model.py:232-235 / :297-301); it is L2-normalised here when norm_style_emb is set. */
+int pttspp_acoustic_encode_ref(pttspp_acoustic_t* h, const int64_t* phoneme, const int64_t* phone_len, int B, int Tx,
+                               const float* pos_emb, int Tp, const float* style_in, float* enc_state, int64_t* dur,
+                               int64_t* frame_len, float* log_dur, void* workspace, size_t workspace_bytes,
+                               pttspp_stream_t stream);
 
 size_t pttspp_acoustic_decode_workspace_bytes(const pttspp_acoustic_t* h, int B, int Tx, int Ty);
 /* Frame side (variance_adaptor.py:185-206, model.py:311-325, diffusion.py:320-356): length regulator ->

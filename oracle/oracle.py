@@ -513,8 +513,55 @@ def style_embedding(sd, cfg, cls_emb, z_style, noise_scale):
     return style.transpose(-1, -2)
 
 
+def style_encoder(sd, speech, in_lens=None, prefix="reference_encoder.", conv_layers=6, stride=2, heads=4):
+    """StyleEncoder.forward (modules/style_encoder.py:70-80): ReferenceEncoder (reference_encoder.py:95-124: 6 x
+    [Conv2d k3 s2 no bias, BatchNorm2d eval, ReLU], GRU whose last VALID state is the embedding -- the packed-sequence
+    branch :112-121) and StyleTokenLayer + MultiHeadedAttention (style_encoder.py:106-171).
+    speech [B, 80, Lmax], in_lens [B] -> [B, 256, 1]."""
+    p = prefix + "ref_enc."
+    x = speech.transpose(1, 2).unsqueeze(1)
+    for i in range(conv_layers):
+        cp, bp = f"{p}convs.{3 * i}.", f"{p}convs.{3 * i + 1}."
+        x = F.conv2d(x, sd[cp + "weight"], None, stride=stride, padding=1)
+        x = F.batch_norm(x, sd[bp + "running_mean"], sd[bp + "running_var"], sd[bp + "weight"], sd[bp + "bias"],
+                         training=False, eps=1e-5)
+        x = torch.relu(x)
+    hs = x.transpose(1, 2)
+    B, T = hs.shape[0], hs.shape[1]
+    hs = hs.contiguous().view(B, T, -1)
+    lens = torch.full((B,), T, dtype=torch.long)
+    if in_lens is not None:
+        lens = torch.clamp(torch.ceil(in_lens.float() / (stride ** conv_layers)).long(), 1)
+    w_ih, w_hh = sd[p + "gru.weight_ih_l0"], sd[p + "gru.weight_hh_l0"]
+    b_ih, b_hh = sd[p + "gru.bias_ih_l0"], sd[p + "gru.bias_hh_l0"]
+    Hn = w_hh.shape[1]
+    ref = torch.zeros(B, Hn)
+    for b in range(B):  # torch.nn.GRU cell equations, gate order (r, z, n)
+        h = torch.zeros(Hn)
+        for t in range(int(lens[b])):
+            gi = F.linear(hs[b, t], w_ih, b_ih)
+            gh = F.linear(h, w_hh, b_hh)
+            r = torch.sigmoid(gi[:Hn] + gh[:Hn])
+            zg = torch.sigmoid(gi[Hn:2 * Hn] + gh[Hn:2 * Hn])
+            n = torch.tanh(gi[2 * Hn:] + r * gh[2 * Hn:])
+            h = (1 - zg) * n + zg * h
+        ref[b] = h
+    q = prefix + "stl."
+    gst = torch.tanh(sd[q + "gst_embs"]).unsqueeze(0).expand(B, -1, -1)
+    m = q + "mha."
+    Fd = sd[m + "linear_q.weight"].shape[0]
+    dk = Fd // heads
+    qv = F.linear(ref.unsqueeze(1), sd[m + "linear_q.weight"], sd[m + "linear_q.bias"]).view(B, -1, heads, dk).transpose(1, 2)
+    kv = F.linear(gst, sd[m + "linear_k.weight"], sd[m + "linear_k.bias"]).view(B, -1, heads, dk).transpose(1, 2)
+    vv = F.linear(gst, sd[m + "linear_v.weight"], sd[m + "linear_v.bias"]).view(B, -1, heads, dk).transpose(1, 2)
+    score = F.softmax((qv @ kv.transpose(-1, -2)) / math.sqrt(dk * heads), dim=-1)
+    o = (score @ vv).transpose(-1, -2).contiguous().view(B, 1, -1)
+    o = F.linear(o, sd[m + "linear_out.weight"], sd[m + "linear_out.bias"])
+    return o.squeeze(1).unsqueeze(-1)
+
+
 def acoustic_infer_batch(sd, cfg, phoneme, phone_lengths, cls_emb, z_style, x_T=None, z=None, noise_scale=1.0,
-                         noise_fn=None, steps=None, return_intermediates=False):
+                         noise_fn=None, steps=None, return_intermediates=False, reference_mel=None, ref_lengths=None):
     """PromptTTSMDNDurCFG.infer_batch (model.py:261-325) with use_max=True and injected noise.
 
     x_T / z may be None, then `noise_fn(shape)` is called in the reference's order once Ty is known.
@@ -525,7 +572,12 @@ def acoustic_infer_batch(sd, cfg, phoneme, phone_lengths, cls_emb, z_style, x_T=
         x = x * math.sqrt(x.shape[-1])
     x = x.transpose(-1, -2) * phone_mask
     x = conformer_encoder(sd, cfg, x.transpose(1, 2), phone_lengths).transpose(1, 2)
-    style = style_embedding(sd, cfg, cls_emb, z_style, noise_scale)
+    if reference_mel is not None:  # model.py:296-301
+        style = style_encoder(sd, reference_mel, ref_lengths)
+        if cfg["norm_style_emb"]:
+            style = F.normalize(style, dim=1)
+    else:
+        style = style_embedding(sd, cfg, cls_emb, z_style, noise_scale)
     x = x + style
     enc_state = x
     pm = phone_mask.to(x.dtype)

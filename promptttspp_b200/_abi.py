@@ -108,6 +108,10 @@ SIGNATURES = {
     "pttspp_relpos_attention": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pttspp_iir_filtfilt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                       C.c_void_p]),
+    "pttspp_conv2d_bn_relu": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 8 + [C.c_void_p]),
+    "pttspp_gru_last_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6),
+    "pttspp_style_token_attention": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+                                     + [C.c_void_p] * 10),
     "pttspp_bigvgan_create": (C.c_int, [C.POINTER(BigVGANConfig), C.POINTER(C.c_void_p)]),
     "pttspp_bigvgan_destroy": (None, [C.c_void_p]),
     "pttspp_bigvgan_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, c_i64p, C.c_int, C.c_void_p]),
@@ -129,6 +133,9 @@ SIGNATURES = {
     "pttspp_acoustic_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "pttspp_acoustic_encode_ref": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_size_t, C.c_void_p]),
     "pttspp_acoustic_decode_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "pttspp_acoustic_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -441,13 +441,15 @@ extern "C" size_t pttspp_acoustic_encode_workspace_bytes(const pttspp_acoustic_t
   return cv.off + 512;
 }
 
-extern "C" int pttspp_acoustic_encode(pttspp_acoustic_t* h, const int64_t* phoneme, const int64_t* phone_len, int B,
-                                      int Tx, const float* pos_emb, int Tp, const float* cls_emb, const float* z_style,
-                                      float noise_scale, int use_max, float* enc_state, int64_t* dur,
-                                      int64_t* frame_len, float* log_dur, float* style_emb, void* workspace,
-                                      size_t workspace_bytes, pttspp_stream_t stream) {
-  PT_API_BEGIN
-  PT_CHECK(h && phoneme && phone_len && pos_emb && cls_emb && z_style && enc_state && dur && frame_len, "null argument");
+// style_in != nullptr: the style vector comes from the reference-mel style encoder (cls_emb / z_style unused)
+static void acoustic_encode_impl(pttspp_acoustic_t* h, const int64_t* phoneme, const int64_t* phone_len, int B, int Tx,
+                                 const float* pos_emb, int Tp, const float* cls_emb, const float* z_style,
+                                 const float* style_in, float noise_scale, int use_max, float* enc_state, int64_t* dur,
+                                 int64_t* frame_len, float* log_dur, float* style_emb, void* workspace,
+                                 size_t workspace_bytes, pttspp_stream_t stream) {
+  {
+  PT_CHECK(h && phoneme && phone_len && pos_emb && enc_state && dur && frame_len, "null argument");
+  PT_CHECK(style_in || (cls_emb && z_style), "null style input");
   PT_CHECK(h->finalized, "acoustic: finalize() has not been called after the last set_tensor()");
   PT_CHECK(B >= 1 && Tx >= 1, "acoustic: empty batch (B=%d, Tx=%d)", B, Tx);
   PT_CHECK(use_max, "acoustic: use_max=False (categorical component sampling) is not implemented");
@@ -514,8 +516,14 @@ extern "C" int pttspp_acoustic_encode(pttspp_acoustic_t* h, const int64_t* phone
   }
   run_ln(h->after_norm, w.x, nullptr, enc_state, B, Tx, C, 1e-12f, nullptr, len, 1.f, nullptr, s);
 
-  // prompt adaptor MLP on the sentence embedding, style MDN, sampled + normalised style vector
-  {
+  if (style_in) {
+    // reference-mel style path (model.py:232-237): normalise, broadcast-add
+    float* style = style_emb ? style_emb : w.style;
+    PT_CUDA(cudaMemcpyAsync(style, style_in, (size_t)B * C * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (c.norm_style_emb) l2_normalize_rows(style, B, C, s);
+    add_row_broadcast(enc_state, style, B, Tx, C, s);
+  } else {
+    // prompt adaptor MLP on the sentence embedding, style MDN, sampled + normalised style vector
     auto d0 = conv_desc(h->ad0, cls_emb, 1, B, w.e1);
     d0.act = PTTSPP_ACT_RELU;
     conv1d_cl(d0, s);
@@ -554,8 +562,32 @@ extern "C" int pttspp_acoustic_encode(pttspp_acoustic_t* h, const int64_t* phone
                       c.dur_gaussians, logd, s);
     duration_quantize(logd, len, B, Tx, dur, frame_len, s);
   }
+  }
+}
+
+extern "C" int pttspp_acoustic_encode(pttspp_acoustic_t* h, const int64_t* phoneme, const int64_t* phone_len, int B,
+                                      int Tx, const float* pos_emb, int Tp, const float* cls_emb, const float* z_style,
+                                      float noise_scale, int use_max, float* enc_state, int64_t* dur,
+                                      int64_t* frame_len, float* log_dur, float* style_emb, void* workspace,
+                                      size_t workspace_bytes, pttspp_stream_t stream) {
+  PT_API_BEGIN
+  PT_CHECK(cls_emb && z_style, "null argument");
+  acoustic_encode_impl(h, phoneme, phone_len, B, Tx, pos_emb, Tp, cls_emb, z_style, nullptr, noise_scale, use_max,
+                       enc_state, dur, frame_len, log_dur, style_emb, workspace, workspace_bytes, stream);
   PT_API_END
 }
+
+extern "C" int pttspp_acoustic_encode_ref(pttspp_acoustic_t* h, const int64_t* phoneme, const int64_t* phone_len, int B,
+                                          int Tx, const float* pos_emb, int Tp, const float* style_in, float* enc_state,
+                                          int64_t* dur, int64_t* frame_len, float* log_dur, void* workspace,
+                                          size_t workspace_bytes, pttspp_stream_t stream) {
+  PT_API_BEGIN
+  PT_CHECK(style_in, "null argument");
+  acoustic_encode_impl(h, phoneme, phone_len, B, Tx, pos_emb, Tp, nullptr, nullptr, style_in, 1.f, 1, enc_state, dur,
+                       frame_len, log_dur, nullptr, workspace, workspace_bytes, stream);
+  PT_API_END
+}
+
 
 extern "C" size_t pttspp_acoustic_decode_workspace_bytes(const pttspp_acoustic_t* h, int B, int Tx, int Ty) {
   (void)Tx;

@@ -154,11 +154,10 @@ class PromptTTSMDNDurCFG(nn.Module):
 
     # ---- inference ---------------------------------------------------------------------------
     @torch.no_grad()
-    def _synthesize(self, phoneme, phone_lengths, style_prompt, reference_mel, use_max, noise_scale, noise):
+    def _synthesize(self, phoneme, phone_lengths, style_prompt, reference_mel, use_max, noise_scale, noise,
+                    ref_lengths=None):
         assert (style_prompt is not None) ^ (reference_mel is not None), "One of style inputs must not be None."
-        if reference_mel is not None:
-            raise NotImplementedError("reference_mel style path (SURVEY.md 8f3) is not accelerated yet")
-        if not use_max:
+        if not use_max and reference_mel is None:
             raise NotImplementedError("use_max=False (categorical MDN component sampling) is not implemented")
         _abi.require_cuda(phoneme, "PromptTTSMDNDurCFG.infer")
         device = phoneme.device
@@ -172,12 +171,21 @@ class PromptTTSMDNDurCFG(nn.Module):
             nat = self._handle(device)
             lib = _abi.lib()
             stream = _abi.stream_ptr(device)
-            cls = self.prompt_encoder.sentence_embedding(style_prompt, device).float().contiguous()
-            if cls.shape[0] != B:
-                raise ValueError(f"{cls.shape[0]} style prompts for a batch of {B}")
-            # RNG draw #1 (model.py:191)
-            z_style = noise.z_style if noise is not None else torch.randn(B, 1, Cc, device=device)
-            z_style = z_style.to(device=device, dtype=torch.float32).reshape(B, Cc).contiguous()
+            style_in = None
+            if reference_mel is not None:
+                # reference-mel style path (model.py:232-235 / :297-301): StyleEncoder on the normalised mel
+                if ref_lengths is None:
+                    ref_lengths = torch.full((B,), reference_mel.shape[-1], dtype=torch.int64, device=device)
+                style_in = self.reference_encoder(reference_mel.to(device), ref_lengths)[:, :, 0].float().contiguous()
+                if style_in.shape[0] != B:
+                    raise ValueError(f"{style_in.shape[0]} reference mels for a batch of {B}")
+            else:
+                cls = self.prompt_encoder.sentence_embedding(style_prompt, device).float().contiguous()
+                if cls.shape[0] != B:
+                    raise ValueError(f"{cls.shape[0]} style prompts for a batch of {B}")
+                # RNG draw #1 (model.py:191)
+                z_style = noise.z_style if noise is not None else torch.randn(B, 1, Cc, device=device)
+                z_style = z_style.to(device=device, dtype=torch.float32).reshape(B, Cc).contiguous()
             legacy = self.encoder.rel_pos_type == "legacy"
             pos = self._pos_table("legacy" if legacy else "new", Tx, device)
             enc_state = torch.empty(B, Tx, Cc, device=device)
@@ -185,11 +193,17 @@ class PromptTTSMDNDurCFG(nn.Module):
             frame_len = torch.empty(B, dtype=torch.int64, device=device)
             log_dur = torch.empty(B, Tx, device=device)
             ws = nat.workspace(lib.pttspp_acoustic_encode_workspace_bytes(nat.h, B, Tx), device)
-            _abi.check(lib.pttspp_acoustic_encode(
-                nat.h, _abi.ptr(phoneme), _abi.ptr(phone_lengths), B, Tx, _abi.ptr(pos), pos.shape[0],
-                _abi.ptr(cls), _abi.ptr(z_style), float(noise_scale), int(use_max), _abi.ptr(enc_state),
-                _abi.ptr(dur), _abi.ptr(frame_len), _abi.ptr(log_dur), None, _abi.ptr(ws),
-                C.c_size_t(ws.numel()), stream))
+            if style_in is not None:
+                _abi.check(lib.pttspp_acoustic_encode_ref(
+                    nat.h, _abi.ptr(phoneme), _abi.ptr(phone_lengths), B, Tx, _abi.ptr(pos), pos.shape[0],
+                    _abi.ptr(style_in), _abi.ptr(enc_state), _abi.ptr(dur), _abi.ptr(frame_len), _abi.ptr(log_dur),
+                    _abi.ptr(ws), C.c_size_t(ws.numel()), stream))
+            else:
+                _abi.check(lib.pttspp_acoustic_encode(
+                    nat.h, _abi.ptr(phoneme), _abi.ptr(phone_lengths), B, Tx, _abi.ptr(pos), pos.shape[0],
+                    _abi.ptr(cls), _abi.ptr(z_style), float(noise_scale), int(use_max), _abi.ptr(enc_state),
+                    _abi.ptr(dur), _abi.ptr(frame_len), _abi.ptr(log_dur), None, _abi.ptr(ws),
+                    C.c_size_t(ws.numel()), stream))
             Ty = int(frame_len.max().item())  # the one device->host sync: sizes the outputs
             pe_abs = self._pos_table("abs", max(Ty, 1), device)
             # RNG draws #2 .. #K+2, same shapes and order as diffusion.py:332 and :218
@@ -230,8 +244,10 @@ class PromptTTSMDNDurCFG(nn.Module):
     def infer_batch(self, phoneme, phone_lengths, style_prompt=None, reference_mel=None, ref_lengths=None,
                     use_max=True, noise_scale=1.0, return_f0=False, *, noise: Optional[InferNoise] = None):
         """Batched inference (model.py:261-325): returns (mel, [log_cf0, vuv,] frame_lengths)."""
+        if reference_mel is not None:
+            assert ref_lengths is not None  # model.py:296
         mel, log_cf0, vuv, frame_lengths = self._synthesize(
-            phoneme, phone_lengths, style_prompt, reference_mel, use_max, noise_scale, noise)
+            phoneme, phone_lengths, style_prompt, reference_mel, use_max, noise_scale, noise, ref_lengths)
         if return_f0:
             return mel, log_cf0, vuv, frame_lengths
         return mel, frame_lengths

@@ -1,14 +1,17 @@
-"""Reference-mel style encoder -- parameter holder only ("next").
+"""Reference-mel style encoder.
 
-Reference: promptttspp/modules/style_encoder.py:23-171 and
-promptttspp/modules/reference_encoder.py:21-124.  The keys are declared so a
-reference checkpoint loads with ``strict=True``; the ``reference_mel=`` style
-path itself is not on the accelerated hot path yet and raises when used.
+Reference: promptttspp/modules/style_encoder.py:23-171 and promptttspp/modules/reference_encoder.py:21-124.
+The sub-modules hold the parameters under the reference's state_dict keys; `StyleEncoder.forward` runs the
+arithmetic through three C-ABI ops (csrc/style_encoder.cu): pttspp_conv2d_bn_relu x 6, pttspp_gru_last_state,
+pttspp_style_token_attention.  CUDA tensors only.
 """
+import math
 from typing import Sequence
 
 import torch
 from torch import nn
+
+from .. import _abi
 
 
 class _TokenAttention(nn.Module):
@@ -53,8 +56,54 @@ class StyleEncoder(nn.Module):
                                         conv_stride, gru_layers, gru_units)
         self.stl = StyleTokenLayer(gru_units, gst_tokens, gst_token_dim, gst_heads)
 
+    @torch.no_grad()
     def forward(self, speech, in_lens=None):
-        raise NotImplementedError(
-            "the reference_mel style path (SURVEY.md 8f3) is not accelerated yet; "
-            "use style_prompt=..."
-        )
+        """speech: [B, idim, Lmax] normalised mel (CUDA), in_lens: [B] frame counts or None -> [B, token_dim, 1]."""
+        _abi.require_cuda(speech, "StyleEncoder.forward")
+        lib = _abi.lib()
+        dev = speech.device
+        enc, stl = self.ref_enc, self.stl
+        x = speech.float().transpose(1, 2).unsqueeze(1).contiguous()  # (B, 1, Lmax, idim), reference_encoder.py:103
+        B = x.shape[0]
+        with torch.cuda.device(dev):
+            stream = _abi.stream_ptr(dev)
+            mods = list(enc.convs)
+            for i in range(0, len(mods), 3):
+                conv, bn = mods[i], mods[i + 1]
+                k, st, pad = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+                _, cin, H, W = x.shape
+                Ho, Wo = (H + 2 * pad - k) // st + 1, (W + 2 * pad - k) // st + 1
+                # eval-mode BatchNorm2d folded to y * scale + shift
+                scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
+                shift = (bn.bias - bn.running_mean * scale).float().contiguous()
+                w = conv.weight.detach().float().contiguous()
+                out = torch.empty(B, conv.out_channels, Ho, Wo, device=dev)
+                _abi.check(lib.pttspp_conv2d_bn_relu(_abi.ptr(x), _abi.ptr(w), _abi.ptr(scale), _abi.ptr(shift), _abi.ptr(out),
+                                                     B, cin, H, W, conv.out_channels, k, st, pad, stream))
+                x = out
+            hs = x.transpose(1, 2).contiguous().view(B, x.shape[2], -1)  # (B, Lmax', C * idim'), :105-108
+            T, I = hs.shape[1], hs.shape[2]
+            lens = None
+            if in_lens is not None:  # :113-118, without the host round trip of hs_lens.to("cpu")
+                n_sub = len(mods) // 3
+                lens = torch.ceil(in_lens.to(dev).float() / (mods[0].stride[0] ** n_sub)).long().clamp(min=1).contiguous()
+            gru = enc.gru
+            Hn = gru.hidden_size
+            ref = torch.empty(B, Hn, device=dev)
+            _abi.check(lib.pttspp_gru_last_state(
+                _abi.ptr(hs), None if lens is None else _abi.ptr(lens), B, T, I, Hn,
+                _abi.ptr(gru.weight_ih_l0.detach().float().contiguous()), _abi.ptr(gru.weight_hh_l0.detach().float().contiguous()),
+                _abi.ptr(gru.bias_ih_l0.detach().float().contiguous()), _abi.ptr(gru.bias_hh_l0.detach().float().contiguous()),
+                _abi.ptr(ref), stream))
+            mha = stl.mha
+            Fd = mha.linear_q.out_features
+            Tk, Dk = stl.gst_embs.shape
+            heads = Fd // Dk
+            out = torch.empty(B, Fd, device=dev)
+            f = lambda t: _abi.ptr(t.detach().float().contiguous())
+            keep = [t.detach().float().contiguous() for t in (
+                stl.gst_embs, mha.linear_q.weight, mha.linear_q.bias, mha.linear_k.weight, mha.linear_k.bias,
+                mha.linear_v.weight, mha.linear_v.bias, mha.linear_out.weight, mha.linear_out.bias)]
+            _abi.check(lib.pttspp_style_token_attention(_abi.ptr(ref), B, Hn, _abi.ptr(keep[0]), Tk, Dk, heads, Fd,
+                                                        *[_abi.ptr(t) for t in keep[1:]], _abi.ptr(out), stream))
+        return out.unsqueeze(-1)

@@ -223,6 +223,46 @@ def make_lowpass():
     print("lowpass", {k: v.shape for k, v in out.items()})
 
 
+def make_style(ns):
+    """Reference StyleEncoder on a ragged batch, and infer_batch(reference_mel=...) end to end."""
+    from golden_cases import ACOUSTIC_REFMEL_CASE, STYLE_CASE, style_inputs
+
+    case = STYLE_CASE
+    model = build_acoustic(rel_pos_type=case["rel_pos_type"], ns=ns).eval()
+    sd = synthetic_state_dict(build_acoustic(rel_pos_type=case["rel_pos_type"], bert=_FixedBert()), seed=case["weight_seed"])
+    model.load_state_dict(sd, strict=True)
+    mel, lens = style_inputs()
+    with torch.no_grad():
+        style = model.reference_encoder(mel, lens)
+        style_full = model.reference_encoder(mel[:1], None)
+    print("style", tuple(style.shape), float(style.abs().max()))
+    out = {"style": style.numpy(), "style_nolen": style_full.numpy()}
+
+    case = ACOUSTIC_REFMEL_CASE
+    model = build_acoustic(rel_pos_type=case["rel_pos_type"], ns=ns, K_step=case["K_step"]).eval()
+    sd = synthetic_state_dict(build_acoustic(rel_pos_type=case["rel_pos_type"], bert=_FixedBert(), K_step=case["K_step"]),
+                              seed=case["weight_seed"], frames_per_phoneme=case["frames_per_phoneme"])
+    model.load_state_dict(sd, strict=True)
+    phoneme, lengths, _ = acoustic_inputs(case)
+    ref_mel, ref_lens = style_inputs(case)
+    B = phoneme.shape[0]
+    noise = {}
+
+    def x_T_fn(shape):
+        noise["full"] = golden_noise(case, B, shape[-1])
+        return noise["full"].x_T.clone()
+
+    def z_fn(shape, n):
+        return noise["full"].z[n].clone()
+
+    with injected_noise(golden_noise(case, B, None).z_style, x_T_fn, z_fn):
+        mel_out, log_cf0, vuv, frame_lengths = model.infer_batch(phoneme, lengths, reference_mel=ref_mel,
+                                                                 ref_lengths=ref_lens, use_max=True, return_f0=True)
+    print("   refmel acoustic Ty", mel_out.shape[-1], frame_lengths.tolist())
+    out.update(mel=mel_out.numpy(), log_cf0=log_cf0.numpy(), vuv=vuv.numpy(), frame_lengths=frame_lengths.numpy())
+    np.savez_compressed(OUT / "style_refmel.npz", **out)
+
+
 def make_ops():
     """Op-level vectors from the reference layers: pin the closed forms used by the kernels."""
     sys.path.insert(0, str(REF))
@@ -267,7 +307,7 @@ def make_ops():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops", "vocoder", "vocoder_f0", "lowpass", "acoustic"]
+    which = sys.argv[1:] or ["ops", "vocoder", "vocoder_f0", "lowpass", "style", "acoustic"]
     if "ops" in which:
         make_ops()
     if "vocoder" in which:
@@ -276,6 +316,8 @@ if __name__ == "__main__":
         make_vocoder_f0()
     if "lowpass" in which:
         make_lowpass()
+    if "style" in which:
+        make_style(reference_namespace())
     if "acoustic" in which:
         make_acoustic(reference_namespace())
     print("done")

@@ -86,3 +86,20 @@ def lowpass_inputs():
     g = torch.Generator().manual_seed(77)
     return [5.0 + 0.5 * torch.randn(3, 1, 400, generator=g).cumsum(-1) * 0.1, 4.0 + torch.randn(1, 1, 57, generator=g),
             torch.randn(2, 1, 17, generator=g)]
+
+
+# reference-mel style path: ragged batch of normalised reference mels
+STYLE_CASE = dict(weight_seed=1234, input_seed=11, lengths=[200, 133, 64], rel_pos_type="legacy")
+ACOUSTIC_REFMEL_CASE = dict(api="infer_batch", rel_pos_type="legacy", lengths=[9, 6], weight_seed=1234,
+                            frames_per_phoneme=3.0, input_seed=7, noise_seed=107, noise_scale=1.0, K_step=100,
+                            ref_lengths=[150, 97])
+
+
+def style_inputs(case=None):
+    case = case or STYLE_CASE
+    lens = case["lengths"] if "ref_lengths" not in case else case["ref_lengths"]
+    g = torch.Generator().manual_seed(case["input_seed"] + 500)
+    mel = torch.randn(len(lens), 80, max(lens), generator=g)
+    for b, n in enumerate(lens):
+        mel[b, :, n:] = 0
+    return mel, torch.tensor(lens, dtype=torch.int64)

@@ -226,3 +226,39 @@ def test_app_py_flow_acoustic_to_f0_vocoder(vocoder_f0):
     w1, w2 = run(), run()
     assert w1.dim() == 2 and w1.shape[1] % 240 == 0 and torch.isfinite(w1).all()
     assert torch.equal(w1, w2)
+
+
+# ---- reference-mel style path ----
+
+def test_style_encoder_and_reference_mel_inference_match_golden(golden_dir):
+    from golden_cases import ACOUSTIC_REFMEL_CASE, STYLE_CASE, style_inputs
+
+    gold = np.load(golden_dir / "style_refmel.npz")
+    model = build_acoustic(bert=FixedPromptEmbedding(torch.zeros(1, 768)))
+    model.load_state_dict(synthetic_state_dict(model, seed=STYLE_CASE["weight_seed"]), strict=True)
+    model = model.cuda().eval()
+    mel, lens = style_inputs()
+    style = model.reference_encoder(mel.cuda(), lens.cuda()).cpu()
+    err = float((style - torch.from_numpy(gold["style"])).abs().max())
+    print(f"style encoder: max-abs err {err:.2e}")
+    assert style.shape == (3, 256, 1) and err < 1e-5
+    assert float((model.reference_encoder(mel[:1].cuda()).cpu() - torch.from_numpy(gold["style_nolen"])).abs().max()) < 1e-5
+
+    case = ACOUSTIC_REFMEL_CASE
+    model = build_acoustic(bert=FixedPromptEmbedding(torch.zeros(1, 768)), K_step=case["K_step"])
+    model.load_state_dict(synthetic_state_dict(model, seed=case["weight_seed"],
+                                               frames_per_phoneme=case["frames_per_phoneme"]), strict=True)
+    model = model.cuda().eval()
+    phoneme, lengths, _ = acoustic_inputs(case)
+    ref_mel, ref_lens = style_inputs(case)
+    Ty = int(gold["mel"].shape[-1])
+    noise = golden_noise(case, phoneme.shape[0], Ty)
+    mel_out, log_cf0, vuv, flen = model.infer_batch(phoneme.cuda(), lengths.cuda(), reference_mel=ref_mel.cuda(),
+                                                    ref_lengths=ref_lens.cuda(), use_max=True, return_f0=True, noise=noise)
+    assert torch.equal(flen.cpu(), torch.from_numpy(gold["frame_lengths"]))
+    err = float((mel_out.cpu() - torch.from_numpy(gold["mel"])).abs().max())
+    print(f"infer_batch(reference_mel): mel max-abs err {err:.2e}")
+    assert err < MEL_TOL
+    assert torch.allclose(log_cf0.cpu(), torch.from_numpy(gold["log_cf0"]), atol=1e-3)
+    with pytest.raises(AssertionError):
+        model.infer_batch(phoneme.cuda(), lengths.cuda(), reference_mel=ref_mel.cuda())  # ref_lengths required (model.py:296)
