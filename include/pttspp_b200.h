@@ -324,6 +324,14 @@ int pttspp_acoustic_encode(pttspp_acoustic_t* h, const int64_t* phoneme, const i
                            int64_t* frame_len, float* log_dur, float* style_emb, void* workspace,
                            size_t workspace_bytes, pttspp_stream_t stream);
 
+/* use_max = False (model.py:185-196 with mdn.py:226-257): the style MDN component of every dimension is a
+ * Categorical(probs = exp(log_pi)) draw instead of the arg-max.  The draw is an input: comp_u [B][C] uniforms in [0, 1),
+ * component = inverse CDF of the normalised probabilities. */
+int pttspp_acoustic_encode_sampled(pttspp_acoustic_t* h, const int64_t* phoneme, const int64_t* phone_len, int B, int Tx,
+                                   const float* pos_emb, int Tp, const float* cls_emb, const float* z_style,
+                                   const float* comp_u, float noise_scale, float* enc_state, int64_t* dur,
+                                   int64_t* frame_len, float* log_dur, float* style_emb, void* workspace,
+                                   size_t workspace_bytes, pttspp_stream_t stream);
 /* The same text side with the style vector given instead of derived from a prompt: style_in [B][C] is the output of
  * the reference-mel style encoder (model.py:232-235 / :297-301); it is L2-normalised here when norm_style_emb is set. */
 int pttspp_acoustic_encode_ref(pttspp_acoustic_t* h, const int64_t* phoneme, const int64_t* phone_len, int B, int Tx,

@@ -495,7 +495,7 @@ VOCODER_CFG = dict(
 )
 
 
-def style_embedding(sd, cfg, cls_emb, z_style, noise_scale):
+def style_embedding(sd, cfg, cls_emb, z_style, noise_scale, comp_u=None):
     """PromptEncoder adaptor (prompt_encoder.py:45-56) + normalise + style MDN + sample_style_emb
     (model.py:284-296, 185-196).  cls_emb [B, 768]; z_style [B, 1, C] -> [B, C, 1]."""
     p = "prompt_encoder.adaptor."
@@ -506,7 +506,18 @@ def style_embedding(sd, cfg, cls_emb, z_style, noise_scale):
         e = F.normalize(e, dim=1)
     C = e.shape[1]
     log_pi, log_sigma, mu = mdn_forward(sd, "style_mdn.", e.transpose(-1, -2), cfg["style_gaussians"], C)
-    sigma, mu = mdn_most_probable(log_pi, log_sigma, mu)
+    if comp_u is None:
+        sigma, mu = mdn_most_probable(log_pi, log_sigma, mu)
+    else:
+        # mdn_sample_sigma_and_mu (mdn.py:226-257), dim-wise: Categorical(probs=pi).sample() per (b, dimension), with
+        # the draw realised as the inverse CDF of the injected uniforms comp_u [B, C]
+        pi = log_pi.exp().squeeze(1).transpose(1, 2)                      # (B, C, G)
+        cdf = torch.cumsum(pi / pi.sum(-1, keepdim=True), dim=-1)
+        idx = (comp_u.unsqueeze(-1) >= cdf).sum(-1).clamp(max=pi.shape[-1] - 1)  # (B, C)
+        one_hot = F.one_hot(idx, pi.shape[-1]).unsqueeze(1).transpose(2, 3)
+        mu_s = torch.sum(mu * one_hot, dim=2)
+        sigma = torch.exp(torch.sum(log_sigma * one_hot, dim=2))
+        mu = mu_s
     style = mu + sigma * z_style * noise_scale
     if cfg["norm_style_emb"]:
         style = F.normalize(style, dim=-1)
@@ -561,7 +572,8 @@ def style_encoder(sd, speech, in_lens=None, prefix="reference_encoder.", conv_la
 
 
 def acoustic_infer_batch(sd, cfg, phoneme, phone_lengths, cls_emb, z_style, x_T=None, z=None, noise_scale=1.0,
-                         noise_fn=None, steps=None, return_intermediates=False, reference_mel=None, ref_lengths=None):
+                         noise_fn=None, steps=None, return_intermediates=False, reference_mel=None, ref_lengths=None,
+                         comp_u=None):
     """PromptTTSMDNDurCFG.infer_batch (model.py:261-325) with use_max=True and injected noise.
 
     x_T / z may be None, then `noise_fn(shape)` is called in the reference's order once Ty is known.
@@ -577,7 +589,7 @@ def acoustic_infer_batch(sd, cfg, phoneme, phone_lengths, cls_emb, z_style, x_T=
         if cfg["norm_style_emb"]:
             style = F.normalize(style, dim=1)
     else:
-        style = style_embedding(sd, cfg, cls_emb, z_style, noise_scale)
+        style = style_embedding(sd, cfg, cls_emb, z_style, noise_scale, comp_u)
     x = x + style
     enc_state = x
     pm = phone_mask.to(x.dtype)

@@ -444,15 +444,16 @@ extern "C" size_t pttspp_acoustic_encode_workspace_bytes(const pttspp_acoustic_t
 // style_in != nullptr: the style vector comes from the reference-mel style encoder (cls_emb / z_style unused)
 static void acoustic_encode_impl(pttspp_acoustic_t* h, const int64_t* phoneme, const int64_t* phone_len, int B, int Tx,
                                  const float* pos_emb, int Tp, const float* cls_emb, const float* z_style,
-                                 const float* style_in, float noise_scale, int use_max, float* enc_state, int64_t* dur,
+                                 const float* style_in, const float* comp_u, float noise_scale, int use_max,
+                                 float* enc_state, int64_t* dur,
                                  int64_t* frame_len, float* log_dur, float* style_emb, void* workspace,
                                  size_t workspace_bytes, pttspp_stream_t stream) {
   {
   PT_CHECK(h && phoneme && phone_len && pos_emb && enc_state && dur && frame_len, "null argument");
   PT_CHECK(style_in || (cls_emb && z_style), "null style input");
+  PT_CHECK(style_in || use_max || comp_u, "acoustic: use_max=0 needs the component draw (pttspp_acoustic_encode_sampled)");
   PT_CHECK(h->finalized, "acoustic: finalize() has not been called after the last set_tensor()");
   PT_CHECK(B >= 1 && Tx >= 1, "acoustic: empty batch (B=%d, Tx=%d)", B, Tx);
-  PT_CHECK(use_max, "acoustic: use_max=False (categorical component sampling) is not implemented");
   const auto& c = h->cfg;
   PT_CHECK(Tp == (c.rel_pos_legacy ? Tx : 2 * Tx - 1), "acoustic: pos_emb has %d rows, expected %d", Tp,
            c.rel_pos_legacy ? Tx : 2 * Tx - 1);
@@ -540,7 +541,8 @@ static void acoustic_encode_impl(pttspp_acoustic_t* h, const int64_t* phoneme, c
     auto p2 = conv_desc(h->mdn_mu, w.e3, 1, B, w.mu);
     conv1d_cl(p2, s);
     float* style = style_emb ? style_emb : w.style;
-    style_mdn_sample(w.lp, w.ls, w.mu, z_style, B, c.style_gaussians, C, noise_scale, c.norm_style_emb, style, s);
+    style_mdn_sample(w.lp, w.ls, w.mu, z_style, B, c.style_gaussians, C, noise_scale, c.norm_style_emb, style, s,
+                     use_max ? nullptr : comp_u);
     add_row_broadcast(enc_state, style, B, Tx, C, s);  // padded phoneme columns become non-zero (model.py:301)
   }
 
@@ -572,7 +574,20 @@ extern "C" int pttspp_acoustic_encode(pttspp_acoustic_t* h, const int64_t* phone
                                       size_t workspace_bytes, pttspp_stream_t stream) {
   PT_API_BEGIN
   PT_CHECK(cls_emb && z_style, "null argument");
-  acoustic_encode_impl(h, phoneme, phone_len, B, Tx, pos_emb, Tp, cls_emb, z_style, nullptr, noise_scale, use_max,
+  acoustic_encode_impl(h, phoneme, phone_len, B, Tx, pos_emb, Tp, cls_emb, z_style, nullptr, nullptr, noise_scale, use_max,
+                       enc_state, dur, frame_len, log_dur, style_emb, workspace, workspace_bytes, stream);
+  PT_API_END
+}
+
+extern "C" int pttspp_acoustic_encode_sampled(pttspp_acoustic_t* h, const int64_t* phoneme, const int64_t* phone_len, int B,
+                                              int Tx, const float* pos_emb, int Tp, const float* cls_emb,
+                                              const float* z_style, const float* comp_u, float noise_scale,
+                                              float* enc_state, int64_t* dur, int64_t* frame_len, float* log_dur,
+                                              float* style_emb, void* workspace, size_t workspace_bytes,
+                                              pttspp_stream_t stream) {
+  PT_API_BEGIN
+  PT_CHECK(cls_emb && z_style && comp_u, "null argument");
+  acoustic_encode_impl(h, phoneme, phone_len, B, Tx, pos_emb, Tp, cls_emb, z_style, nullptr, comp_u, noise_scale, 0,
                        enc_state, dur, frame_len, log_dur, style_emb, workspace, workspace_bytes, stream);
   PT_API_END
 }
@@ -583,7 +598,7 @@ extern "C" int pttspp_acoustic_encode_ref(pttspp_acoustic_t* h, const int64_t* p
                                           size_t workspace_bytes, pttspp_stream_t stream) {
   PT_API_BEGIN
   PT_CHECK(style_in, "null argument");
-  acoustic_encode_impl(h, phoneme, phone_len, B, Tx, pos_emb, Tp, nullptr, nullptr, style_in, 1.f, 1, enc_state, dur,
+  acoustic_encode_impl(h, phoneme, phone_len, B, Tx, pos_emb, Tp, nullptr, nullptr, style_in, nullptr, 1.f, 1, enc_state, dur,
                        frame_len, log_dur, nullptr, workspace, workspace_bytes, stream);
   PT_API_END
 }

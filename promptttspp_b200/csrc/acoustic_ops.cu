@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(256) style_mdn_sample_kernel(const float* __re
                                                                const float* __restrict__ mu,
                                                                const float* __restrict__ z, int G, int D,
                                                                float noise_scale, int normalize,
-                                                               float* __restrict__ style) {
+                                                               float* __restrict__ style,
+                                                               const float* __restrict__ comp_u) {
   __shared__ float red[32];
   const int b = blockIdx.x;
   const float* lp = logpi + (int64_t)b * G * D;
@@ -132,6 +133,22 @@ __global__ void __launch_bounds__(256) style_mdn_sample_kernel(const float* __re
       if (v > bestv) {
         bestv = v;
         best = g;
+      }
+    }
+    if (comp_u) {
+      // use_max=False (mdn.py:226-257): one Categorical(probs=exp(log_pi)) draw per dimension, here by inverse CDF of
+      // the supplied uniform (the draw itself is an input, like every other random number of the path)
+      const float u = comp_u[(int64_t)b * D + dd];
+      float tot = 0.f;
+      for (int g = 0; g < G; ++g) tot += expf((lp[g * D + dd] - mx) - lse);
+      float cum = 0.f;
+      best = G - 1;
+      for (int g = 0; g < G; ++g) {
+        cum += expf((lp[g * D + dd] - mx) - lse) / tot;
+        if (u < cum) {
+          best = g;
+          break;
+        }
       }
     }
     const float sigma = expf(ls[best * D + dd]);
@@ -488,9 +505,9 @@ void l2_normalize_rows(float* x, int rows, int C, cudaStream_t s) {
 }
 
 void style_mdn_sample(const float* logpi, const float* logsigma, const float* mu, const float* z, int B, int G, int D,
-                      float noise_scale, int normalize, float* style, cudaStream_t s) {
+                      float noise_scale, int normalize, float* style, cudaStream_t s, const float* comp_u) {
   if (B == 0) return;
-  style_mdn_sample_kernel<<<B, 256, 0, s>>>(logpi, logsigma, mu, z, G, D, noise_scale, normalize, style);
+  style_mdn_sample_kernel<<<B, 256, 0, s>>>(logpi, logsigma, mu, z, G, D, noise_scale, normalize, style, comp_u);
   PT_LAUNCHED();
 }
 

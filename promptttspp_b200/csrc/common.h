@@ -118,7 +118,8 @@ void glu_dw_bn_swish_cl(const float* in /*[B][T][2C]*/, const int64_t* len, cons
                         int K, float* out, cudaStream_t s);
 void l2_normalize_rows(float* x, int rows, int C, cudaStream_t s);
 void style_mdn_sample(const float* logpi, const float* logsigma, const float* mu /*[B][G*D]*/, const float* z,
-                      int B, int G, int D, float noise_scale, int normalize, float* style, cudaStream_t s);
+                      int B, int G, int D, float noise_scale, int normalize, float* style, cudaStream_t s,
+                      const float* comp_u = nullptr);
 void add_row_broadcast(float* x /*[B][T][C]*/, const float* v /*[B][C]*/, int B, int T, int C, cudaStream_t s);
 void mdn_duration_head(const float* h /*[B][T][C]*/, const float* w_pi, const float* b_pi, const float* w_ls,
                        const float* b_ls, const float* w_mu, const float* b_mu, int rows, int C, int G,

@@ -33,6 +33,7 @@ class InferNoise(NamedTuple):
     z_style: torch.Tensor
     x_T: Optional[torch.Tensor]
     z: Optional[torch.Tensor]
+    comp_u: Optional[torch.Tensor] = None  # [B, C] uniforms: the per-dimension component draw of use_max=False
 
 
 def _sinusoid_table(positions: torch.Tensor, d_model: int) -> torch.Tensor:
@@ -157,8 +158,6 @@ class PromptTTSMDNDurCFG(nn.Module):
     def _synthesize(self, phoneme, phone_lengths, style_prompt, reference_mel, use_max, noise_scale, noise,
                     ref_lengths=None):
         assert (style_prompt is not None) ^ (reference_mel is not None), "One of style inputs must not be None."
-        if not use_max and reference_mel is None:
-            raise NotImplementedError("use_max=False (categorical MDN component sampling) is not implemented")
         _abi.require_cuda(phoneme, "PromptTTSMDNDurCFG.infer")
         device = phoneme.device
         B, Tx = phoneme.shape
@@ -186,6 +185,14 @@ class PromptTTSMDNDurCFG(nn.Module):
                 # RNG draw #1 (model.py:191)
                 z_style = noise.z_style if noise is not None else torch.randn(B, 1, Cc, device=device)
                 z_style = z_style.to(device=device, dtype=torch.float32).reshape(B, Cc).contiguous()
+                comp_u = None
+                if not use_max:
+                    # mdn_sample_sigma_and_mu (mdn.py:226-257): one component draw per (utterance, dimension), supplied
+                    # as uniforms (the reference's Categorical.sample consumes its own generator stream)
+                    comp_u = getattr(noise, "comp_u", None) if noise is not None else None
+                    if comp_u is None:
+                        comp_u = torch.rand(B, Cc, device=device)
+                    comp_u = comp_u.to(device=device, dtype=torch.float32).reshape(B, Cc).contiguous()
             legacy = self.encoder.rel_pos_type == "legacy"
             pos = self._pos_table("legacy" if legacy else "new", Tx, device)
             enc_state = torch.empty(B, Tx, Cc, device=device)
@@ -198,6 +205,12 @@ class PromptTTSMDNDurCFG(nn.Module):
                     nat.h, _abi.ptr(phoneme), _abi.ptr(phone_lengths), B, Tx, _abi.ptr(pos), pos.shape[0],
                     _abi.ptr(style_in), _abi.ptr(enc_state), _abi.ptr(dur), _abi.ptr(frame_len), _abi.ptr(log_dur),
                     _abi.ptr(ws), C.c_size_t(ws.numel()), stream))
+            elif not use_max:
+                _abi.check(lib.pttspp_acoustic_encode_sampled(
+                    nat.h, _abi.ptr(phoneme), _abi.ptr(phone_lengths), B, Tx, _abi.ptr(pos), pos.shape[0],
+                    _abi.ptr(cls), _abi.ptr(z_style), _abi.ptr(comp_u), float(noise_scale), _abi.ptr(enc_state),
+                    _abi.ptr(dur), _abi.ptr(frame_len), _abi.ptr(log_dur), None, _abi.ptr(ws),
+                    C.c_size_t(ws.numel()), stream))
             else:
                 _abi.check(lib.pttspp_acoustic_encode(
                     nat.h, _abi.ptr(phoneme), _abi.ptr(phone_lengths), B, Tx, _abi.ptr(pos), pos.shape[0],

@@ -263,6 +263,49 @@ def make_style(ns):
     np.savez_compressed(OUT / "style_refmel.npz", **out)
 
 
+def make_sampled(ns):
+    """infer_batch(use_max=False): the reference's Categorical(probs=pi).sample() replaced by the inverse CDF of seeded
+    uniforms (same distribution; the draw becomes an input like the Gaussian ones)."""
+    from golden_cases import ACOUSTIC_SAMPLED_CASE, component_uniforms
+
+    case = ACOUSTIC_SAMPLED_CASE
+    model = build_acoustic(rel_pos_type=case["rel_pos_type"], ns=ns, K_step=case["K_step"]).eval()
+    sd = synthetic_state_dict(build_acoustic(rel_pos_type=case["rel_pos_type"], bert=_FixedBert(), K_step=case["K_step"]),
+                              seed=case["weight_seed"], frames_per_phoneme=case["frames_per_phoneme"])
+    model.load_state_dict(sd, strict=True)
+    phoneme, lengths, cls_emb = acoustic_inputs(case)
+    _FixedBert.table = cls_emb
+    B = phoneme.shape[0]
+    u = component_uniforms(case, B)
+    noise = {}
+
+    def x_T_fn(shape):
+        noise["full"] = golden_noise(case, B, shape[-1])
+        return noise["full"].x_T.clone()
+
+    def z_fn(shape, n):
+        return noise["full"].z[n].clone()
+
+    real_sample = torch.distributions.Categorical.sample
+
+    def fake_sample(self, sample_shape=torch.Size()):
+        probs = self.probs                                   # (B, C, G), normalised by Categorical
+        assert tuple(probs.shape[:2]) == tuple(u.shape), probs.shape
+        cdf = torch.cumsum(probs, dim=-1)
+        return (u.unsqueeze(-1) >= cdf).sum(-1).clamp(max=probs.shape[-1] - 1)
+
+    torch.distributions.Categorical.sample = fake_sample
+    try:
+        with injected_noise(golden_noise(case, B, None).z_style, x_T_fn, z_fn):
+            mel, log_cf0, vuv, frame_lengths = model.infer_batch(phoneme, lengths, style_prompt=["p"] * B, use_max=False,
+                                                                 noise_scale=case["noise_scale"], return_f0=True)
+    finally:
+        torch.distributions.Categorical.sample = real_sample
+    print("   sampled acoustic Ty", mel.shape[-1], frame_lengths.tolist())
+    np.savez_compressed(OUT / "acoustic_sampled_b2.npz", mel=mel.numpy(), log_cf0=log_cf0.numpy(), vuv=vuv.numpy(),
+                        frame_lengths=frame_lengths.numpy())
+
+
 def make_ops():
     """Op-level vectors from the reference layers: pin the closed forms used by the kernels."""
     sys.path.insert(0, str(REF))
@@ -307,7 +350,7 @@ def make_ops():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops", "vocoder", "vocoder_f0", "lowpass", "style", "acoustic"]
+    which = sys.argv[1:] or ["ops", "vocoder", "vocoder_f0", "lowpass", "style", "sampled", "acoustic"]
     if "ops" in which:
         make_ops()
     if "vocoder" in which:
@@ -318,6 +361,8 @@ if __name__ == "__main__":
         make_lowpass()
     if "style" in which:
         make_style(reference_namespace())
+    if "sampled" in which:
+        make_sampled(reference_namespace())
     if "acoustic" in which:
         make_acoustic(reference_namespace())
     print("done")

@@ -103,3 +103,13 @@ def style_inputs(case=None):
     for b, n in enumerate(lens):
         mel[b, :, n:] = 0
     return mel, torch.tensor(lens, dtype=torch.int64)
+
+
+# use_max=False: per-dimension Categorical draw of the style MDN component (mdn.py:226-257), realised from uniforms
+ACOUSTIC_SAMPLED_CASE = dict(api="infer_batch", rel_pos_type="legacy", lengths=[8, 5], weight_seed=1234,
+                             frames_per_phoneme=3.0, input_seed=9, noise_seed=109, noise_scale=0.7, K_step=100)
+
+
+def component_uniforms(case, B, C=256):
+    g = torch.Generator().manual_seed(case["noise_seed"] + 5000)
+    return torch.rand(B, C, generator=g)

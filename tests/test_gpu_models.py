@@ -262,3 +262,28 @@ def test_style_encoder_and_reference_mel_inference_match_golden(golden_dir):
     assert torch.allclose(log_cf0.cpu(), torch.from_numpy(gold["log_cf0"]), atol=1e-3)
     with pytest.raises(AssertionError):
         model.infer_batch(phoneme.cuda(), lengths.cuda(), reference_mel=ref_mel.cuda())  # ref_lengths required (model.py:296)
+
+
+def test_use_max_false_matches_reference_golden(golden_dir):
+    from golden_cases import ACOUSTIC_SAMPLED_CASE, component_uniforms
+    from promptttspp_b200.models.prompttts_mdn_v2_final.model import InferNoise
+
+    case = ACOUSTIC_SAMPLED_CASE
+    gold = np.load(golden_dir / "acoustic_sampled_b2.npz")
+    phoneme, lengths, cls_emb = acoustic_inputs(case)
+    model = build_acoustic(bert=FixedPromptEmbedding(cls_emb), K_step=case["K_step"])
+    model.load_state_dict(synthetic_state_dict(model, seed=case["weight_seed"],
+                                               frames_per_phoneme=case["frames_per_phoneme"]), strict=True)
+    model = model.cuda().eval()
+    B = phoneme.shape[0]
+    n = golden_noise(case, B, int(gold["mel"].shape[-1]))
+    noise = InferNoise(n.z_style, n.x_T, n.z, component_uniforms(case, B))
+    mel, log_cf0, vuv, flen = model.infer_batch(phoneme.cuda(), lengths.cuda(), style_prompt=["p"] * B, use_max=False,
+                                                noise_scale=case["noise_scale"], return_f0=True, noise=noise)
+    assert torch.equal(flen.cpu(), torch.from_numpy(gold["frame_lengths"]))
+    err = float((mel.cpu() - torch.from_numpy(gold["mel"])).abs().max())
+    print(f"infer_batch(use_max=False): mel max-abs err {err:.2e}")
+    assert err < MEL_TOL
+    torch.manual_seed(3)
+    m2, _ = model.infer_batch(phoneme.cuda(), lengths.cuda(), style_prompt=["p"] * B, use_max=False)  # own draws
+    assert torch.isfinite(m2).all()

@@ -159,3 +159,24 @@ def test_style_encoder_oracle_matches_reference(golden_dir):
     # the restated GRU / conv2d differ from ATen's in the last bits of the style vector (< 2e-6 above); 100 diffusion
     # steps amplify that to ~3e-5 on the mel -- still 30x inside the 1e-3 bar
     assert float((mel_out - torch.from_numpy(gold["mel"])).abs().max()) < 1e-4
+
+
+def test_acoustic_use_max_false_oracle_matches_reference(golden_dir):
+    """use_max=False (mdn.py:226-257): component draw realised from injected uniforms on both sides."""
+    from golden_cases import ACOUSTIC_SAMPLED_CASE, component_uniforms
+
+    case = ACOUSTIC_SAMPLED_CASE
+    gold = np.load(golden_dir / "acoustic_sampled_b2.npz")
+    sd = synthetic_state_dict(build_acoustic(rel_pos_type="legacy", bert=lambda *a: None, K_step=case["K_step"]),
+                              seed=case["weight_seed"], frames_per_phoneme=case["frames_per_phoneme"])
+    phoneme, lengths, cls_emb = acoustic_inputs(case)
+    B = phoneme.shape[0]
+    noise = golden_noise(case, B, int(gold["mel"].shape[-1]))
+    cfg = dict(oracle.ACOUSTIC_CFG, K_step=case["K_step"])
+    mel, _, _, flen = oracle.acoustic_infer_batch(sd, cfg, phoneme, lengths, cls_emb, noise.z_style, noise.x_T, noise.z,
+                                                  noise_scale=case["noise_scale"], comp_u=component_uniforms(case, B))
+    assert torch.equal(flen, torch.from_numpy(gold["frame_lengths"]))
+    assert float((mel - torch.from_numpy(gold["mel"])).abs().max()) < 1e-5
+    mel_max, _, _, _ = oracle.acoustic_infer_batch(sd, cfg, phoneme, lengths, cls_emb, noise.z_style, noise.x_T, noise.z,
+                                                   noise_scale=case["noise_scale"])
+    assert float((mel_max - mel).abs().max()) > 1e-3  # the sampled components really differ from the arg-max ones
