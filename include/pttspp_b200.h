@@ -223,6 +223,16 @@ int pttspp_style_token_attention(const float* ref, int B, int R, const float* gs
                                  const float* wq, const float* bq, const float* wk, const float* bk, const float* wv,
                                  const float* bv, const float* wo, const float* bo, float* out, pttspp_stream_t stream);
 
+/* BERT building blocks for the prompt encoder's sentence embedding (promptttspp/modules/prompt_encoder.py:22-38 calls HF
+ * transformers' BertModel; third-party).  bert_embed: out[b][t] = word_emb[ids[b][t]] + type_emb0 + pos_emb[t]
+ * (BertEmbeddings before its LayerNorm).  mha_masked: BertSelfAttention on a fused q|k|v buffer qkv [B][T][3*heads*dk]:
+ * softmax(q k^T / sqrt(dk) + (1 - key_mask) * finfo.min) v -> out [B][T][heads*dk]; key_mask [B][T] int64 (1 = token) or
+ * NULL.  Linear / GELU / LayerNorm layers use pttspp_conv1d_cl and pttspp_layernorm_cl. */
+int pttspp_bert_embed(const int64_t* ids, int B, int T, const float* word_emb, int vocab, const float* pos_emb,
+                      const float* type_emb0, int hidden, float* out, pttspp_stream_t stream);
+int pttspp_mha_masked(const float* qkv, const int64_t* key_mask, int B, int T, int heads, int dk, float* out,
+                      pttspp_stream_t stream);
+
 /* Relative-position multi-head self-attention (Transformer-XL style), both ESPnet variants.
  *   scores = ((q+u) k^T + rel_shift((q+v) p^T)) / sqrt(d_k); masked softmax; . v
  * q,k,v,out: [B][T][H*d_k]; p: [Tp][H*d_k] with Tp = T (legacy) or 2T-1 (new);

@@ -524,6 +524,39 @@ def style_embedding(sd, cfg, cls_emb, z_style, noise_scale, comp_u=None):
     return style.transpose(-1, -2)
 
 
+def bert_forward(sd, input_ids, attention_mask, heads, eps=1e-12, prefix=""):
+    """HF transformers BertModel(...).last_hidden_state (the reference's third-party dependency, prompt_encoder.py:25,
+    33-38; transformers 5.5.0 modeling_bert.py): BertEmbeddings (word + token_type(0) + position, LayerNorm), then per
+    layer BertSelfAttention (eager: softmax(q k^T / sqrt(dk) + (1 - mask) * finfo.min) v), BertSelfOutput (dense +
+    residual, LayerNorm), BertIntermediate (dense, exact-erf GELU), BertOutput (dense + residual, LayerNorm)."""
+    e = prefix + "embeddings."
+    B, T = input_ids.shape
+    x = F.embedding(input_ids, sd[e + "word_embeddings.weight"]) + sd[e + "token_type_embeddings.weight"][0]
+    x = x + sd[e + "position_embeddings.weight"][:T]
+    Hd = x.shape[-1]
+    x = F.layer_norm(x, (Hd,), sd[e + "LayerNorm.weight"], sd[e + "LayerNorm.bias"], eps)
+    dk = Hd // heads
+    add = torch.zeros(B, 1, 1, T)
+    if attention_mask is not None:
+        add = (1.0 - attention_mask[:, None, None, :].float()) * torch.finfo(torch.float32).min
+    n = 0
+    while f"{prefix}encoder.layer.{n}.attention.self.query.weight" in sd:
+        p = f"{prefix}encoder.layer.{n}."
+        lin = lambda t, name: F.linear(t, sd[p + name + ".weight"], sd[p + name + ".bias"])
+        q = lin(x, "attention.self.query").view(B, T, heads, dk).transpose(1, 2)
+        k = lin(x, "attention.self.key").view(B, T, heads, dk).transpose(1, 2)
+        v = lin(x, "attention.self.value").view(B, T, heads, dk).transpose(1, 2)
+        w = F.softmax(q @ k.transpose(-1, -2) / math.sqrt(dk) + add, dim=-1)
+        ctx = (w @ v).transpose(1, 2).reshape(B, T, Hd)
+        x = F.layer_norm(lin(ctx, "attention.output.dense") + x, (Hd,), sd[p + "attention.output.LayerNorm.weight"],
+                         sd[p + "attention.output.LayerNorm.bias"], eps)
+        h = F.gelu(lin(x, "intermediate.dense"))
+        x = F.layer_norm(lin(h, "output.dense") + x, (Hd,), sd[p + "output.LayerNorm.weight"],
+                         sd[p + "output.LayerNorm.bias"], eps)
+        n += 1
+    return x
+
+
 def style_encoder(sd, speech, in_lens=None, prefix="reference_encoder.", conv_layers=6, stride=2, heads=4):
     """StyleEncoder.forward (modules/style_encoder.py:70-80): ReferenceEncoder (reference_encoder.py:95-124: 6 x
     [Conv2d k3 s2 no bias, BatchNorm2d eval, ReLU], GRU whose last VALID state is the embedding -- the packed-sequence

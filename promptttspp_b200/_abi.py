@@ -108,6 +108,9 @@ SIGNATURES = {
     "pttspp_relpos_attention": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pttspp_iir_filtfilt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                       C.c_void_p]),
+    "pttspp_bert_embed": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_void_p, C.c_void_p]),
+    "pttspp_mha_masked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "pttspp_conv2d_bn_relu": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 8 + [C.c_void_p]),
     "pttspp_gru_last_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6),
     "pttspp_style_token_attention": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]

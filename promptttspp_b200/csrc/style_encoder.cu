@@ -196,3 +196,93 @@ extern "C" int pttspp_style_token_attention(const float* ref, int B, int R, cons
   PT_LAUNCHED();
   PT_API_END
 }
+
+// ---- BERT building blocks (the prompt encoder's sentence embedding) ----------------------
+// BertEmbeddings (HF transformers modeling_bert.py, the reference's dependency at promptttspp/modules/prompt_encoder.py:
+// 25,33-38): word + position + token-type(0) embeddings (the LayerNorm that follows is pttspp_layernorm_cl);
+// BertSelfAttention: softmax(q k^T / sqrt(dk) + (1 - mask) * finfo.min) v on a fused [B][T][3*H*dk] q|k|v buffer.
+namespace pttspp {
+namespace {
+
+__global__ void __launch_bounds__(256) bert_embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ word,
+                                                         const float* __restrict__ pos, const float* __restrict__ type0,
+                                                         float* __restrict__ out, int T, int Hd, int vocab, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % Hd);
+  const int64_t bt = i / Hd;
+  const int t = (int)(bt % T);
+  int64_t id = ids[bt];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  out[i] = (word[id * Hd + c] + type0[c]) + pos[(int64_t)t * Hd + c];  // inputs_embeds + token_type, then + position
+}
+
+// one warp per query row; scores of that row in shared memory
+__global__ void __launch_bounds__(128) mha_masked_kernel(const float* __restrict__ qkv, const int64_t* __restrict__ mask,
+                                                         float* __restrict__ out, int T, int heads, int dk) {
+  extern __shared__ float sc[];  // [4 warps][T]
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Hd = heads * dk, ld = 3 * Hd;
+  const float* base = qkv + (int64_t)b * T * ld;
+  float* s = sc + warp * T;
+  const float scale = 1.f / sqrtf((float)dk);
+  for (int qi = blockIdx.x * 4 + warp; qi < T; qi += gridDim.x * 4) {
+    const float* q = base + (int64_t)qi * ld + h * dk;
+    for (int j = 0; j < T; ++j) {
+      const float* k = base + (int64_t)j * ld + Hd + h * dk;
+      float a = 0.f;
+      for (int d = lane; d < dk; d += 32) a = fmaf(q[d], k[d], a);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) s[j] = a * scale + ((mask && mask[(int64_t)b * T + j] == 0) ? -3.4028234663852886e38f : 0.f);
+    }
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) mx = fmaxf(mx, s[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      const float e = expf(s[j] - mx);
+      s[j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    for (int d = lane; d < dk; d += 32) {
+      float a = 0.f;
+      for (int j = 0; j < T; ++j) a = fmaf(s[j], base[(int64_t)j * ld + 2 * Hd + h * dk + d], a);
+      out[((int64_t)b * T + qi) * Hd + h * dk + d] = a / sum;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+}  // namespace pttspp
+
+extern "C" int pttspp_bert_embed(const int64_t* ids, int B, int T, const float* word_emb, int vocab, const float* pos_emb,
+                                 const float* type_emb0, int hidden, float* out, pttspp_stream_t stream) {
+  PT_API_BEGIN
+  PT_CHECK(ids && word_emb && pos_emb && type_emb0 && out, "null argument");
+  PT_CHECK(B >= 1 && T >= 1 && hidden >= 1 && vocab >= 1, "bert_embed: bad shape");
+  const int64_t total = (int64_t)B * T * hidden;
+  bert_embed_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(ids, word_emb, pos_emb, type_emb0,
+                                                                                       out, T, hidden, vocab, total);
+  PT_LAUNCHED();
+  PT_API_END
+}
+
+extern "C" int pttspp_mha_masked(const float* qkv, const int64_t* key_mask, int B, int T, int heads, int dk, float* out,
+                                 pttspp_stream_t stream) {
+  PT_API_BEGIN
+  PT_CHECK(qkv && out, "null argument");
+  PT_CHECK(B >= 1 && T >= 1 && heads >= 1 && dk >= 1 && T <= 2048, "mha: bad shape (T <= 2048)");
+  ProfScope prof(PROF_ATTENTION, (cudaStream_t)stream, 4.0 * B * heads * (double)T * T * dk, 0.0);
+  dim3 grid(std::min(ceil_div(T, 4), 64), heads, B);
+  mha_masked_kernel<<<grid, 128, (size_t)4 * T * sizeof(float), (cudaStream_t)stream>>>(qkv, key_mask, out, T, heads, dk);
+  PT_LAUNCHED();
+  PT_API_END
+}

@@ -1,10 +1,10 @@
 """Prompt encoder: external BERT sentence embedding + the adaptor MLP weights.
 
-Reference: promptttspp/modules/prompt_encoder.py:22-56.  BERT-base itself is a
-third-party model (HF transformers) and is SURVEY.md row f2 ("next"): this
-class keeps the reference's ``bert`` sub-module so its checkpoint keys load,
-and accepts any callable ``(prompts, device) -> [B, in_channels]`` in its
-place (``bert=...``) -- benchmarks and tests use a fixed-embedding provider.
+Reference: promptttspp/modules/prompt_encoder.py:22-56.  ``BertWrapper`` runs BERT
+natively (modules/bert.py) under HF's parameter names so the
+checkpoint keys load; any callable ``(prompts, device) -> [B, in_channels]`` can
+take its place (``bert=...``) -- benchmarks use a fixed-embedding provider, as
+BASELINE.json's configs prescribe.
 The adaptor MLP + L2-normalise + style MDN run in csrc/acoustic.cu.
 """
 from typing import List
@@ -14,19 +14,33 @@ from torch import nn
 
 
 class BertWrapper(nn.Module):
-    """CLS embedding of a HF BertModel (prompt_encoder.py:22-38)."""
+    """CLS embedding of BERT (prompt_encoder.py:22-38).  `model` is the native encoder (modules/bert.py) under HF's
+    state_dict names; the tokenizer is HF's (host string work) when its vocabulary is available.  `forward` accepts the
+    reference's list of strings, or already tokenised `(input_ids, attention_mask)` tensors."""
 
-    def __init__(self, class_name="bert-base-uncased"):
+    def __init__(self, class_name="bert-base-uncased", **bert_config):
         super().__init__()
-        from transformers import BertModel, BertTokenizer
+        from .bert import NativeBert
 
-        self.model = BertModel.from_pretrained(class_name)
-        self.tokenizer = BertTokenizer.from_pretrained(class_name)
+        self.class_name = class_name
+        self.model = NativeBert(**bert_config)
+        self.tokenizer = None
+
+    def _tokenizer(self):
+        if self.tokenizer is None:
+            from transformers import BertTokenizer
+
+            self.tokenizer = BertTokenizer.from_pretrained(self.class_name)  # needs the vocabulary file on disk
+        return self.tokenizer
 
     @torch.no_grad()
-    def forward(self, prompts: List[str], device) -> torch.Tensor:
-        inputs = self.tokenizer(prompts, padding=True, return_tensors="pt").to(device)
-        return self.model(**inputs).last_hidden_state[:, 0, :]
+    def forward(self, prompts, device) -> torch.Tensor:
+        if isinstance(prompts, (tuple, list)) and len(prompts) == 2 and isinstance(prompts[0], torch.Tensor):
+            ids, mask = prompts
+        else:
+            enc = self._tokenizer()(list(prompts), padding=True, return_tensors="pt")
+            ids, mask = enc["input_ids"], enc["attention_mask"]
+        return self.model(ids.to(device), mask.to(device))[:, 0, :]
 
 
 class FixedPromptEmbedding(nn.Module):

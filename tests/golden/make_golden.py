@@ -306,6 +306,31 @@ def make_sampled(ns):
                         frame_lengths=frame_lengths.numpy())
 
 
+def make_bert():
+    """HF transformers BertModel (the reference's dependency, prompt_encoder.py:25) with a small seeded config: weights
+    and last_hidden_state stored together."""
+    from golden_cases import BERT_SMALL, bert_inputs
+    from transformers import BertConfig, BertModel
+
+    torch.manual_seed(99)
+    hf = BertModel(BertConfig(**BERT_SMALL, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)).eval()
+    with torch.no_grad():
+        for n, p in hf.named_parameters():  # de-degenerate LayerNorm / biases
+            if "LayerNorm.weight" in n:
+                p.copy_(1.0 + 0.1 * torch.randn_like(p))
+            elif n.endswith("bias"):
+                p.copy_(0.05 * torch.randn_like(p))
+            else:
+                p.mul_(4.0)
+    ids, mask = bert_inputs(BERT_SMALL["vocab_size"])
+    with torch.no_grad():
+        out = hf(input_ids=ids, attention_mask=mask).last_hidden_state
+    blob = {"w::" + k: v.numpy() for k, v in hf.state_dict().items()}
+    blob["last_hidden_state"] = out.numpy()
+    np.savez_compressed(OUT / "bert_small.npz", **blob)
+    print("bert", tuple(out.shape), float(out.abs().max()))
+
+
 def make_ops():
     """Op-level vectors from the reference layers: pin the closed forms used by the kernels."""
     sys.path.insert(0, str(REF))
@@ -350,7 +375,7 @@ def make_ops():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops", "vocoder", "vocoder_f0", "lowpass", "style", "sampled", "acoustic"]
+    which = sys.argv[1:] or ["ops", "vocoder", "vocoder_f0", "lowpass", "style", "sampled", "bert", "acoustic"]
     if "ops" in which:
         make_ops()
     if "vocoder" in which:
@@ -363,6 +388,8 @@ if __name__ == "__main__":
         make_style(reference_namespace())
     if "sampled" in which:
         make_sampled(reference_namespace())
+    if "bert" in which:
+        make_bert()
     if "acoustic" in which:
         make_acoustic(reference_namespace())
     print("done")

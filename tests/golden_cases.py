@@ -113,3 +113,20 @@ ACOUSTIC_SAMPLED_CASE = dict(api="infer_batch", rel_pos_type="legacy", lengths=[
 def component_uniforms(case, B, C=256):
     g = torch.Generator().manual_seed(case["noise_seed"] + 5000)
     return torch.rand(B, C, generator=g)
+
+
+# BERT: a small config whose weights fit in the golden file; bert-base dimensions are exercised on the
+# GPU against the oracle with seeded weights
+BERT_SMALL = dict(vocab_size=120, hidden_size=128, num_hidden_layers=2, num_attention_heads=4, intermediate_size=256,
+                  max_position_embeddings=64, type_vocab_size=2, layer_norm_eps=1e-12)
+
+
+def bert_inputs(vocab=120, B=3, T=11, seed=13):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(1, vocab, (B, T), generator=g)
+    lens = [T, T - 4, 3]
+    mask = torch.zeros(B, T, dtype=torch.int64)
+    for b, n in enumerate(lens[:B]):
+        mask[b, :n] = 1
+        ids[b, n:] = 0
+    return ids, mask

@@ -287,3 +287,37 @@ def test_use_max_false_matches_reference_golden(golden_dir):
     torch.manual_seed(3)
     m2, _ = model.infer_batch(phoneme.cuda(), lengths.cuda(), style_prompt=["p"] * B, use_max=False)  # own draws
     assert torch.isfinite(m2).all()
+
+
+# ---- BERT sentence embedding ----
+
+def test_native_bert_matches_hf_golden_and_oracle(golden_dir):
+    from golden_cases import BERT_SMALL, bert_inputs
+    from promptttspp_b200.modules.bert import NativeBert
+    from promptttspp_b200.modules.prompt_encoder import BertWrapper
+
+    gold = np.load(golden_dir / "bert_small.npz")
+    sd = {k[3:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith("w::")}
+    bert = NativeBert(**BERT_SMALL)
+    bert.load_state_dict(sd, strict=True)  # HF BertModel's own key names
+    bert = bert.cuda().eval()
+    ids, mask = bert_inputs(BERT_SMALL["vocab_size"])
+    out = bert(ids.cuda(), mask.cuda()).cpu()
+    ref = torch.from_numpy(gold["last_hidden_state"])
+    err = float(((out - ref) * mask.bool().unsqueeze(-1)).abs().max())
+    print(f"native bert (small) vs HF: max-abs err on valid tokens {err:.2e}")
+    assert err < 5e-5
+    # bert-base dimensions, 4 layers, seeded weights: native vs the oracle restatement (CLS rows)
+    torch.manual_seed(5)
+    big = NativeBert(vocab_size=1000, num_hidden_layers=4)
+    for n, p in big.named_parameters():
+        if "LayerNorm.weight" not in n:
+            p.data.mul_(0.0).add_(torch.randn_like(p) * (0.04 if p.dim() > 1 else 0.02))
+    ids2, mask2 = bert_inputs(1000, B=3, T=40, seed=3)
+    want = oracle.bert_forward({k: v.detach() for k, v in big.state_dict().items()}, ids2, mask2, 12)[:, 0]
+    wrap = BertWrapper(vocab_size=1000, num_hidden_layers=4)
+    wrap.model.load_state_dict(big.state_dict())
+    got = wrap.cuda()((ids2, mask2), torch.device("cuda")).cpu()
+    err2 = float((got - want).abs().max())
+    print(f"native bert (base dims) CLS vs oracle: max-abs err {err2:.2e}")
+    assert got.shape == (3, 768) and err2 < 1e-4

@@ -180,3 +180,17 @@ def test_acoustic_use_max_false_oracle_matches_reference(golden_dir):
     mel_max, _, _, _ = oracle.acoustic_infer_batch(sd, cfg, phoneme, lengths, cls_emb, noise.z_style, noise.x_T, noise.z,
                                                    noise_scale=case["noise_scale"])
     assert float((mel_max - mel).abs().max()) > 1e-3  # the sampled components really differ from the arg-max ones
+
+
+def test_bert_oracle_matches_hf_transformers(golden_dir):
+    """Prompt encoder's BERT: oracle restatement vs HF transformers' BertModel (small seeded config)."""
+    from golden_cases import BERT_SMALL, bert_inputs
+
+    gold = np.load(golden_dir / "bert_small.npz")
+    sd = {k[3:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith("w::")}
+    ids, mask = bert_inputs(BERT_SMALL["vocab_size"])
+    out = oracle.bert_forward(sd, ids, mask, BERT_SMALL["num_attention_heads"])
+    ref = torch.from_numpy(gold["last_hidden_state"])
+    valid = mask.bool().unsqueeze(-1)
+    assert float(((out - ref) * valid).abs().max()) < 2e-5
+    assert float((out[:, 0] - ref[:, 0]).abs().max()) < 2e-5  # the CLS rows the prompt encoder reads
