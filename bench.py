@@ -28,6 +28,8 @@ os.environ.setdefault("TQDM_DISABLE", "1")
 
 import torch  # noqa: E402
 
+WORKLOAD = ("cfg2: prompttts_mdn_v2 acoustic model only, batch 16 synthetic phoneme seqs len<=256 (legacy rel-pos demo "
+            "config), text->mel incl. 100-step diffusion")
 METRIC = "mel_frames_per_sec"
 UNIT = "frames/s"
 TAGS = ["conv1d_simt_fp32", "conv1d_tcgen05_splitfp16", "aa_snake", "layernorm", "relpos_attention", "other"]
@@ -232,8 +234,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2 prompttts_mdn_v2 acoustic (bounded CPU sample, see cpu_baseline.sample)",
-                   "K_step": 100},
+        "config": {"workload": WORKLOAD, "K_step": 100, "sample": base["sample"]},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "bigvgan": cpu_bigvgan_sample(max(1, min(args.steps, 3)), 1),
@@ -351,8 +352,7 @@ def run_native(args, rank, local_rank, world):
             "metric": METRIC, "value": frames_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg2: prompttts_mdn_v2 acoustic model only, batch 16 synthetic phoneme seqs "
-                                   "len<=256 (legacy rel-pos demo config), text->mel incl. 100-step diffusion",
+            "config": {"workload": WORKLOAD,
                        "batch_per_gpu": B, "valid_frames": float(valid), "padded_frames": float(padded),
                        "K_step": 100, "l2": "working set (>1 GB of activations per step) exceeds the 126 MB L2",
                        "parallelism": f"utterance batches sharded over {world} GPU(s), no data-path collective"},
