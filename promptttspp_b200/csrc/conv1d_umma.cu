@@ -1380,12 +1380,12 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
 // for the whole kernel; per 128-row tile the producer loads ONE halo block (128 + (K-1)*dil rows x 64 B x 2 planes,
 // SWIZZLE_64B K-major) and every tap's MMAs read it through a descriptor advanced by tap*dil rows.  The tensor work per
 // tile is tiny (K x 6 MMAs of 128 x 32 x 16), so the kernel is organised for memory-level parallelism: a deep
-// activation ring, four accumulator buffers, and TWO epilogue groups of 8 warps that alternate tiles, so that one
+// activation ring, every TMEM column as accumulator buffers, and TWO epilogue groups of 8 warps that alternate tiles, so that one
 // group's residual loads are in flight while the other computes and stores.
 constexpr int US_EW = 8;            // epilogue warps per group
 constexpr int US_GROUPS = 2;
 constexpr int US_THREADS = (US_GROUPS * US_EW + 2) * 32;
-constexpr int US_NBUF = 4;          // accumulator buffers (main | cross, 64 TMEM columns each)
+constexpr int US_MAX_NBUF = 8;       // accumulator buffers (main | cross): 512 TMEM columns / (2 * channels)
 constexpr int US_MAXK = 11;
 
 // K-major, SWIZZLE_64B shared-memory matrix descriptor: rows of 64 bytes, 8-row groups 512 bytes apart
@@ -1406,7 +1406,8 @@ __global__ void __launch_bounds__(US_THREADS, 1)
 conv1d_umma_c32_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                        const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                        const pttspp_conv1d_desc d, const int n_mt, const int n_tiles, const int rowsA) {
-  constexpr uint32_t TMEM_COLS = US_NBUF * 2 * US_C;  // 256 / 512
+  constexpr int NBUF = 512 / (2 * US_C);  // accumulator buffers: all 512 TMEM columns (8 at 32 channels, 4 at 64)
+  constexpr uint32_t TMEM_COLS = 512;
   constexpr uint32_t ROWB = US_C * 2;                 // bytes per operand row
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1419,12 +1420,12 @@ conv1d_umma_c32_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_c
   const uint32_t bars_off = ((w_bytes + 1023u) & ~1023u) + (uint32_t)NST * a_stage;
   const uint32_t bars = base + bars_off;
   // fullW, fullA[NST], emptyA[NST], tfull[NBUF], tempty[NBUF]
-  constexpr int NBARS = 1 + 2 * NST + 2 * US_NBUF;
+  constexpr int NBARS = 1 + 2 * NST + 2 * NBUF;
   const uint32_t fullW = bars;
   auto fullA = [&](int st) { return bars + (1 + st) * 8; };
   auto emptyA = [&](int st) { return bars + (1 + NST + st) * 8; };
   auto tfull_bar = [&](int u) { return bars + (1 + 2 * NST + u) * 8; };
-  auto tempty_bar = [&](int u) { return bars + (1 + 2 * NST + US_NBUF + u) * 8; };
+  auto tempty_bar = [&](int u) { return bars + (1 + 2 * NST + NBUF + u) * 8; };
   const uint32_t tmem_slot = bars + NBARS * 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + bars_off + NBARS * 8);
 
@@ -1436,7 +1437,7 @@ conv1d_umma_c32_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_c
       mbar_init(fullA(st), 1);
       mbar_init(emptyA(st), 1);
     }
-    for (int u = 0; u < US_NBUF; ++u) {
+    for (int u = 0; u < NBUF; ++u) {
       mbar_init(tfull_bar(u), 1);
       mbar_init(tempty_bar(u), US_EW);
     }
@@ -1489,8 +1490,8 @@ conv1d_umma_c32_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_c
     tc_fence_after();
     uint32_t g = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++g) {
-      const int st = g % NST, u = g % US_NBUF;
-      mbar_wait_warp(tempty_bar(u), ((g / US_NBUF) & 1u) ^ 1u);
+      const int st = g % NST, u = g % NBUF;
+      mbar_wait_warp(tempty_bar(u), ((g / NBUF) & 1u) ^ 1u);
       mbar_wait_warp(fullA(st), (g / NST) & 1u);
       tc_fence_after();
       const uint32_t acc_main = tmem_base + (uint32_t)(u * 2 * US_C);
@@ -1524,8 +1525,8 @@ conv1d_umma_c32_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_c
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++g) {
       if ((int)(g % US_GROUPS) != grp) continue;
       const int mt = tile % n_mt, b = tile / n_mt;
-      const int u = g % US_NBUF;
-      umma_tile_epilogue_rl<US_C, 2, US_EW>(d, 0, mt, b, u, (g / US_NBUF) & 1u, wl, lane, tmem_base, tfull_bar(u), 1, 0);
+      const int u = g % NBUF;
+      umma_tile_epilogue_rl<US_C, 2, US_EW>(d, 0, mt, b, u, (g / NBUF) & 1u, wl, lane, tmem_base, tfull_bar(u), 1, 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(u));
@@ -1868,7 +1869,7 @@ void conv1d_umma_c32_launch(const pttspp_conv1d_desc& d_in, cudaStream_t s) {
   const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, swz);
   const size_t w_bytes = round_up(2 * d.K * C * rowb, 1024);
   const size_t a_stage = round_up(2 * rowsA * rowb, 1024);
-  const size_t misc = (1 + 2 * 6 + 2 * US_NBUF) * 8 + 16 + 1024;
+  const size_t misc = (1 + 2 * 6 + 2 * US_MAX_NBUF) * 8 + 16 + 1024;
   const size_t cap = 227 * 1024;
   PT_CHECK(w_bytes + 2 * a_stage + misc <= cap, "conv1d weight-resident kernel: shared memory budget exceeded");
   int nst = (int)std::min<size_t>(6, (cap - w_bytes - misc) / a_stage);
