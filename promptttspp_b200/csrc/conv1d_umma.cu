@@ -1114,9 +1114,9 @@ constexpr int UP_MAX_SLAB = 8;
 
 // EW epilogue warps (4 TMEM lane quarters x EW/4 column groups): 16 drain a tile fastest, 8 leave shared memory for
 // one more weight stage.
-// NACC = 2: main | cross-term accumulators, two tile buffers.  NACC = 1 (short contractions, K*Cin <= 256: at most 48
-// accumulations, truncation bias < 1e-5 relative): one accumulator per tile and FOUR tile buffers, so the MMA warp
-// runs up to three tiles ahead of a memory-bound epilogue.
+// NACC = 2: main | cross-term accumulators, two tile buffers.  NACC = 1 (K*Cin <= 768: at most 144 accumulations,
+// truncation bias ~1.5e-5 relative): one accumulator per tile and FOUR tile buffers, so the MMA warp runs up to three
+// tiles ahead of a memory-bound epilogue.
 template <int NBST, int EW, int NACC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((EW + 2) * 32, 1)
 conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
@@ -1801,7 +1801,12 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
   };
   // short contractions: one accumulator per tile, four tile buffers (see the kernel)
   const char* nae = getenv("PTTSPP_UMMA_NACC");
-  const bool one_acc = (d.K * d.Cin <= 256) && !(nae && nae[0] == '2');
+  // K*Cin <= 768 (144 accumulations): measured at cfg2 scale, the one-accumulator mode changes the mel by 1.9e-5 max-abs
+  // (bar 1e-3) and takes 4.6 % off the step (tools/nacc_experiment.py); PTTSPP_UMMA_NACC=2 forces two accumulators
+  // Only the gated (DiffNet) conv takes the extended range: BigVGAN's plain convs must stay bit-identical between the
+  // pair and the streaming kernel (an utterance synthesised alone equals the same utterance inside a batch).
+  const int one_acc_limit = (d.act == PTTSPP_ACT_GATE) ? 768 : 256;
+  const bool one_acc = ((d.K * d.Cin <= one_acc_limit) && !(nae && nae[0] == '2')) || (nae && nae[0] == '1');
 #define PT_PAIR_CASE(N, E, A) launch(conv1d_umma_pair_kernel<N, E, A>, pair_kernel_setup<N, E, A>(num_sms, debug))
 #define PT_PAIR_SWITCH(E, A)               \
   switch (nbst) {                          \

@@ -107,8 +107,10 @@ def test_conv1d_umma_plain(ops, monkeypatch, Cin, Cout, K, dil, B, T, variant):
                                 pad=pad)
     err = float((_bct(out) - ref).abs().max())
     print(f"umma {Cin}->{Cout} k{K} d{dil}: max-abs err {err:.3e}")
-    # the tensor core truncates on accumulate: the bias grows linearly with the K*Cin/16 accumulations
-    assert err < 1e-5 + 6e-9 * K * Cin, err
+    # the tensor core truncates on accumulate: the bias grows linearly with the K*Cin/16 accumulations; the CTA-pair
+    # kernel keeps main and cross terms in ONE accumulator up to K*Cin = 256 (768 for the gated DiffNet conv)
+    slope = 1.8e-8 if variant == "pair" and K * Cin <= 256 else 6e-9
+    assert err < 1e-5 + slope * K * Cin, err
 
 
 @pytest.mark.parametrize("variant", ["stream", "stream_tma", "pair", "pair_co"])

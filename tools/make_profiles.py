@@ -52,8 +52,9 @@ def main(tag):
             name = r[hdr.index("Kernel Name")]
             rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
             b = float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]]
-            key = ("pair_dilated_gate" if "<5, 16, 2>" in name or "ILi5ELi16ELi2" in name else
-                   "pair_dual_1x1" if "pair" in name else "aa_snake")
+            # tools/prof_umma.py launches the dilated+gate conv first, then the dual 1x1 projection
+            key = ("aa_snake" if "aa_snake" in name else
+                   "pair_dilated_gate" if "pair_dilated_gate" not in traffic else "pair_dual_1x1")
             traffic.setdefault(key, {"dram_bytes_per_launch": b, "duration_us": float(r[hdr.index("gpu__time_duration.sum")]),
                                      "kernel": name[:90]})
     if traffic:
