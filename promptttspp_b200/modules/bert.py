@@ -83,8 +83,11 @@ class NativeBert(nn.Module):
         self.pooler = _Pooler(hidden_size)
         self._packed, self._sig = None, None
 
+    def weights_signature(self):
+        return tuple((k, v.data_ptr(), v._version, str(v.device)) for k, v in self.state_dict(keep_vars=True).items())
+
     def _pack(self, device):
-        sig = tuple((k, v.data_ptr(), v._version, str(v.device)) for k, v in self.state_dict(keep_vars=True).items())
+        sig = self.weights_signature()
         if self._packed is not None and sig == self._sig:
             return self._packed
         f = lambda t: t.detach().float().to(device).contiguous()

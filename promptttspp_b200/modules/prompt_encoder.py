@@ -37,10 +37,20 @@ class BertWrapper(nn.Module):
     def forward(self, prompts, device) -> torch.Tensor:
         if isinstance(prompts, (tuple, list)) and len(prompts) == 2 and isinstance(prompts[0], torch.Tensor):
             ids, mask = prompts
-        else:
-            enc = self._tokenizer()(list(prompts), padding=True, return_tensors="pt")
-            ids, mask = enc["input_ids"], enc["attention_mask"]
-        return self.model(ids.to(device), mask.to(device))[:, 0, :]
+            return self.model(ids.to(device), mask.to(device))[:, 0, :]
+        # strings: the CLS vector depends only on the string (padding is masked), so serving the same style prompts
+        # again costs a dictionary lookup; the cache dies with the packed weights it was computed from
+        prompts = list(prompts)
+        sig = self.model.weights_signature()
+        if getattr(self, "_cache_sig", None) != sig or len(self._cache) > 4096:
+            self._cache, self._cache_sig = {}, sig
+        todo = [p for p in dict.fromkeys(prompts) if p not in self._cache]
+        if todo:
+            enc = self._tokenizer()(todo, padding=True, return_tensors="pt")
+            cls = self.model(enc["input_ids"].to(device), enc["attention_mask"].to(device))[:, 0, :]
+            for p, v in zip(todo, cls):
+                self._cache[p] = v
+        return torch.stack([self._cache[p].to(device) for p in prompts])
 
 
 class FixedPromptEmbedding(nn.Module):
@@ -72,6 +82,10 @@ class PromptEncoder(nn.Module):
         )
 
     def sentence_embedding(self, prompts, device) -> torch.Tensor:
+        """[B, in_channels] sentence embeddings of `prompts`: a list of strings (BERT), a pair of token tensors, or an
+        already computed float tensor [B, in_channels] (e.g. cached CLS vectors of recurring prompts), passed through."""
+        if isinstance(prompts, torch.Tensor) and prompts.is_floating_point():
+            return prompts.to(device=device, dtype=torch.float32)
         if isinstance(prompts, str):
             prompts = [prompts]
         return self.bert(prompts, device)
