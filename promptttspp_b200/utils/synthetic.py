@@ -159,6 +159,12 @@ def synthetic_state_dict(module, seed=1234, frames_per_phoneme=8.0):
             v = out[k[:-1] + "v"]
             norm = v.flatten(1).norm(dim=1).view(sd[k].shape)
             out[k] = norm * uniform(tuple(sd[k].shape), 0.8, 1.2)
+    # BigVGAN: the residual stages grow the activations to a standard deviation of ~30 in front of conv_post; with a
+    # unit-gain head the final tanh saturates (|wav| > 0.99 on 92 % of the samples) and squashes every upstream error,
+    # which would make the waveform parity bar meaningless.  A head gain of 0.012 gives a speech-like output
+    # (pre-tanh standard deviation ~0.3), so errors anywhere in the stack reach the waveform linearly.
+    if "conv_post.weight_g" in out:
+        out["conv_post.weight_g"] = out["conv_post.weight_g"] * 0.012
     # observable denoiser head (zero-initialised upstream) and a speech-like duration head
     k = "decoder.denoise_fn.output_projection.weight"
     if k in out:

@@ -26,8 +26,8 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 REF = Path("/root/reference")
 
-from golden_cases import (ACOUSTIC_CASES, AA_CASES, VOCODER_CASES, acoustic_inputs, golden_noise,  # noqa: E402
-                          vocoder_inputs)
+from golden_cases import (ACOUSTIC_CASES, ACOUSTIC_LARGE_CASES, AA_CASES, TEXT_CASES, VOCODER_CASES,  # noqa: E402
+                          VOCODER_LARGE_CASES, acoustic_inputs, golden_noise, vocoder_inputs)
 
 from promptttspp_b200.utils.synthetic import build_acoustic, build_vocoder, synthetic_state_dict  # noqa: E402
 
@@ -100,8 +100,48 @@ def injected_noise(z_style, x_T_fn, z_fn):
         torch.randn_like, torch.randn, dmod.noise_like = orig_randn_like, orig_randn, orig_noise_like
 
 
-def make_acoustic(ns):
-    for name, case in ACOUSTIC_CASES.items():
+class _StopAfterDurations(Exception):
+    pass
+
+
+def make_text(ns):
+    """cfg2's text side through the reference up to the duration predictor (the rest of infer_batch is skipped by
+    raising from the hooked predictor): log-durations and the integer durations of >= 3 k phonemes."""
+    for name, case in TEXT_CASES.items():
+        print("text", name)
+        model = build_acoustic(rel_pos_type=case["rel_pos_type"], ns=ns, K_step=case["K_step"]).eval()
+        sd = synthetic_state_dict(build_acoustic(rel_pos_type=case["rel_pos_type"], bert=_FixedBert(),
+                                                 K_step=case["K_step"]),
+                                  seed=case["weight_seed"], frames_per_phoneme=case["frames_per_phoneme"])
+        model.load_state_dict(sd, strict=True)
+        phoneme, lengths, cls_emb = acoustic_inputs(case)
+        _FixedBert.table = cls_emb
+        B = phoneme.shape[0]
+        inter = {}
+        va = model.variance_adaptor
+        orig_dur = va.duration_predictor.infer
+
+        def hooked(x, m):
+            inter["log_d"] = orig_dur(x, m)
+            raise _StopAfterDurations()
+
+        va.duration_predictor.infer = hooked
+        z_style = golden_noise(case, B, None).z_style
+        try:
+            with injected_noise(z_style, None, None):
+                model.infer_batch(phoneme, lengths, style_prompt=["p"] * B, use_max=True,
+                                  noise_scale=case["noise_scale"], return_f0=True)
+        except _StopAfterDurations:
+            pass
+        log_d = inter["log_d"]
+        dur = log_d.exp().round().clamp_min(1).long().squeeze(1)
+        dur = dur * (torch.arange(phoneme.shape[1])[None] < lengths[:, None]).long()
+        print("   phonemes", int(lengths.sum()), "frames", dur.sum(1).tolist())
+        np.savez_compressed(OUT / f"text_{name}.npz", log_d=log_d.numpy(), duration=dur.numpy())
+
+
+def make_acoustic(ns, cases=None, store_cond=True):
+    for name, case in (cases or ACOUSTIC_CASES).items():
         print("acoustic", name, case)
         model = build_acoustic(rel_pos_type=case["rel_pos_type"], ns=ns, K_step=case["K_step"]).eval()
         sd = synthetic_state_dict(build_acoustic(rel_pos_type=case["rel_pos_type"], bert=_FixedBert(),
@@ -142,18 +182,19 @@ def make_acoustic(ns):
         if case["api"] != "infer":
             dur = dur * (torch.arange(phoneme.shape[1])[None] < lengths[:, None]).long()
         print("   Ty", mel.shape[-1], "frame_lengths", frame_lengths.tolist(), "mel absmax", float(mel.abs().max()))
+        extra = dict(cond=inter["cond"].numpy()) if store_cond else {}
         np.savez_compressed(
             OUT / f"acoustic_{name}.npz",
             mel=mel.numpy(), log_cf0=log_cf0.numpy(), vuv=vuv.numpy(), frame_lengths=frame_lengths.numpy(),
-            log_d=log_d.numpy(), duration=dur.numpy(), cond=inter["cond"].numpy(),
+            log_d=log_d.numpy(), duration=dur.numpy(), **extra,
         )
 
 
-def make_vocoder():
+def make_vocoder(cases=None):
     sys.path.insert(0, str(REF))
     import promptttspp.vocoders as ref_voc
 
-    for name, case in VOCODER_CASES.items():
+    for name, case in (cases or VOCODER_CASES).items():
         print("vocoder", name, case)
         voc = build_vocoder(ns=ref_voc).eval()
         sd = synthetic_state_dict(build_vocoder(), seed=case["weight_seed"])
@@ -392,4 +433,11 @@ if __name__ == "__main__":
         make_bert()
     if "acoustic" in which:
         make_acoustic(reference_namespace())
+    # benchmark-scale cases (minutes of CPU time): only on request
+    if "vocoder_large" in which:
+        make_vocoder(VOCODER_LARGE_CASES)
+    if "text" in which:
+        make_text(reference_namespace())
+    if "acoustic_large" in which:
+        make_acoustic(reference_namespace(), ACOUSTIC_LARGE_CASES, store_cond=False)
     print("done")

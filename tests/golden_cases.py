@@ -21,9 +21,28 @@ ACOUSTIC_CASES = {
                          frames_per_phoneme=3.0, input_seed=0, noise_seed=100, noise_scale=0.5, K_step=100),
 }
 
+# Benchmark-scale cases: large enough that the kernels bench.py runs are the kernels under test --
+# >= 9.5 k padded frames selects the cta_group::2 DiffNet kernels at cfg2's shape class (100 steps, legacy rel-pos).
+ACOUSTIC_LARGE_CASES = {
+    "legacy_b8_bench": dict(api="infer_batch", rel_pos_type="legacy", lengths=[131, 160, 97, 152, 118, 143, 104, 126],
+                            weight_seed=1234, frames_per_phoneme=8.0, input_seed=21, noise_seed=121, noise_scale=1.0,
+                            K_step=100),
+}
+# cfg2's text side exactly (B=16, Tx in [128, 256], one row at 256): >= 3 k phonemes whose integer durations must be
+# bit-exact; the reference runs only up to the duration predictor
+TEXT_CASES = {
+    "cfg2_text": dict(api="infer_batch", rel_pos_type="legacy", weight_seed=1234, frames_per_phoneme=8.0, input_seed=2,
+                      noise_seed=122, noise_scale=1.0, K_step=100,
+                      lengths=[256, 203, 141, 187, 250, 129, 233, 176, 198, 160, 221, 149, 244, 135, 212, 169]),
+}
+
 VOCODER_CASES = {
     "b2_t12": dict(weight_seed=4321, input_seed=3, B=2, T=12, remove_weight_norm=True),
     "b1_t33": dict(weight_seed=4321, input_seed=4, B=1, T=33),
+}
+# cfg3's per-utterance shape (1024 frames -> 245 760 samples): the reference's own output at the benchmarked length
+VOCODER_LARGE_CASES = {
+    "b1_t1024": dict(weight_seed=4321, input_seed=3, B=1, T=1024),
 }
 
 # F0-aware vocoder (conf/vocoder/bigvgan_f0.yaml): mel + frame-level f0 with unvoiced stretches + injected source noise

@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 import torch
 
-from golden_cases import ACOUSTIC_CASES, VOCODER_CASES, acoustic_inputs, golden_noise, vocoder_inputs
+from golden_cases import (ACOUSTIC_CASES, ACOUSTIC_LARGE_CASES, TEXT_CASES, VOCODER_CASES, VOCODER_LARGE_CASES,
+                          acoustic_inputs, golden_noise, vocoder_inputs)
 from oracle import oracle
 from promptttspp_b200.modules.prompt_encoder import FixedPromptEmbedding
 from promptttspp_b200.utils.synthetic import build_acoustic, build_vocoder, synthetic_state_dict
@@ -27,9 +28,10 @@ def vocoder():
     return voc.cuda().eval()
 
 
-@pytest.mark.parametrize("name", list(VOCODER_CASES))
+@pytest.mark.parametrize("name", list(VOCODER_CASES) + list(VOCODER_LARGE_CASES))
 def test_bigvgan_matches_reference_golden(golden_dir, vocoder, name):
-    case = VOCODER_CASES[name]
+    """incl. b1_t1024: the reference's own output at cfg3's per-utterance length (245 760 samples)"""
+    case = {**VOCODER_CASES, **VOCODER_LARGE_CASES}[name]
     ref = torch.from_numpy(np.load(golden_dir / f"vocoder_{name}.npz")["wav"])
     wav = vocoder(vocoder_inputs(case).cuda()).cpu()
     assert wav.shape == ref.shape
@@ -81,9 +83,51 @@ def test_bigvgan_batch_invariance_full_size(vocoder):
         assert torch.equal(single, wav[b:b + 1])
 
 
-@pytest.mark.parametrize("name", list(ACOUSTIC_CASES))
+def test_bigvgan_cfg3_batch_row_matches_reference_golden(golden_dir, vocoder):
+    """The golden utterance inside a cfg3-sized batch (16 x 1024 frames): the kernels bench.py runs at cfg3 are the ones
+    compared with the reference here (kernel selection depends on the problem size)."""
+    case = VOCODER_LARGE_CASES["b1_t1024"]
+    ref = torch.from_numpy(np.load(golden_dir / "vocoder_b1_t1024.npz")["wav"])
+    g = torch.Generator().manual_seed(3)
+    mel = (torch.randn(16, 80, 1024, generator=g) * 2 - 5).clamp(-11.5, 2)
+    mel[5] = vocoder_inputs(case)[0]
+    wav = vocoder(mel.cuda())[5:6].cpu()
+    err = _rms(wav, ref)
+    print(f"bigvgan cfg3 batch row: rms err {err:.3e}, max-abs {float((wav - ref).abs().max()):.3e}")
+    assert err < WAV_TOL
+
+
+def test_text_side_durations_bit_exact_cfg2(golden_dir):
+    """cfg2's text side, 3063 phonemes: integer durations bit-exact against the reference (VERDICT r1 #1c)."""
+    case = TEXT_CASES["cfg2_text"]
+    gold = {k: torch.from_numpy(v) for k, v in np.load(golden_dir / "text_cfg2_text.npz").items()}
+    phoneme, lengths, cls_emb = acoustic_inputs(case)
+    model = build_acoustic(rel_pos_type=case["rel_pos_type"], bert=FixedPromptEmbedding(cls_emb), K_step=1)
+    model.load_state_dict(synthetic_state_dict(model, seed=case["weight_seed"],
+                                               frames_per_phoneme=case["frames_per_phoneme"]), strict=True)
+    model = model.cuda().eval()
+    B = phoneme.shape[0]
+    z_style = golden_noise(case, B, None).z_style
+    from promptttspp_b200.models.prompttts_mdn_v2_final.model import InferNoise
+
+    torch.manual_seed(0)
+    _, flen = model.infer_batch(phoneme.cuda(), lengths.cuda(), style_prompt=["p"] * B, use_max=True,
+                                noise_scale=case["noise_scale"], noise=InferNoise(z_style, None, None))
+    ndiff = int((model.last_durations.cpu() != gold["duration"]).sum())
+    lerr = float((model.last_log_durations.cpu() - gold["log_d"].squeeze(1)).abs().max())
+    print(f"cfg2 text side: {int(lengths.sum())} phonemes, durations differing {ndiff}, log_d max err {lerr:.3e}")
+    assert ndiff == 0 and lerr < 1e-4
+    assert torch.equal(flen.cpu().long(), gold["duration"].sum(1))
+
+
+_ACOUSTIC_ALL = {**ACOUSTIC_CASES, **ACOUSTIC_LARGE_CASES}
+
+
+@pytest.mark.parametrize("name", list(_ACOUSTIC_ALL))
 def test_acoustic_matches_reference_golden(golden_dir, name):
-    case = ACOUSTIC_CASES[name]
+    """incl. legacy_b8_bench: 8 x 1.3 k frames = the problem-size class of cfg2 (all 148 SMs busy, the CTA-pair DiffNet
+    kernels bench.py runs), 100 steps, against the REFERENCE's own output"""
+    case = _ACOUSTIC_ALL[name]
     gold = {k: torch.from_numpy(v) for k, v in np.load(golden_dir / f"acoustic_{name}.npz").items()}
     phoneme, lengths, cls_emb = acoustic_inputs(case)
     model = build_acoustic(rel_pos_type=case["rel_pos_type"], bert=FixedPromptEmbedding(cls_emb),
@@ -107,10 +151,13 @@ def test_acoustic_matches_reference_golden(golden_dir, name):
           f"{float((model.last_log_durations.cpu() - gold['log_d'].squeeze(1)).abs().max()):.3e}")
     assert ndiff == 0, "integer durations must be bit-exact"
     assert torch.equal(flen.cpu(), gold["frame_lengths"])
-    assert torch.allclose(log_cf0.cpu(), gold["log_cf0"], atol=1e-3)
-    assert torch.allclose(vuv.cpu(), gold["vuv"], atol=1e-3)
+    e_f0 = float((log_cf0.cpu() - gold["log_cf0"]).abs().max())
+    e_vuv = float((vuv.cpu() - gold["vuv"]).abs().max())
     err = float((mel.cpu() - gold["mel"]).abs().max())
-    print(f"{name}: mel max-abs err {err:.3e}")
+    rms = _rms(mel.cpu(), gold["mel"])
+    print(f"{name}: mel max-abs err {err:.3e} (rms {rms:.3e}), log_cf0 {e_f0:.3e}, vuv {e_vuv:.3e}; "
+          f"{int(flen.sum())} valid frames")
+    assert e_f0 < 3e-4 and e_vuv < 3e-4
     assert err < MEL_TOL
 
 
