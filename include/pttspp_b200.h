@@ -233,6 +233,47 @@ int pttspp_bert_embed(const int64_t* ids, int B, int T, const float* word_emb, i
 int pttspp_mha_masked(const float* qkv, const int64_t* key_mask, int B, int T, int heads, int dk, float* out,
                       pttspp_stream_t stream);
 
+/* Fused DiffNet residual-layer stack on tcgen05 (one persistent cta_group::2 kernel per launch, layers chained inside the
+ * kernel by completion flags).  Per layer l, on split-fp16 operand planes y = h + step_emb[l]:
+ *     g|f = dilated_conv_l(y) + bias_d + cond_l;  z = sigmoid(g) * tanh(f);  r|s = W_o z + bias_o;
+ *     y' = (h + r) / sqrt(2) + step_emb[l+1];  skip += s
+ * z stays in tensor memory (operand of the second contraction), h only travels as the planes.
+ * Replaces promptttspp/modules/denoiser.py:69-83 (ResidualBlock.forward) for residual_channels = 256, kernel 3,
+ * dilation <= 8.  All pointers are device pointers, 32-byte aligned.
+ *   wd_hi/wd_lo: [3][512][256] halves, gate/filter rows interleaved (pttspp_pack_conv_weight_split, interleave_halves=1);
+ *   wo_hi/wo_lo: [512][256] halves (residual rows, then skip rows); scale_* = the packers' scale_inv;
+ *   bias_d: [512] in the interleaved order, bias_o: [512]. */
+typedef struct {
+  const void* wd_hi;
+  const void* wd_lo;
+  const void* wo_hi;
+  const void* wo_lo;
+  const float* bias_d;
+  const float* bias_o;
+  float scale_d, scale_o;
+  int32_t dil;
+} pttspp_diffnet_layer;
+typedef struct {
+  int32_t B, T;                 /* utterances, frames per utterance (all rows are live: no masks, diffusion.py:199) */
+  int32_t layer_begin, layer_end; /* layers [begin, end) of the stack run by this launch */
+  const float* cond;            /* [layers][B][T][512] conditioner projections incl. bias, gate/filter interleaved */
+  const float* step_emb;        /* [layers + 1][256]: diffusion-step embedding per layer (row `layers` is never read
+                                   by the last layer, which has no residual output) */
+  void* y_hi[2];                /* ping-pong planes [B][T][256] halves: layer l reads y[l & 1], writes y[(l + 1) & 1] */
+  void* y_lo[2];
+  float* skip;                  /* [B][T][256] running skip sum (layer 0 overwrites) */
+  void* skip_hi;                /* optional: the last layer writes the skip sum as operand planes instead of `skip` */
+  void* skip_lo;
+  uint32_t* done;               /* pttspp_diffnet_flags_bytes() bytes, zeroed by the caller before epoch 1 */
+  uint32_t epoch;               /* 1, 2, ...: one more per launch over the same `done` array */
+  float* dbg_z;                 /* tests: [B][T][256] gate output z of the last layer run, or NULL */
+} pttspp_diffnet_run_desc;
+typedef struct pttspp_diffnet pttspp_diffnet_t;
+int pttspp_diffnet_create(const pttspp_diffnet_layer* layers, int n_layers, pttspp_diffnet_t** out);
+void pttspp_diffnet_destroy(pttspp_diffnet_t* h);
+size_t pttspp_diffnet_flags_bytes(const pttspp_diffnet_t* h, int B, int T);
+int pttspp_diffnet_run(pttspp_diffnet_t* h, const pttspp_diffnet_run_desc* r, pttspp_stream_t stream);
+
 /* Relative-position multi-head self-attention (Transformer-XL style), both ESPnet variants.
  *   scores = ((q+u) k^T + rel_shift((q+v) p^T)) / sqrt(d_k); masked softmax; . v
  * q,k,v,out: [B][T][H*d_k]; p: [Tp][H*d_k] with Tp = T (legacy) or 2T-1 (new);

@@ -79,6 +79,27 @@ class AcousticConfig(C.Structure):
     ]
 
 
+class DiffNetLayer(C.Structure):
+    """pttspp_diffnet_layer"""
+
+    _fields_ = [
+        ("wd_hi", C.c_void_p), ("wd_lo", C.c_void_p), ("wo_hi", C.c_void_p), ("wo_lo", C.c_void_p),
+        ("bias_d", C.c_void_p), ("bias_o", C.c_void_p), ("scale_d", C.c_float), ("scale_o", C.c_float),
+        ("dil", C.c_int32),
+    ]
+
+
+class DiffNetRunDesc(C.Structure):
+    """pttspp_diffnet_run_desc"""
+
+    _fields_ = [
+        ("B", C.c_int32), ("T", C.c_int32), ("layer_begin", C.c_int32), ("layer_end", C.c_int32),
+        ("cond", C.c_void_p), ("step_emb", C.c_void_p), ("y_hi", C.c_void_p * 2), ("y_lo", C.c_void_p * 2),
+        ("skip", C.c_void_p), ("skip_hi", C.c_void_p), ("skip_lo", C.c_void_p), ("done", C.c_void_p),
+        ("epoch", C.c_uint32), ("dbg_z", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol declared in include/pttspp_b200.h
 SIGNATURES = {
     "pttspp_last_error": (C.c_char_p, []),
@@ -105,6 +126,10 @@ SIGNATURES = {
                                            C.c_void_p]),
     "pttspp_length_regulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
+    "pttspp_diffnet_create": (C.c_int, [C.POINTER(DiffNetLayer), C.c_int, C.POINTER(C.c_void_p)]),
+    "pttspp_diffnet_destroy": (None, [C.c_void_p]),
+    "pttspp_diffnet_flags_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "pttspp_diffnet_run": (C.c_int, [C.c_void_p, C.POINTER(DiffNetRunDesc), C.c_void_p]),
     "pttspp_relpos_attention": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pttspp_iir_filtfilt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                       C.c_void_p]),

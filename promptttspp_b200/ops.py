@@ -219,3 +219,64 @@ def conv1d_umma_dual_cl(x_planes, w_split, cout1, kw1, kw2):
     d2, o2, p2, keep2 = conv1d_umma_cl(x_planes, (wh2, wl2, sc), cout2, _desc_only=True, **kw2)
     _abi.check(_abi.lib().pttspp_conv1d_dual_cl(C.byref(d1), C.byref(d2), _abi.stream_ptr(x_planes[0].device)))
     return (o1, p1), (o2, p2)
+
+
+class DiffNetStack:
+    """Fused DiffNet residual-layer stack (pttspp_diffnet_*; denoiser.py:69-83 for 256 channels, kernel 3, dilation <= 8).
+
+    layers: list of dicts with `dilated` [512, 256, 3], `dilated_bias` [512], `outp` [512, 256(, 1)], `outp_bias` [512]
+    (torch layouts, reference channel order) and `dil`.  Packing (gate/filter interleave, split-fp16 planes) happens here.
+    """
+
+    def __init__(self, layers, device):
+        self.device = torch.device(device)
+        self._keep = []
+        arr = (_abi.DiffNetLayer * len(layers))()
+        for i, l in enumerate(layers):
+            wdh, wdl, sd = pack_conv_weight_split(l["dilated"], interleave_halves=True, device=self.device)
+            woh, wol, so = pack_conv_weight_split(l["outp"], device=self.device)
+            bd = l["dilated_bias"].detach().float().cpu()
+            half = bd.numel() // 2
+            bdi = torch.stack([bd[:half], bd[half:]], dim=1).reshape(-1).contiguous().to(self.device)
+            bo = l["outp_bias"].detach().float().contiguous().to(self.device)
+            self._keep += [wdh, wdl, woh, wol, bdi, bo]
+            arr[i].wd_hi, arr[i].wd_lo, arr[i].wo_hi, arr[i].wo_lo = (t.data_ptr() for t in (wdh, wdl, woh, wol))
+            arr[i].bias_d, arr[i].bias_o = bdi.data_ptr(), bo.data_ptr()
+            arr[i].scale_d, arr[i].scale_o, arr[i].dil = sd, so, int(l["dil"])
+        self.n_layers = len(layers)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _abi.check(_abi.lib().pttspp_diffnet_create(arr, len(layers), C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _abi.lib().pttspp_diffnet_destroy(self.h)
+            self.h = None
+
+    def new_flags(self, B, T):
+        n = _abi.lib().pttspp_diffnet_flags_bytes(self.h, B, T)
+        return torch.zeros(n // 4, dtype=torch.int32, device=self.device)
+
+    @staticmethod
+    def interleave_cond(cond):
+        """[..., 512] reference order (gate half | filter half) -> the kernel's interleaved column order."""
+        half = cond.shape[-1] // 2
+        return torch.stack([cond[..., :half], cond[..., half:]], dim=-1).reshape(cond.shape).contiguous()
+
+    def run(self, cond, step_emb, y, skip, done, epoch, layer_begin=0, layer_end=None, skip_planes=None, dbg_z=None):
+        """cond [L, B, T, 512] (interleaved), step_emb [L + 1, 256], y = ((hi0, lo0), (hi1, lo1)) planes [B, T, 256]."""
+        (h0, l0), (h1, l1) = y
+        B, T, _ = h0.shape
+        r = _abi.DiffNetRunDesc()
+        r.B, r.T = B, T
+        r.layer_begin, r.layer_end = layer_begin, self.n_layers if layer_end is None else layer_end
+        r.cond, r.step_emb = cond.data_ptr(), step_emb.data_ptr()
+        r.y_hi[0], r.y_lo[0], r.y_hi[1], r.y_lo[1] = h0.data_ptr(), l0.data_ptr(), h1.data_ptr(), l1.data_ptr()
+        r.skip = skip.data_ptr()
+        if skip_planes is not None:
+            r.skip_hi, r.skip_lo = skip_planes[0].data_ptr(), skip_planes[1].data_ptr()
+        r.done, r.epoch = done.data_ptr(), int(epoch)
+        r.dbg_z = None if dbg_z is None else dbg_z.data_ptr()
+        with torch.cuda.device(self.device):
+            _abi.check(_abi.lib().pttspp_diffnet_run(self.h, C.byref(r), _abi.stream_ptr(self.device)))

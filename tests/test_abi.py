@@ -44,14 +44,15 @@ def test_struct_sizes_match_header(libpath):
 
     from promptttspp_b200 import _abi
 
-    src = '#include <stdio.h>\n#include "pttspp_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n",' \
+    src = '#include <stdio.h>\n#include "pttspp_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",' \
           "sizeof(pttspp_conv1d_desc),sizeof(pttspp_layernorm_desc),sizeof(pttspp_bigvgan_config)," \
-          "sizeof(pttspp_acoustic_config));return 0;}\n"
+          "sizeof(pttspp_acoustic_config),sizeof(pttspp_diffnet_layer),sizeof(pttspp_diffnet_run_desc));return 0;}\n"
     with tempfile.TemporaryDirectory() as d:
         (Path(d) / "p.c").write_text(src)
         subprocess.check_call(["gcc", "-I", str(ROOT / "include"), str(Path(d) / "p.c"), "-o", str(Path(d) / "p")])
         sizes = [int(x) for x in subprocess.check_output([str(Path(d) / "p")]).split()]
-    mirrors = [_abi.Conv1dDesc, _abi.LayerNormDesc, _abi.BigVGANConfig, _abi.AcousticConfig]
+    mirrors = [_abi.Conv1dDesc, _abi.LayerNormDesc, _abi.BigVGANConfig, _abi.AcousticConfig, _abi.DiffNetLayer,
+               _abi.DiffNetRunDesc]
     assert sizes == [ctypes.sizeof(m) for m in mirrors]
 
 
