@@ -38,6 +38,10 @@ int pttspp_device_check(void);
 int64_t pttspp_launch_count(void);
 void pttspp_reset_launch_count(void);
 
+/* Developer knobs (PTTSPP_UMMA_* environment variables: kernel-variant selection for op tests and A/B measurements) are
+ * read once; this re-reads them. */
+void pttspp_debug_reload_env(void);
+
 /* Optional per-launch timing for bench.py's roofline leg (off by default, single-threaded use).
  * While enabled, every op-level call records a CUDA event pair on its stream and accounts its
  * ALGORITHMIC work; the report sums them per kernel family:

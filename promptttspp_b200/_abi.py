@@ -107,6 +107,7 @@ SIGNATURES = {
     "pttspp_device_check": (C.c_int, []),
     "pttspp_launch_count": (C.c_int64, []),
     "pttspp_reset_launch_count": (None, []),
+    "pttspp_debug_reload_env": (None, []),
     "pttspp_prof_enable": (None, [C.c_int]),
     "pttspp_prof_report": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "pttspp_conv1d_cl": (C.c_int, [C.POINTER(Conv1dDesc), C.c_void_p]),

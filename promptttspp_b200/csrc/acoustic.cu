@@ -9,6 +9,7 @@
 // concatenated conditioner projections of all residual layers (step-invariant, hoisted out of the
 // sampling loop), gate/filter channel interleaving.
 #include "common.h"
+#include "diffnet_layer.h"
 
 namespace pttspp {
 
@@ -76,6 +77,11 @@ struct pttspp_acoustic {
   std::vector<pttspp::DiffLayerW> diff;
   float* step_table = nullptr;  // [K_step][layers][C]
   bool use_umma = true;         // tcgen05 split-fp16 path for the DiffNet contractions (PTTSPP_DISABLE_UMMA=1: off)
+  // all residual layers of one diffusion step in ONE persistent kernel (csrc/diffnet_layer.cu); PTTSPP_DIFFNET_FUSED=0
+  // keeps the two-launches-per-layer path (the only one for other channel counts / kernel sizes)
+  pttspp::DiffNetStack diffnet;
+  bool use_fused = false;
+  bool h_fp32 = false;          // PTTSPP_H_FP32=1: fp32 copy of the residual stream (two-launch path, A/B measurements)
   std::vector<float> c_recip, c_recipm1, coef1, coef2, logvar;
 };
 
@@ -220,9 +226,11 @@ struct DecodeWs {
   float *xa, *xb, *tmp, *lcf0, *vuv, *condp, *xt, *h, *z, *skip, *s, *eps;
   uint16_t *yh, *yl, *zh, *zl, *sh, *sl, *ph, *pl;  // split-fp16 operand planes [B][Ty][DC]
   uint16_t *xh, *xl;                                // x_t planes [B][Ty][round_up(mel, 64)]
+  uint16_t *yh2, *yl2;                              // second pair of residual-stream planes (fused stack: ping-pong)
+  unsigned* done;                                   // fused stack: per (layer, unit) completion counters
 };
 
-DecodeWs carve_decode(const pttspp_acoustic_config& c, int B, int Ty, Carver& cv) {
+DecodeWs carve_decode(const pttspp_acoustic_config& c, int B, int Ty, Carver& cv, size_t flags_bytes = 0) {
   DecodeWs w;
   const int C = c.channels, DC = c.diff_channels;
   const int64_t n = (int64_t)B * Ty;
@@ -243,6 +251,8 @@ DecodeWs carve_decode(const pttspp_acoustic_config& c, int B, int Ty, Carver& cv
   w.sh = cv.take<uint16_t>(n * DC); w.sl = cv.take<uint16_t>(n * DC);
   w.ph = cv.take<uint16_t>(n * DC); w.pl = cv.take<uint16_t>(n * DC);
   w.xh = cv.take<uint16_t>(n * round_up(c.mel_dim, 64)); w.xl = cv.take<uint16_t>(n * round_up(c.mel_dim, 64));
+  w.yh2 = cv.take<uint16_t>(flags_bytes ? n * DC : 0); w.yl2 = cv.take<uint16_t>(flags_bytes ? n * DC : 0);
+  w.done = cv.take<unsigned>((int64_t)(flags_bytes / sizeof(unsigned)));
   return w;
 }
 
@@ -423,6 +433,20 @@ extern "C" int pttspp_acoustic_finalize(pttspp_acoustic_t* h, pttspp_stream_t) {
   {
     const char* e = getenv("PTTSPP_DISABLE_UMMA");
     h->use_umma = !(e && e[0] == '1') && DC % 64 == 0;
+    h->h_fp32 = getenv("PTTSPP_H_FP32") != nullptr;
+    const char* f = getenv("PTTSPP_DIFFNET_FUSED");
+    const int max_dil = 1 << (std::min(c.diff_dilation_cycle, c.diff_layers) - 1);
+    h->use_fused = h->use_umma && !(f && f[0] == '0') && !h->h_fp32 && h->in_proj_tc.w_hi != nullptr &&
+                   DiffNetStack::supported(DC, c.diff_kernel, max_dil);
+    if (h->use_fused) {
+      std::vector<DiffLayerHost> hl;
+      for (int l = 0; l < c.diff_layers; ++l) {
+        const DiffLayerW& w = h->diff[l];
+        hl.push_back(DiffLayerHost{w.dilated.w_hi, w.dilated.w_lo, w.outp.w_hi, w.outp.w_lo, w.dilated.bias, w.outp.bias,
+                                   w.dilated.w_scale_inv, w.outp.w_scale_inv, w.dilated.dil});
+      }
+      h->diffnet.set_layers(hl);
+    }
   }
   h->step_table = dev.upload(build_step_table(st, c));
   h->c_recip = st.get("decoder.sqrt_recip_alphas_cumprod", c.K_step).data;
@@ -608,7 +632,7 @@ extern "C" size_t pttspp_acoustic_decode_workspace_bytes(const pttspp_acoustic_t
   (void)Tx;
   if (!h || B <= 0 || Ty <= 0) return 0;
   Carver cv(nullptr);
-  carve_decode(h->cfg, B, Ty, cv);
+  carve_decode(h->cfg, B, Ty, cv, h->use_fused ? h->diffnet.flags_bytes(B, Ty) : 0);
   return cv.off + 512;
 }
 
@@ -626,7 +650,9 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
   cudaStream_t s = (cudaStream_t)stream;
   const auto& c = h->cfg;
   Carver cv((void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255));
-  DecodeWs w = carve_decode(c, B, Ty, cv);
+  const bool fused = h->use_fused;
+  const size_t flags_bytes = fused ? h->diffnet.flags_bytes(B, Ty) : 0;
+  DecodeWs w = carve_decode(c, B, Ty, cv, flags_bytes);
   const int C = c.channels, DC = c.diff_channels, M = c.mel_dim;
   const int64_t* flen = frame_len;
   const int64_t bsC = (int64_t)Ty * C;
@@ -695,7 +721,20 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
   // ---- DDPM ancestral sampling (diffusion.py:320-356) ----
   // conditioner projections of all residual layers: step-invariant, computed once
   const int CP = 2 * DC * c.diff_layers;
-  {
+  if (fused) {
+    // layer-major layout [layer][B][Ty][2*DC]: the fused kernel reads one contiguous 2 KB row per (layer, frame)
+    split_f16_rows(cond, B, Ty, C, nullptr, w.yh, w.yl, s);
+    for (int l = 0; l < c.diff_layers; ++l) {
+      auto d = conv_desc(h->cond_all, cond, B, Ty, w.condp + (size_t)l * B * Ty * 2 * DC);
+      d.Cout = 2 * DC; d.out_ld = 2 * DC; d.out_bs = (int64_t)Ty * 2 * DC;
+      d.bias = h->cond_all.bias + (size_t)l * 2 * DC;
+      tc_in(d, w.yh, w.yl, h->cond_all);
+      d.w_hi = (const uint16_t*)h->cond_all.w_hi + (size_t)l * 2 * DC * C;
+      d.w_lo = (const uint16_t*)h->cond_all.w_lo + (size_t)l * 2 * DC * C;
+      conv1d_cl(d, s);
+    }
+    PT_CUDA(cudaMemsetAsync(w.done, 0, flags_bytes, s));
+  } else {
     auto d = conv_desc(h->cond_all, cond, B, Ty, w.condp);
     if (h->use_umma && h->cond_all.w_hi) {
       split_f16_rows(cond, B, Ty, C, nullptr, w.yh, w.yl, s);
@@ -712,7 +751,7 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
   const int64_t bsD = (int64_t)Ty * DC;
   const bool um = h->use_umma;
   // PTTSPP_H_FP32=1 keeps an fp32 copy of the residual stream (the pre-planes behaviour, for A/B measurements)
-  const bool h_planes = um && tc_inproj && DC % 16 == 0 && getenv("PTTSPP_H_FP32") == nullptr;
+  const bool h_planes = um && tc_inproj && DC % 16 == 0 && !h->h_fp32;
   auto planes_in = [&](pttspp_conv1d_desc& q, const uint16_t* hi, const uint16_t* lo, const PackedConv& pc, int row_off) {
     q.in_hi = hi; q.in_lo = lo; q.in_bs = bsD; q.in_ld = DC;
     q.w_hi = (const uint16_t*)pc.w_hi + (size_t)row_off * pc.Cin;
@@ -735,7 +774,19 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
       }
       conv1d_cl(d, s);
     }
-    for (int l = 0; l < c.diff_layers; ++l) {
+    if (fused) {
+      DiffNetRun r;
+      r.B = B; r.T = Ty; r.layer_begin = 0; r.layer_end = c.diff_layers;
+      r.cond = w.condp; r.step_emb = step_emb;
+      r.y_hi[0] = w.yh; r.y_lo[0] = w.yl; r.y_hi[1] = w.yh2; r.y_lo[1] = w.yl2;
+      r.skip = w.skip; r.skip_hi = w.sh; r.skip_lo = w.sl;
+      r.done = w.done; r.epoch = (unsigned)(c.K_step - step); r.dbg_z = nullptr;
+      const double flops = 2.0 * B * (double)Ty * c.diff_layers * (3.0 * DC * 2 * DC + (double)DC * 2 * DC) -
+                           2.0 * B * (double)Ty * DC * DC;  // the last layer has no residual half
+      ProfScope prof(PROF_CONV_UMMA, s, flops, 0.0);
+      h->diffnet.run(r, s);
+    }
+    for (int l = 0; l < (fused ? 0 : c.diff_layers); ++l) {
       const DiffLayerW& lw = h->diff[l];
       const bool last = (l + 1 == c.diff_layers);
       // z = sigmoid(gate) * tanh(filter) of dilated_conv(h + step_emb) + cond_proj  (denoiser.py:69-77)

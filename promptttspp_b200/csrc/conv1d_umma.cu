@@ -19,6 +19,9 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "common.h"
 #include "conv_epilogue.cuh"
 #include "umma_ptx.cuh"
@@ -1388,9 +1391,70 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Developer knobs (kernel-variant selection for the op tests and A/B measurements) are read from the environment ONCE
+// and cached; pttspp_debug_reload_env() re-reads them (tests that switch variants inside one process call it).
+struct UmmaEnv {
+  char pair = 0, rl = 0, nacc = 0, epi = 0;  // first character of the variable, 0 when unset
+  bool no_tma_store = false, debug = false, no_wres64 = false, a_stationary = false;
+  int order = 0;
+  void load() {
+    auto first = [](const char* name) -> char { const char* e = getenv(name); return e ? e[0] : (char)0; };
+    pair = first("PTTSPP_UMMA_PAIR");
+    rl = first("PTTSPP_UMMA_RL");
+    nacc = first("PTTSPP_UMMA_NACC");
+    epi = first("PTTSPP_UMMA_EPI");
+    no_tma_store = getenv("PTTSPP_UMMA_NO_TMA_STORE") != nullptr;
+    debug = getenv("PTTSPP_UMMA_DEBUG") != nullptr;
+    no_wres64 = getenv("PTTSPP_UMMA_NO_WRES64") != nullptr;
+    a_stationary = getenv("PTTSPP_UMMA_AS") != nullptr;
+    const char* oe = getenv("PTTSPP_UMMA_ORDER");  // experiments: bits 0-1 MMA order, 4 no operand loads, 8 no stores, 16 no L2 prefetch
+    order = oe ? atoi(oe) : 0;
+  }
+};
+std::mutex g_env_mutex;
+UmmaEnv& umma_env_storage() {
+  static UmmaEnv e = [] { UmmaEnv x; x.load(); return x; }();
+  return e;
+}
+UmmaEnv umma_env() {
+  std::lock_guard<std::mutex> lk(g_env_mutex);
+  return umma_env_storage();
+}
+
+// cuTensorMapEncodeTiled costs microseconds and the same (pointer, geometry) recurs on every step of the sampling loop
+// and every call with a stable workspace: encoded maps are cached (bounded; cleared when full).
+struct MapKey {
+  const void* ptr;
+  uint64_t dims[3], strides[2];
+  uint32_t box[3];
+  int rank, dtype, swz;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return (size_t)h;
+  }
+};
+static_assert(sizeof(MapKey) % 8 == 0, "MapKey is hashed as 64-bit words");
+
 CUtensorMap make_map(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
                      CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                      CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.rank = rank; key.dtype = (int)dtype; key.swz = (int)swz;
+  for (int i = 0; i < rank; ++i) key.dims[i] = dims[i], key.box[i] = box[i];
+  for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_bytes[i];
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+  }
   EncodeTiledFn fn = encode_fn();
   PT_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   CUtensorMap m;
@@ -1403,7 +1467,43 @@ CUtensorMap make_map(const void* ptr, int rank, const uint64_t* dims, const uint
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PT_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d (rank %d, dims %llu x %llu)", (int)r, rank,
            (unsigned long long)dims[0], (unsigned long long)dims[1]);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() >= 8192) cache.clear();
+    cache.emplace(key, m);
+  }
   return m;
+}
+
+// Per-device launch state: the multiprocessor count, and which kernels have opted in to 227 KB of dynamic shared memory
+// on that device (cudaFuncSetAttribute is per device; a process may drive several GPUs from several threads).
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+  int num_sms = 0;
+  std::unordered_map<const void*, int> kernel_setup;  // kernel -> resident clusters (pair kernels) or 1
+};
+std::mutex g_dev_mutex;
+DeviceState g_dev[kMaxDevices];
+int current_device() {
+  int dev = 0;
+  PT_CUDA(cudaGetDevice(&dev));
+  PT_CHECK(dev >= 0 && dev < kMaxDevices, "device ordinal %d out of range", dev);
+  return dev;
+}
+int device_num_sms() {
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lk(g_dev_mutex);
+  if (g_dev[dev].num_sms == 0) PT_CUDA(cudaDeviceGetAttribute(&g_dev[dev].num_sms, cudaDevAttrMultiProcessorCount, dev));
+  return g_dev[dev].num_sms;
+}
+// opt the kernel in to `smem` bytes of dynamic shared memory once per device
+void ensure_smem_optin(const void* kern, int smem) {
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lk(g_dev_mutex);
+  auto& m = g_dev[dev].kernel_setup;
+  if (m.find(kern) != m.end()) return;
+  PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  m.emplace(kern, 1);
 }
 
 constexpr int UM_BN = 128;
@@ -1415,7 +1515,7 @@ bool tma_out_ok(const pttspp_conv1d_desc& d) {
   if (d.out_mul != 1 || d.out_off != 0 || d.m_begin != 0 || d.M != d.T_out) return false;
   if (d.out && (d.out_ld % 4 != 0 || d.out_bs % 4 != 0)) return false;
   if (d.out_hi && (d.out_plane_ld % 8 != 0 || d.out_plane_bs % 8 != 0)) return false;
-  return getenv("PTTSPP_UMMA_NO_TMA_STORE") == nullptr;
+  return !umma_env().no_tma_store;
 }
 
 OutMaps make_out_maps(const pttspp_conv1d_desc& d) {
@@ -1502,23 +1602,27 @@ int pair_clusters(const void* kern, size_t smem, int threads) {
 // one-time setup per kernel instantiation: opt in to 227 KB of dynamic shared memory, query resident clusters
 template <int NBST, int EW, int NACC>
 int pair_kernel_setup(int num_sms, bool debug) {
-  static int max_clusters = -1;
-  if (max_clusters < 0) {
-    auto kern = conv1d_umma_pair_kernel<NBST, EW, NACC>;
-    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    int n = pair_clusters((const void*)kern, 227 * 1024, (EW + 2) * 32);
-    if (debug) fprintf(stderr, "[pttspp] pair kernel<%d>: cudaOccupancyMaxActiveClusters -> %d\n", NBST, n);
-    max_clusters = (n > 0) ? std::min(n, num_sms / 2) : num_sms / 2;
-  }
+  auto kern = conv1d_umma_pair_kernel<NBST, EW, NACC>;
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lk(g_dev_mutex);
+  auto& m = g_dev[dev].kernel_setup;
+  auto it = m.find((const void*)kern);
+  if (it != m.end()) return it->second;
+  PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  int n = pair_clusters((const void*)kern, 227 * 1024, (EW + 2) * 32);
+  if (debug) fprintf(stderr, "[pttspp] pair kernel<%d>: cudaOccupancyMaxActiveClusters -> %d\n", NBST, n);
+  const int max_clusters = (n > 0) ? std::min(n, num_sms / 2) : num_sms / 2;
+  m.emplace((const void*)kern, max_clusters);
   return max_clusters;
 }
 
 // Pair kernel launch; returns false when the shape does not qualify (caller falls back to the streaming kernel).
 bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool dual, int cout1, int total_cout,
                              cudaStream_t s, int num_sms) {
-  const char* env = getenv("PTTSPP_UMMA_PAIR");
+  const UmmaEnv ev = umma_env();
+  const char env_pair = ev.pair;
   const bool needs_pair = d.res_hi != nullptr || (dual && d2.res_hi != nullptr);  // only this kernel's epilogue reads it
-  if (env && env[0] == '0' && !needs_pair) return false;
+  if (env_pair == '0' && !needs_pair) return false;
   if (!epilogue_co_ok(d) || (dual && !epilogue_co_ok(d2))) return false;
   if (total_cout % UP_BN != 0 || d.Cin % UM_BK != 0 || d.Cin / UM_BK > UP_MAX_SLAB) return false;
   if (d.K * d.Cin / 16 > 64) return false;  // long contractions keep the multi-accumulator streaming kernel
@@ -1532,8 +1636,7 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
   const size_t a_bytes = (size_t)nslab * 2 * rowsA * 128;
   const int ew = 16;  // epilogue warps (8 measured slower: tools/bench_conv.py history in profiles/)
   // row-per-lane 256-bit epilogue (no staging tile) whenever the alignment allows it; PTTSPP_UMMA_RL=0: coalescing one
-  const char* rle = getenv("PTTSPP_UMMA_RL");
-  const bool epi_rl = epilogue_rl_ok(d) && (!dual || epilogue_rl_ok(d2)) && (needs_pair || !(rle && rle[0] == '0'));
+  const bool epi_rl = epilogue_rl_ok(d) && (!dual || epilogue_rl_ok(d2)) && (needs_pair || ev.rl != '0');
   PT_CHECK(!needs_pair || epi_rl, "conv1d: a residual from operand planes needs 32-byte aligned tensors (row-per-lane epilogue)");
   const size_t fixed = a_bytes + (epi_rl ? 0 : (size_t)ew * 2048) + (2 * UP_MAX_SLAB + 2 * 6 + 8) * 8 + 16 + 1024;
   const size_t cap = 227 * 1024;
@@ -1545,7 +1648,7 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
   if (n_tiles >= (1ll << 30)) return false;
   // worth it only when every pair gets at least a couple of tiles (the activation block is loaded per unit)
   // and when the activation block is reused by at least two N tiles (otherwise the streaming kernel is faster)
-  if (!(env && env[0] == '2') && !needs_pair && (n_tiles < num_sms || n_nt < 2)) return false;
+  if (env_pair != '2' && !needs_pair && (n_tiles < num_sms || n_nt < 2)) return false;
 
   const uint64_t wdims[2] = {(uint64_t)d.Cin, (uint64_t)d.K * total_cout};
   const uint64_t wstr[1] = {(uint64_t)d.Cin * 2};
@@ -1559,13 +1662,12 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
   const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox);
   const size_t smem = fixed + (size_t)nbst * UP_BST_BYTES;
 
-  const bool debug = getenv("PTTSPP_UMMA_DEBUG") != nullptr;
+  const bool debug = ev.debug;
   auto launch = [&](auto kern, int max_clusters) {
     const int n_clusters = (int)std::min<long long>(n_tiles, std::min(max_clusters, num_sms / 2));
     int cout_first = dual ? cout1 : total_cout, cout_all = total_cout, a_n_mt2 = n_mt, a_n_nt = n_nt, a_tiles = (int)n_tiles,
         a_rowsA = rowsA;
-    const char* oe = getenv("PTTSPP_UMMA_ORDER");  // experiments: bits 0-1 MMA order, 4 no operand loads, 8 no stores, 16 no L2 prefetch
-    int a_order = oe ? atoi(oe) : 0, a_rl = epi_rl ? 1 : 0;
+    int a_order = ev.order, a_rl = epi_rl ? 1 : 0;
     void* args[] = {(void*)&mAh, (void*)&mAl, (void*)&mBh, (void*)&mBl, (void*)&d, (void*)&d2, &cout_first, &cout_all,
                     &a_n_mt2, &a_n_nt, &a_tiles, &a_rowsA, &a_order, &a_rl};
     if (debug)
@@ -1576,13 +1678,13 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
     ++g_launch_count;
   };
   // short contractions: one accumulator per tile, four tile buffers (see the kernel)
-  const char* nae = getenv("PTTSPP_UMMA_NACC");
+  const char nae = ev.nacc;
   // K*Cin <= 768 (144 accumulations): measured at cfg2 scale, the one-accumulator mode changes the mel by 1.9e-5 max-abs
   // (bar 1e-3) and takes 4.6 % off the step (tools/nacc_experiment.py); PTTSPP_UMMA_NACC=2 forces two accumulators
   // Only the gated (DiffNet) conv takes the extended range: BigVGAN's plain convs must stay bit-identical between the
   // pair and the streaming kernel (an utterance synthesised alone equals the same utterance inside a batch).
   const int one_acc_limit = (d.act == PTTSPP_ACT_GATE) ? 768 : 256;
-  const bool one_acc = ((d.K * d.Cin <= one_acc_limit) && !(nae && nae[0] == '2')) || (nae && nae[0] == '1');
+  const bool one_acc = ((d.K * d.Cin <= one_acc_limit) && nae != '2') || nae == '1';
 #define PT_PAIR_CASE(N, E, A) launch(conv1d_umma_pair_kernel<N, E, A>, pair_kernel_setup<N, E, A>(num_sms, debug))
 #define PT_PAIR_SWITCH(E, A)               \
   switch (nbst) {                          \
@@ -1601,7 +1703,7 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
 // weight-resident kernel: 32 channels with up to 11 taps, 64 channels with up to 7 (weights + >= 2 halo stages fit)
 bool conv1d_umma_c32_ok(const pttspp_conv1d_desc& d) {
   if (!((d.Cin == 32 && d.Cout == 32 && d.K <= US_MAXK) || (d.Cin == 64 && d.Cout == 64 && d.K <= 7))) return false;
-  if (d.Cin == 64 && getenv("PTTSPP_UMMA_NO_WRES64")) return false;
+  if (d.Cin == 64 && umma_env().no_wres64) return false;
   return d.K >= 1 && d.in_hi && d.in_lo && d.w_hi && d.w_lo && d.in_stride == 1 && !d.in_len && !d.in_add &&
          d.in_ld % 8 == 0 && d.in_bs % 8 == 0 && aligned16(d.in_hi) && aligned16(d.in_lo) && aligned16(d.w_hi) &&
          aligned16(d.w_lo) && d.w_scale_inv > 0.f && UM_BM + round_up((d.K - 1) * d.dil, 8) <= 256 && epilogue_rl_ok(d);
@@ -1612,11 +1714,7 @@ void conv1d_umma_wres_launch_t(const pttspp_conv1d_desc& d, const CUtensorMap& m
                                const CUtensorMap& mBh, const CUtensorMap& mBl, int rowsA, size_t smem, int num_sms,
                                cudaStream_t s) {
   auto kern = conv1d_umma_c32_kernel<C, NST>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  ensure_smem_optin((const void*)kern, 227 * 1024);
   const int n_mt = ceil_div(d.M, UM_BM);
   const long long n_tiles = (long long)n_mt * d.B;
   PT_CHECK(n_tiles < (1ll << 30), "conv1d: too many tiles");
@@ -1628,12 +1726,7 @@ void conv1d_umma_wres_launch_t(const pttspp_conv1d_desc& d, const CUtensorMap& m
 void conv1d_umma_c32_launch(const pttspp_conv1d_desc& d_in, cudaStream_t s) {
   pttspp_conv1d_desc d = d_in;
   d.acc_scale = d_in.acc_scale * d_in.w_scale_inv;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    PT_CUDA(cudaGetDevice(&dev));
-    PT_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int num_sms = device_num_sms();
   const int C = d.Cin;
   const int rowb = C * 2;
   const CUtensorMapSwizzle swz = (C == 32) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
@@ -1700,12 +1793,7 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
     vec = vec && conv_epilogue_vec_ok(d2);
     d.Cout = cout1 + d2.Cout;  // contraction-wide column count (TMA rows, tile count)
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    PT_CUDA(cudaGetDevice(&dev));
-    PT_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int num_sms = device_num_sms();
   const int total_cout = d.Cout;
   if (d2_in) d.Cout = cout1;  // the epilogue of the first half sees its own column count again
   if (conv1d_umma_pair_launch(d, d2, d2_in != nullptr, cout1, total_cout, s, num_sms)) return;
@@ -1733,7 +1821,7 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
   const long long n_units = (long long)n_mt * d.B;
   // The streaming kernel measured faster on every shape of this model (tools/bench_conv.py: the A-stationary kernel
   // is left with two weight stages in flight and becomes latency bound), so the latter is opt-in.
-  const bool a_stationary = getenv("PTTSPP_UMMA_AS") != nullptr;
+  const bool a_stationary = umma_env().a_stationary;
   if (a_stationary && rowsA <= 256 && a_bytes + 2 * bst <= cap && n_units * 2 >= num_sms) {
     const int nbst = (int)std::min<size_t>(6, (cap - a_bytes) / bst);
     const uint32_t abox[3] = {UM_BK, (uint32_t)rowsA, 1};
@@ -1741,11 +1829,7 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
     const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox);
     const size_t smem = a_bytes + nbst * bst + 512 + 1024;
     auto kern = conv1d_umma_as_kernel<UM_BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
-      PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set = true;
-    }
+    ensure_smem_optin((const void*)kern, 227 * 1024);
     const int grid = (int)std::min<long long>(n_units, num_sms);
     kern<<<grid, UM_THREADS, smem, s>>>(mAh, mAl, mBh, mBl, d, d2, d2_in ? cout1 : total_cout, total_cout, vec ? 1 : 0,
                                         n_mt, n_nt, (int)n_units, rowsA, nbst);
@@ -1764,8 +1848,7 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
   memset(&om2, 0, sizeof(om2));
   // streaming kernel: the TMA bulk-store epilogue measured ~7 % faster than the coalescing one on the BigVGAN shapes
   // (tools/bench_conv.py); PTTSPP_UMMA_EPI=co selects the latter
-  const char* epi_env = getenv("PTTSPP_UMMA_EPI");
-  const bool want_co = epi_env && epi_env[0] == 'c';
+  const bool want_co = umma_env().epi == 'c';
   const bool tma_possible = vec && tma_out_ok(e1) && (!d2_in || tma_out_ok(e2));
   if ((want_co || !tma_possible) && epilogue_co_ok(e1) && (!d2_in || epilogue_co_ok(e2))) {
     tma_out = 4;  // coalescing epilogue
@@ -1789,12 +1872,7 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
     const CUtensorMap mBl64 = make_map(d.w_lo, 2, wdims, wstr, wbox64);
     const size_t smem = (size_t)ST * UmmaSmem<BN>::STAGE_BYTES + 256 + UM_EPI_WARPS * 2048 + 1024;
     auto kern = (tma_out & 4) ? conv1d_umma_kernel<BN, ST, NA, 1, false> : conv1d_umma_kernel<BN, ST, NA, 0, false>;
-    static bool attr_set = false;
-    if (!attr_set) {
-      PT_CUDA(cudaFuncSetAttribute(conv1d_umma_kernel<BN, ST, NA, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      PT_CUDA(cudaFuncSetAttribute(conv1d_umma_kernel<BN, ST, NA, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
+    ensure_smem_optin((const void*)kern, (int)smem);
     const int nnt = ceil_div(total_cout, BN);
     const long long n_tiles = (long long)n_mt * nnt * d.B;
     PT_CHECK(n_tiles < (1ll << 30), "conv1d: too many tiles");
@@ -1810,14 +1888,7 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
                                      : conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC, 0, true>)
                     : ((tma_out & 4) ? conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC, 1, false>
                                      : conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC, 0, false>);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PT_CUDA(cudaFuncSetAttribute(conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PT_CUDA(cudaFuncSetAttribute(conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PT_CUDA(cudaFuncSetAttribute(conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PT_CUDA(cudaFuncSetAttribute(conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  ensure_smem_optin((const void*)kern, (int)smem);
   const long long n_tiles = (long long)n_mt * n_nt * d.B;
   PT_CHECK(n_tiles < (1ll << 30), "conv1d: too many tiles");
   const int grid = (int)std::min<long long>(n_tiles, num_sms);
@@ -1854,6 +1925,11 @@ void umma_probe(const void* a_half /*[rows][64]*/, int rows, const void* b_half 
 }
 
 }  // namespace pttspp
+
+extern "C" void pttspp_debug_reload_env(void) {
+  std::lock_guard<std::mutex> lk(pttspp::g_env_mutex);
+  pttspp::umma_env_storage().load();
+}
 
 extern "C" int pttspp_umma_probe(const void* a_half, int rows, const void* b_half, int row_off, int mode, float* out,
                                  pttspp_stream_t stream) {

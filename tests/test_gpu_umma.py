@@ -84,11 +84,23 @@ VARIANTS = {
 }
 
 
+@pytest.fixture(autouse=True)
+def _clean_knobs():
+    """set up before (and torn down after) monkeypatch: the library's cached knobs follow the restored environment"""
+    yield
+    from promptttspp_b200 import _abi
+
+    _abi.lib().pttspp_debug_reload_env()
+
+
 def _select(monkeypatch, variant):
+    from promptttspp_b200 import _abi
+
     for k in ("PTTSPP_UMMA_PAIR", "PTTSPP_UMMA_EPI", "PTTSPP_UMMA_AS", "PTTSPP_UMMA_RL", "PTTSPP_UMMA_NACC"):
         monkeypatch.delenv(k, raising=False)
     for k, v in VARIANTS[variant].items():
         monkeypatch.setenv(k, v)
+    _abi.lib().pttspp_debug_reload_env()  # the knobs are cached by the library
 
 
 @pytest.mark.parametrize("variant", list(VARIANTS))

@@ -7,7 +7,7 @@ from pathlib import Path
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
-from promptttspp_b200 import ops  # noqa: E402
+from promptttspp_b200 import _abi, ops  # noqa: E402
 
 torch.set_grad_enabled(False)
 
@@ -68,11 +68,13 @@ def main():
             for k in KEYS:
                 os.environ.pop(k, None)
             os.environ.update(env)
+            _abi.lib().pttspp_debug_reload_env()
             ms = timeit(fn)
             rows.append((name, ms, fl / ms / 1e9))
             print(f"{tag:8s} {name:58s} {ms*1e3:9.1f} us   {fl / ms / 1e9:8.1f} TFLOP/s (algorithmic)", flush=True)
         for k in KEYS:
             os.environ.pop(k, None)
+        _abi.lib().pttspp_debug_reload_env()
 
     for dil in (1, 8):
         add(f"umma dilated k3 d{dil} 256->512 plain fp32 out", fl1,
