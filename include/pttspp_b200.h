@@ -271,6 +271,7 @@ typedef struct {
   uint32_t* done;               /* pttspp_diffnet_flags_bytes() bytes, zeroed by the caller before epoch 1 */
   uint32_t epoch;               /* 1, 2, ...: one more per launch over the same `done` array */
   float* dbg_z;                 /* tests: [B][T][256] gate output z of the last layer run, or NULL */
+  uint64_t* dbg_prof;           /* profiling: [74][16] cycle counters of the kernel's barrier waits, or NULL */
 } pttspp_diffnet_run_desc;
 typedef struct pttspp_diffnet pttspp_diffnet_t;
 int pttspp_diffnet_create(const pttspp_diffnet_layer* layers, int n_layers, pttspp_diffnet_t** out);

@@ -96,7 +96,7 @@ class DiffNetRunDesc(C.Structure):
         ("B", C.c_int32), ("T", C.c_int32), ("layer_begin", C.c_int32), ("layer_end", C.c_int32),
         ("cond", C.c_void_p), ("step_emb", C.c_void_p), ("y_hi", C.c_void_p * 2), ("y_lo", C.c_void_p * 2),
         ("skip", C.c_void_p), ("skip_hi", C.c_void_p), ("skip_lo", C.c_void_p), ("done", C.c_void_p),
-        ("epoch", C.c_uint32), ("dbg_z", C.c_void_p),
+        ("epoch", C.c_uint32), ("dbg_z", C.c_void_p), ("dbg_prof", C.c_void_p),
     ]
 
 

@@ -79,6 +79,13 @@ __device__ __forceinline__ f8 ldcg256(const void* p) {
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ f8 ldna256(const void* p) {
+  f8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -103,6 +110,17 @@ __device__ __forceinline__ void wait_prev_layer(const unsigned* done_prev, int u
 }
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+// barrier wait that accounts its duration (profiling runs only)
+__device__ __forceinline__ void mbar_wait_warp_t(uint32_t bar, uint32_t parity, unsigned long long* ctr) {
+  if (ctr) {
+    const long long t0 = clock64();
+    mbar_wait_warp(bar, parity);
+    if ((threadIdx.x & 31) == 0) *ctr += (unsigned long long)(clock64() - t0);
+  } else {
+    mbar_wait_warp(bar, parity);
+  }
 }
 
 struct TaskGeom {
@@ -181,22 +199,25 @@ diffnet_layers_kernel(const __grid_constant__ CUtensorMap mapY0h, const __grid_c
     // ================= TMA producer (both CTAs: own activation rows, own half of every weight tile) =================
     uint32_t g = 0;
     int ablk = 0;
+    unsigned long long* pc = (a.dbg_prof && rank == 0) ? a.dbg_prof + (size_t)cluster_id * 16 : nullptr;
     for (int t = cluster_id; t < n_tasks; t += n_clusters, ++ablk) {
       const TaskGeom tg = task_geom(a, t, rank);
       const DiffLayerConst* L = a.layers + tg.layer;
       const int dil = L->dil;
       const int row0 = tg.mt * 128 - dil;
       if (tg.layer > a.layer_begin) {
+        const long long tw = pc ? clock64() : 0;
         wait_prev_layer(a.done + (size_t)(tg.layer - 1) * a.n_units, tg.unit, a.n_units, a.done_target, lane);
+        if (pc && lane == 0) pc[10] += (unsigned long long)(clock64() - tw);
         asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other SMs -> this warp's TMA reads
       }
       const CUtensorMap* mYh = (tg.layer & 1) ? &mapY1h : &mapY0h;
       const CUtensorMap* mYl = (tg.layer & 1) ? &mapY1l : &mapY0l;
-      const int n_o_begin = (tg.layer == last_layer) ? 2 : 0;  // the last layer's residual half has no consumer
+      const int n_o_begin = (a.dbg_flags & 4) ? 4 : ((tg.layer == last_layer) ? 2 : 0);  // the last layer's residual half has no consumer
       for (int nt = 0; nt < 4; ++nt)
         for (int slab = 0; slab < DL_NSLAB; ++slab) {
           if (nt == 0) {
-            mbar_wait_warp(emptyA(slab), ((uint32_t)ablk & 1u) ^ 1u);
+            mbar_wait_warp_t(emptyA(slab), ((uint32_t)ablk & 1u) ^ 1u, pc ? pc + 8 : nullptr);
             if (elect_one()) {
               if (rank == 0) mbar_expect_tx(fullA(slab), 4u * DL_A_PLANE);
               tma_load_3d_pair(base + (uint32_t)(2 * slab) * DL_A_PLANE, mYh, fullA(slab), slab * 64, row0, tg.b);
@@ -206,7 +227,7 @@ diffnet_layers_kernel(const __grid_constant__ CUtensorMap mapY0h, const __grid_c
           }
           for (int tap = 0; tap < DL_TAPS; ++tap, ++g) {
             const int st = g % DL_NB;
-            mbar_wait_warp(emptyB(st), ((g / DL_NB) & 1u) ^ 1u);
+            mbar_wait_warp_t(emptyB(st), ((g / DL_NB) & 1u) ^ 1u, pc ? pc + 9 : nullptr);
             const uint32_t dst = ring + (uint32_t)st * DL_BST;
             const int wrow = tap * (2 * DL_C) + nt * 128 + (int)rank * 64;
             if (elect_one()) {
@@ -238,25 +259,28 @@ diffnet_layers_kernel(const __grid_constant__ CUtensorMap mapY0h, const __grid_c
       const uint64_t desc0 = umma_desc_k_sw128(base);  // descriptors differ only in the start-address field
       uint32_t g = 0;
       int i = 0, ablk = 0;
+      unsigned long long* pc = a.dbg_prof ? a.dbg_prof + (size_t)cluster_id * 16 : nullptr;
+      const long long t_start = pc ? clock64() : 0;
       for (int t = cluster_id; t < n_tasks; t += n_clusters, ++ablk) {
         const int layer = a.layer_begin + t / a.n_units;
         const int dil = a.layers[layer].dil;
-        const int n_o_begin = (layer == last_layer) ? 2 : 0;
+        const int n_o_begin = (a.dbg_flags & 4) ? 4 : ((layer == last_layer) ? 2 : 0);
+        const bool one_mma = (a.dbg_flags & 2) != 0;
         // ---- dilated conv: tiles D0..D3 (operands from shared memory) ----
         for (int nt = 0; nt < 4; ++nt, ++i) {
           const int u = i & 1;
-          mbar_wait_warp(tempty_bar(u), (((uint32_t)i >> 1) & 1u) ^ 1u);  // both CTAs have drained accumulator buffer u
+          mbar_wait_warp_t(tempty_bar(u), (((uint32_t)i >> 1) & 1u) ^ 1u, pc ? pc + 0 : nullptr);  // both CTAs have drained accumulator buffer u
           tc_fence_after();
           const uint32_t acc = tmem_base + (uint32_t)(u * 128);
           uint32_t first = 0;
           for (int slab = 0; slab < DL_NSLAB; ++slab) {
             if (nt == 0) {
-              mbar_wait_warp(fullA(slab), (uint32_t)ablk & 1u);
+              mbar_wait_warp_t(fullA(slab), (uint32_t)ablk & 1u, pc ? pc + 2 : nullptr);
               tc_fence_after();
             }
             for (int tap = 0; tap < DL_TAPS; ++tap, ++g) {
               const int st = g % DL_NB;
-              mbar_wait_warp(fullB(st), (g / DL_NB) & 1u);
+              mbar_wait_warp_t(fullB(st), (g / DL_NB) & 1u, pc ? pc + 3 : nullptr);
               tc_fence_after();
               const uint32_t a_off = (uint32_t)(2 * slab) * DL_A_PLANE + (uint32_t)(tap * dil) * 128u;  // taps share the halo tile
               const uint64_t dAh = desc0 + (uint64_t)(a_off >> 4);
@@ -268,6 +292,7 @@ diffnet_layers_kernel(const __grid_constant__ CUtensorMap mapY0h, const __grid_c
                 for (int kk = 0; kk < 4; ++kk) {
                   const uint64_t adv = (uint64_t)(kk * 2);  // 16 halves = 32 bytes inside the swizzle span
                   umma_f16_pair(acc, dAl + adv, dBh + adv, idesc, kk ? 1u : first);
+                  if (one_mma) continue;
                   umma_f16_pair(acc, dAh + adv, dBl + adv, idesc, 1u);
                   umma_f16_pair(acc, dAh + adv, dBh + adv, idesc, 1u);
                 }
@@ -283,16 +308,16 @@ diffnet_layers_kernel(const __grid_constant__ CUtensorMap mapY0h, const __grid_c
         // ---- 1x1 output projection: tiles R0, R1, S0, S1 (A operand = z planes in tensor memory) ----
         for (int nt = n_o_begin; nt < 4; ++nt, ++i) {
           const int u = i & 1;
-          mbar_wait_warp(tempty_bar(u), (((uint32_t)i >> 1) & 1u) ^ 1u);
+          mbar_wait_warp_t(tempty_bar(u), (((uint32_t)i >> 1) & 1u) ^ 1u, pc ? pc + 1 : nullptr);
           tc_fence_after();
           const uint32_t acc = tmem_base + (uint32_t)(u * 128);
           for (int slab = 0; slab < DL_NSLAB; ++slab, ++g) {
             if (nt == n_o_begin) {
-              mbar_wait_warp(zfull(slab), (uint32_t)ablk & 1u);  // z slab `slab` of both CTAs is in tensor memory
+              mbar_wait_warp_t(zfull(slab), (uint32_t)ablk & 1u, pc ? pc + 5 : nullptr);  // z slab `slab` of both CTAs is in tensor memory
               tc_fence_after();
             }
             const int st = g % DL_NB;
-            mbar_wait_warp(fullB(st), (g / DL_NB) & 1u);
+            mbar_wait_warp_t(fullB(st), (g / DL_NB) & 1u, pc ? pc + 4 : nullptr);
             tc_fence_after();
             const uint64_t dBh = desc0 + (uint64_t)((DL_A_BYTES + (uint32_t)st * DL_BST) >> 4);
             const uint64_t dBl = dBh + (uint64_t)(DL_BHALF >> 4);
@@ -302,6 +327,7 @@ diffnet_layers_kernel(const __grid_constant__ CUtensorMap mapY0h, const __grid_c
               for (int kk = 0; kk < 4; ++kk) {
                 const uint64_t adv = (uint64_t)(kk * 2);
                 umma_f16_pair_ts(acc, zl + (uint32_t)(kk * 8), dBh + adv, idesc, (slab | kk) ? 1u : 0u);
+                if (one_mma) continue;
                 umma_f16_pair_ts(acc, zh + (uint32_t)(kk * 8), dBl + adv, idesc, 1u);
                 umma_f16_pair_ts(acc, zh + (uint32_t)(kk * 8), dBh + adv, idesc, 1u);
               }
@@ -312,6 +338,7 @@ diffnet_layers_kernel(const __grid_constant__ CUtensorMap mapY0h, const __grid_c
           }
         }
       }
+      if (pc && lane == 0) pc[7] += (unsigned long long)(clock64() - t_start);
     }
   } else {
     // ================= epilogue: warps 0-15 of both CTAs, each CTA drains its own 128 TMEM lanes =================
@@ -319,6 +346,7 @@ diffnet_layers_kernel(const __grid_constant__ CUtensorMap mapY0h, const __grid_c
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const float inv_sqrt2 = 0.70710678118654752440f;
     int i = 0;
+    unsigned long long* pc = (a.dbg_prof && rank == 0 && warp == 0) ? a.dbg_prof + (size_t)cluster_id * 16 : nullptr;
     auto release_acc = [&](int u) {
       tc_fence_before();
       __syncwarp();
@@ -331,10 +359,10 @@ diffnet_layers_kernel(const __grid_constant__ CUtensorMap mapY0h, const __grid_c
       const TaskGeom tg = task_geom(a, t, rank);
       const DiffLayerConst* L = a.layers + tg.layer;
       const int row = tg.mt * 128 + q * 32 + lane;
-      const bool ok = tg.blk_ok && row < a.T;
+      const bool ok = tg.blk_ok && row < a.T && !(a.dbg_flags & 1);
       const int64_t rix = (int64_t)tg.b * a.T + row;  // flat row index of this lane
       const float scale_d = L->scale_d, scale_o = L->scale_o;
-      const int n_o_begin = (tg.layer == last_layer) ? 2 : 0;
+      const int n_o_begin = (a.dbg_flags & 4) ? 4 : ((tg.layer == last_layer) ? 2 : 0);
       // ---- D tiles: z = sigmoid(g) * tanh(f) of (acc + bias + cond), stored to tensor memory as operand planes ----
       const float* cond_row = a.cond + (int64_t)tg.layer * a.cond_layer_stride + rix * (2 * DL_C);
 #pragma unroll 1
@@ -344,13 +372,13 @@ diffnet_layers_kernel(const __grid_constant__ CUtensorMap mapY0h, const __grid_c
         f8 pre[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if (ok) pre[k] = ldg256(cond_row + col0 + 8 * k);
+          if (ok && !(a.dbg_flags & 8)) pre[k] = (a.dbg_flags & 64) ? ldna256(cond_row + col0 + 8 * k) : ldg256(cond_row + col0 + 8 * k);
           else {
 #pragma unroll
             for (int e = 0; e < 8; ++e) pre[k].v[e] = 0.f;
           }
         }
-        mbar_wait_warp(tfull_bar(u), ((uint32_t)i >> 1) & 1u);
+        mbar_wait_warp_t(tfull_bar(u), ((uint32_t)i >> 1) & 1u, pc ? pc + 11 : nullptr);
         tc_fence_after();
         uint32_t acc[2][16];
         tmem_ld16_nowait(lane_base + (uint32_t)(u * 128 + cg * 32), acc[0]);
@@ -375,7 +403,7 @@ diffnet_layers_kernel(const __grid_constant__ CUtensorMap mapY0h, const __grid_c
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster_release(zfull(nt), 0);
+        if (lane == 0) mbar_arrive_cluster(zfull(nt), 0);  // relaxed: tcgen05.wait::st + fence precede it (like tempty)
         if (a.dbg_z && ok) {
           float* dz = a.dbg_z + rix * DL_C + nt * 64 + cg * 16;
           stg256(dz, zf);
@@ -402,7 +430,7 @@ diffnet_layers_kernel(const __grid_constant__ CUtensorMap mapY0h, const __grid_c
 #pragma unroll
           for (int e = 0; e < 8; ++e) pre[k].v[e] = 0.f;
         }
-        if (ok) {
+        if (ok && !(a.dbg_flags & 16)) {
           if (is_res) {  // residual from the operand planes: 32 halves of each plane, raw bits
             pre[0] = ldcg256(yin_h + rix * DL_C + col0);
             pre[1] = ldcg256(yin_h + rix * DL_C + col0 + 16);
@@ -413,14 +441,14 @@ diffnet_layers_kernel(const __grid_constant__ CUtensorMap mapY0h, const __grid_c
             for (int k = 0; k < 4; ++k) pre[k] = ldcg256(a.skip + rix * DL_C + col0 + 8 * k);
           }
         }
-        mbar_wait_warp(tfull_bar(u), ((uint32_t)i >> 1) & 1u);
+        mbar_wait_warp_t(tfull_bar(u), ((uint32_t)i >> 1) & 1u, pc ? pc + 12 : nullptr);
         tc_fence_after();
         uint32_t acc[2][16];
         tmem_ld16_nowait(lane_base + (uint32_t)(u * 128 + cg * 32), acc[0]);
         tmem_ld16_nowait(lane_base + (uint32_t)(u * 128 + cg * 32 + 16), acc[1]);
         tmem_wait_ld();
         release_acc(u);
-        if (ok) {
+        if (ok && !(a.dbg_flags & 32)) {
           const float* bias = L->bias_o + (is_res ? 0 : DL_C) + col0;
           float v[32];
 #pragma unroll
@@ -626,6 +654,11 @@ void DiffNetStack::run(const DiffNetRun& r, cudaStream_t s) {
   a.done = r.done;
   a.done_target = r.epoch * (2u * DL_EW);
   a.dbg_z = r.dbg_z;
+  a.dbg_prof = r.dbg_prof;
+  {
+    static const int dbg = [] { const char* e = getenv("PTTSPP_DIFFNET_DBG"); return e ? atoi(e) : 0; }();
+    a.dbg_flags = dbg;
+  }
   const long long n_tasks = (long long)(r.layer_end - r.layer_begin) * a.n_units;
   PT_CHECK(n_tasks < (1ll << 30), "diffnet: too many tasks");
   // all clusters must be co-resident: a task may wait for a task of another cluster (flag protocol)
@@ -676,7 +709,7 @@ extern "C" int pttspp_diffnet_run(pttspp_diffnet_t* h, const pttspp_diffnet_run_
   q.cond = r->cond; q.step_emb = r->step_emb;
   for (int k = 0; k < 2; ++k) { q.y_hi[k] = r->y_hi[k]; q.y_lo[k] = r->y_lo[k]; }
   q.skip = r->skip; q.skip_hi = r->skip_hi; q.skip_lo = r->skip_lo;
-  q.done = r->done; q.epoch = r->epoch; q.dbg_z = r->dbg_z;
+  q.done = r->done; q.epoch = r->epoch; q.dbg_z = r->dbg_z; q.dbg_prof = (unsigned long long*)r->dbg_prof;
   const double rows = (double)r->B * r->T * (r->layer_end - r->layer_begin);
   pttspp::ProfScope prof(pttspp::PROF_CONV_UMMA, (cudaStream_t)stream, rows * 2.0 * (3 * 256 * 512 + 256 * 512), 0.0);
   h->stack.run(q, (cudaStream_t)stream);

@@ -32,6 +32,9 @@ struct DiffNetArgs {
   unsigned* done;         // [layers][units] completion counters
   unsigned done_target;
   float* dbg_z;           // tests: [B][T][256] gate output of the (single) layer run
+  unsigned long long* dbg_prof;  // optional [clusters][16] cycle counters of the barrier waits (tools/bench_diffnet.py)
+  int dbg_flags;          // timing experiments (PTTSPP_DIFFNET_DBG): 1 no epilogue global traffic, 2 one MMA per product,
+                          // 4 no output projection
 };
 
 struct DiffLayerHost {
@@ -53,6 +56,7 @@ struct DiffNetRun {
   unsigned* done;  // flags_bytes(); zeroed by the caller before epoch 1
   unsigned epoch;  // 1, 2, ...: incremented per launch over the same `done` array
   float* dbg_z;
+  unsigned long long* dbg_prof = nullptr;
 };
 
 struct DiffNetStack {

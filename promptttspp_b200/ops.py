@@ -264,7 +264,8 @@ class DiffNetStack:
         half = cond.shape[-1] // 2
         return torch.stack([cond[..., :half], cond[..., half:]], dim=-1).reshape(cond.shape).contiguous()
 
-    def run(self, cond, step_emb, y, skip, done, epoch, layer_begin=0, layer_end=None, skip_planes=None, dbg_z=None):
+    def run(self, cond, step_emb, y, skip, done, epoch, layer_begin=0, layer_end=None, skip_planes=None, dbg_z=None,
+            dbg_prof=None):
         """cond [L, B, T, 512] (interleaved), step_emb [L + 1, 256], y = ((hi0, lo0), (hi1, lo1)) planes [B, T, 256]."""
         (h0, l0), (h1, l1) = y
         B, T, _ = h0.shape
@@ -278,5 +279,6 @@ class DiffNetStack:
             r.skip_hi, r.skip_lo = skip_planes[0].data_ptr(), skip_planes[1].data_ptr()
         r.done, r.epoch = done.data_ptr(), int(epoch)
         r.dbg_z = None if dbg_z is None else dbg_z.data_ptr()
+        r.dbg_prof = None if dbg_prof is None else dbg_prof.data_ptr()
         with torch.cuda.device(self.device):
             _abi.check(_abi.lib().pttspp_diffnet_run(self.h, C.byref(r), _abi.stream_ptr(self.device)))
