@@ -8,7 +8,11 @@ valid mel frames per second.  The same JSON line carries the BigVGAN leg of the 
 16 x 1024-frame mel -> 24 kHz waveform, real-time factor) under "bigvgan".
 A "step" is one pass of the path over one batch.  N > 1 (torchrun, one rank per GPU): every rank runs its
 own batch (weak scaling, utterances are independent -- no data-path collective); time = max over ranks.
-`--impl reference` times the CPU oracle port of the reference (oracle/oracle.py) on the host cores.
+The line also carries BASELINE.json's other configs: "cfg1" (one 50-phoneme utterance: latency), "cfg4" (32 variable-length
+utterances, text ids -> waveform through serving.BatchedSynthesizer, plain and F0-aware vocoder) and "cfg5" (256
+utterances through dist.synthesize_sharded over the N ranks: strong scaling).
+`--impl reference` times the UNMODIFIED reference modules installed in baseline/_ref (baseline/reference_arm.py) on the
+host cores; the oracle port is only the fallback when that install is missing.
 """
 import argparse
 import ctypes
@@ -32,7 +36,8 @@ WORKLOAD = ("cfg2: prompttts_mdn_v2 acoustic model only, batch 16 synthetic phon
             "config), text->mel incl. 100-step diffusion")
 METRIC = "mel_frames_per_sec"
 UNIT = "frames/s"
-TAGS = ["conv1d_simt_fp32", "conv1d_tcgen05_splitfp16", "aa_snake", "layernorm", "relpos_attention", "other"]
+TAGS = ["conv1d_simt_fp32", "conv1d_tcgen05_splitfp16", "aa_snake", "layernorm", "relpos_attention", "other",
+        "diffnet_layers_tcgen05_splitfp16"]
 # algorithmic work per padded mel frame
 DIFFNET_FLOP_PER_FRAME = 2.643e9
 BIGVGAN_FLOP_PER_FRAME = 422.5e6
@@ -122,7 +127,7 @@ def build_models(device):
 
 
 def prof_report(lib):
-    n = 6
+    n = len(TAGS)
     ms, fl, by = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_double * n)()
     calls = (ctypes.c_int64 * n)()
     from promptttspp_b200 import _abi
@@ -134,6 +139,12 @@ def prof_report(lib):
 def ncu_traffic(kernel, rows):
     """DRAM bytes per launch of `kernel`'s family from the committed ncu --set full capture (profiles/), scaled from
     the capture's row count to this run's; None when no capture covers the family."""
+    p2 = ROOT / "profiles" / "r02_ncu_traffic.json"
+    if kernel == TAGS[6] and p2.exists() and rows:
+        t = json.loads(p2.read_text())["diffnet_layers_kernel"]
+        return t["dram_bytes_per_launch"] * rows / t["rows"], (
+            f"profiles/r02_ncu_traffic.json (ncu --set full capture of one diffnet_layers_kernel launch at {t['rows']} "
+            f"rows: dram__bytes_read.sum + dram__bytes_write.sum), scaled to {int(rows)} rows")
     p = ROOT / "profiles" / "r01_ncu_traffic.json"
     if not p.exists():
         return None, None
@@ -159,7 +170,7 @@ def roofline_from(report, pk, in_long_step, rows=None):
         return {"bound": "tensor", "kernel": top["kernel"], "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "launches": top["calls"],
                 "avg_launch_ms": top["ms"] / top["calls"], "share_of_step": top["ms"] / sum(r["ms"] for r in report),
-                "mma_frac": (3.0 * ach / peak) if top["kernel"] == TAGS[1] else None,
+                "mma_frac": (3.0 * ach / peak) if top["kernel"] in (TAGS[1], TAGS[6]) else None,
                 "peak_source": pk["source"] + (", bf16 dense sustained" if in_long_step else ", bf16 dense burst"),
                 "note": ("fp32 CUDA-core FFMA path; the tensor peak is the contract's denominator"
                          if top["kernel"] == TAGS[0] else
@@ -177,70 +188,160 @@ def roofline_from(report, pk, in_long_step, rows=None):
 # ---------------------------------------------------------------------------------------------
 
 def cpu_acoustic_sample(steps, warmup):
-    """Bounded sample of cfg2: B=2, Tx<=32 (cost is linear in padded frames x 100 steps)."""
-    from oracle import oracle
-    from promptttspp_b200.modules.prompt_encoder import FixedPromptEmbedding
-    from promptttspp_b200.utils.synthetic import build_acoustic, synthetic_state_dict
+    from baseline import reference_arm
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    model = build_acoustic(bert=FixedPromptEmbedding(torch.zeros(1, 768)))
-    sd = synthetic_state_dict(model, seed=1234)
-    phoneme, lengths, cls_emb = cfg2_inputs(seed=2, B=2, lo=24, hi=33)
-    g = torch.Generator().manual_seed(7)
-    z_style = torch.randn(2, 1, 256, generator=g)
-    cfg = dict(oracle.ACOUSTIC_CFG)
-    times, frames = [], 0
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        mel, _, _, flen = oracle.acoustic_infer_batch(sd, cfg, phoneme, lengths, cls_emb, z_style,
-                                                      noise_fn=lambda s: torch.randn(s))
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-        frames = float(flen.sum())
-        padded = mel.shape[0] * mel.shape[-1]
-    t = statistics.median(times)
-    return dict(value=frames / t, unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                sample=f"oracle/oracle.py acoustic_infer_batch, B=2 Tx<=32 -> {int(frames)} valid / {padded} padded "
-                       f"frames, 100 diffusion steps, median of {len(times)} ({t:.2f} s each)"), t
+    return reference_arm.acoustic_sample(steps, warmup)
 
 
 def cpu_bigvgan_sample(steps, warmup):
-    from oracle import oracle
-    from promptttspp_b200.utils.synthetic import build_vocoder, synthetic_state_dict
+    from baseline import reference_arm
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    sd = synthetic_state_dict(build_vocoder(), seed=4321)
-    mel = cfg3_inputs(B=2, T=256)
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        oracle.bigvgan_forward(sd, oracle.VOCODER_CFG, mel)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    t = statistics.median(times)
-    audio_s = mel.shape[0] * mel.shape[-1] / 100.0
-    return dict(rtf=t / audio_s, frames_per_sec=mel.shape[0] * mel.shape[-1] / t, cores=torch.get_num_threads(),
-                kind="port", sample=f"oracle/oracle.py bigvgan_forward, B=2 x 256 frames ({audio_s:.2f} s audio), "
-                                    f"median of {len(times)} ({t:.2f} s each)")
+    return reference_arm.bigvgan_sample(steps, warmup)
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    base, t = cpu_acoustic_sample(args.steps, args.warmup)
+    from baseline import reference_arm
+
+    # each step is a bounded sample (>= 2 k padded frames, ~10 s of CPU work): at most 1 warm-up + 4 timed repetitions
+    # so that the arm ends within a few minutes whatever --steps / --warmup the native arm was given
+    steps, warmup = max(1, min(args.steps, 4)), max(1, min(args.warmup, 1))
+    base, t = reference_arm.acoustic_sample(steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "K_step": 100, "sample": base["sample"]},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "bigvgan": cpu_bigvgan_sample(max(1, min(args.steps, 3)), 1),
+        "bigvgan": reference_arm.bigvgan_sample(3, 1),
+        "cfg1": reference_arm.cfg1_sample(3, 1),
     }
     print(json.dumps(line))
 
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json's other configs (reported inside the headline line)
+# ---------------------------------------------------------------------------------------------
+
+def var_len_requests(n, seed, lo=32, hi=257):
+    """n synthetic requests: phoneme id sequences of length [lo, hi) + sentence embeddings (host tensors)."""
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(lo, hi, (n,), generator=g).tolist()
+    return [torch.randint(3, 90, (k,), generator=g) for k in lens], torch.randn(n, 768, generator=g)
+
+
+def _event_time(fn, device):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(device)
+    e0.record()
+    out = fn()
+    e1.record()
+    torch.cuda.synchronize(device)
+    return e0.elapsed_time(e1), out
+
+
+def leg_cfg1(model, device, reps=7):
+    """configs[0]: ONE utterance of 50 phonemes through `infer` (the app.py:56-82 call): latency."""
+    from baseline import reference_arm
+
+    phoneme, _, cls = reference_arm._inputs(11, 1, 50, 51)
+    ph_h, cls_h = phoneme.pin_memory(), cls.pin_memory()
+    ph_d, cls_d = phoneme.to(device), cls.to(device)
+
+    def dev():
+        torch.manual_seed(7)
+        return model.infer(ph_d, style_prompt=cls_d, use_max=True, noise_scale=0.5)
+
+    def e2e():
+        torch.manual_seed(7)
+        return model.infer(ph_h.to(device, non_blocking=True), style_prompt=cls_h.to(device, non_blocking=True),
+                           use_max=True, noise_scale=0.5).cpu()
+
+    for _ in range(2):
+        dev()
+    t_dev = sorted(_event_time(dev, device)[0] for _ in range(reps))
+    t_e2e = sorted(_event_time(e2e, device)[0] for _ in range(reps))
+    frames = int(dev().shape[-1])
+    ms, ms_e = t_dev[len(t_dev) // 2], t_e2e[len(t_e2e) // 2]
+    return {"workload": "cfg1: single utterance, 50 synthetic phonemes, fixed style-prompt embedding, acoustic -> mel "
+                        "(model.infer, 100 diffusion steps)",
+            "latency_ms": ms, "latency_ms_min": t_dev[0], "frames": frames, "frames_per_sec": frames / (ms * 1e-3),
+            "e2e": {"latency_ms": ms_e, "frames_per_sec": frames / (ms_e * 1e-3), "h2d_bytes": 50 * 8 + 768 * 4,
+                    "d2h_bytes": frames * 80 * 4},
+            "reps": reps}
+
+
+def leg_cfg4(model, voc, voc_f0, device, n=32):
+    """configs[3]: text ids + style-prompt embeddings -> waveforms for 32 variable-length requests through
+    serving.BatchedSynthesizer (token-bucketed batches, acoustic -> f0 post-processing -> vocoder, one D2H per batch).
+    Host tensors in, host waveforms out: the timed region holds every copy."""
+    from promptttspp_b200.serving import BatchedSynthesizer, MelStats
+
+    phonemes, emb = var_len_requests(n, seed=41)
+    res = {"workload": f"cfg4: end-to-end text+style-prompt -> 24 kHz waveform, {n} variable-length requests "
+                       "(32..256 phonemes) through serving.BatchedSynthesizer (max_tokens 8192)"}
+    for name, v in (("bigvgan", voc), ("bigvgan_f0", voc_f0)):
+        srv = BatchedSynthesizer(model, v, MelStats(mean=-5.0, std=2.0), max_tokens=8192, max_sentences=32)
+
+        def run():
+            torch.manual_seed(11)
+            return srv.synthesize(phonemes, emb, device=device)
+
+        run()
+        ms, out = _event_time(run, device)
+        samples = sum(int(w.numel()) for w in out.values())
+        frames = samples // 240
+        res[name] = {"ms": ms, "valid_frames": frames, "frames_per_sec": frames / (ms * 1e-3),
+                     "audio_seconds": samples / 24000.0, "rtf": (ms * 1e-3) / (samples / 24000.0),
+                     "h2d_bytes": sum(p.numel() for p in phonemes) * 8 + emb.numel() * 4, "d2h_bytes": samples * 4}
+    return res
+
+
+def leg_cfg5(model, voc, device, rank, world, n=256, batch_size=16):
+    """configs[4]: 256 utterances sharded over the `world` ranks with dist.synthesize_sharded (length-sorted round-robin
+    deal, batches of 16 neighbouring lengths, no data-path collective), text ids -> waveform; STRONG scaling: the job
+    is the same 256 utterances at every N, time = max over ranks."""
+    import torch.distributed as dist
+
+    from promptttspp_b200.dist import gather_frame_counts, synthesize_sharded
+
+    phonemes, emb = var_len_requests(n, seed=51, lo=64)
+    emb_d = emb.to(device)
+
+    def synth_batch(padded, lens, idx):
+        torch.manual_seed(1000 + idx[0])  # the draw depends on the batch, not on the rank that runs it
+        p = padded.pin_memory().to(device, non_blocking=True)
+        l = lens.pin_memory().to(device, non_blocking=True)
+        mel, flen = model.infer_batch(p, l, style_prompt=emb_d[idx], use_max=True, noise_scale=0.5)
+        wav = voc(mel * 2.0 - 5.0).squeeze(1).cpu()
+        nf = flen.cpu().long().tolist()
+        return [(nf[b], float(wav[b, : nf[b] * 240].double().abs().sum())) for b in range(len(idx))]
+
+    synthesize_sharded(phonemes[: 2 * world], synth_batch, batch_size, world, rank)  # warm-up: one small batch
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    mine = synthesize_sharded(phonemes, synth_batch, batch_size, world, rank)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    counts = gather_frame_counts({i: r[0] for i, r in mine.items()}, n)
+    frames = sum(counts)
+    return {"workload": f"cfg5: {n} utterances (64..256 phonemes), text ids -> waveform, dist.synthesize_sharded over "
+                        f"{world} rank(s), batches of {batch_size}",
+            "scaling": "strong", "n_gpus": world, "ms": float(ms), "valid_frames": frames,
+            "frames_per_sec": frames / (float(ms) * 1e-3), "audio_seconds": frames / 100.0,
+            "rtf": float(ms) * 1e-3 / (frames / 100.0), "utterances_this_rank": len(mine),
+            "frame_count_checksum": int(sum((i + 1) * c for i, c in enumerate(counts)) % 1000000007)}
 
 # ---------------------------------------------------------------------------------------------
 # native arm
@@ -342,9 +443,28 @@ def run_native(args, rank, local_rank, world):
     voc_frames = mel_d.shape[0] * mel_d.shape[-1] * world
     audio_s = voc_frames / 100.0
 
+    # ---- the other BASELINE configs ----
+    extra = {}
+    if not args.no_extra:
+        from golden_cases import F0_KWARGS
+        from promptttspp_b200.utils.synthetic import build_vocoder_f0, synthetic_state_dict
+
+        if rank == 0:
+            extra["cfg1"] = leg_cfg1(model, device)
+            voc_f0 = build_vocoder_f0(**F0_KWARGS)
+            voc_f0.load_state_dict(synthetic_state_dict(voc_f0, seed=4322), strict=True)
+            extra["cfg4"] = leg_cfg4(model, voc, voc_f0.to(device).eval(), device)
+            del voc_f0
+        barrier()
+        extra["cfg5"] = leg_cfg5(model, voc, device, rank, world)
+
     if rank == 0:
-        cpu_ac, _ = cpu_acoustic_sample(1, 0) if world == 1 and not args.no_cpu else (None, None)
-        cpu_voc = cpu_bigvgan_sample(1, 0) if world == 1 and not args.no_cpu else None
+        cpu_ac, _ = cpu_acoustic_sample(2, 1) if world == 1 and not args.no_cpu else (None, None)
+        cpu_voc = cpu_bigvgan_sample(2, 1) if world == 1 and not args.no_cpu else None
+        if "cfg1" in extra and world == 1 and not args.no_cpu:
+            from baseline import reference_arm
+
+            extra["cfg1"]["cpu_baseline"] = reference_arm.cfg1_sample(2, 1)
         roof_ac = roofline_from(rep_ac, pk, in_long_step=True, rows=float(padded) / world)
         roof_voc = roofline_from(rep_voc, pk, in_long_step=True)
         frames_s = float(valid) / (ms_dev * 1e-3)
@@ -376,6 +496,7 @@ def run_native(args, rank, local_rank, world):
                 "cpu_baseline": cpu_voc,
             },
         }
+        line.update(extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -389,6 +510,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg1 / cfg4 / cfg5 legs")
     ap.add_argument("--leg", default="both", choices=["both", "acoustic", "bigvgan"],
                     help="profiling aid (ncu launch lists): run only one leg; the default line carries both")
     args = ap.parse_args()

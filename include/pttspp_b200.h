@@ -45,8 +45,9 @@ void pttspp_debug_reload_env(void);
 /* Optional per-launch timing for bench.py's roofline leg (off by default, single-threaded use).
  * While enabled, every op-level call records a CUDA event pair on its stream and accounts its
  * ALGORITHMIC work; the report sums them per kernel family:
- *   tag 0 conv1d CUDA-core, 1 conv1d tcgen05, 2 anti-aliased Snake, 3 LayerNorm, 4 attention, 5 other.
- * ms / flops / bytes / calls: arrays of >= 6 entries.  prof_enable() also clears the counters. */
+ *   tag 0 conv1d CUDA-core, 1 conv1d tcgen05, 2 anti-aliased Snake, 3 LayerNorm, 4 attention, 5 other,
+ *   6 the fused DiffNet layer-stack kernel (one launch = all residual layers of one diffusion step).
+ * ms / flops / bytes / calls: arrays of >= 7 entries.  prof_enable() also clears the counters. */
 void pttspp_prof_enable(int on);
 int pttspp_prof_report(double* ms, double* flops, double* bytes, int64_t* calls, int ntags);
 
@@ -211,6 +212,26 @@ int pttspp_length_regulate(const float* x, const int64_t* dur, int B, int Tx, in
  * Butterworth low-pass app.py:77 applies to log-f0 between the acoustic model and the vocoder). */
 int pttspp_iir_filtfilt(const float* x, float* y, float* scratch, int rows, int T, const float* b_coeffs,
                         const float* a_coeffs, int ntaps, pttspp_stream_t stream);
+/* The same filter over a zero-padded ragged batch: row r holds row_len[r] valid samples and is filtered exactly like a
+ * per-utterance call of promptttspp/utils/model.py:164-196 on x[r, :row_len[r]] (the backward pass starts at the row's own
+ * last sample with zero state); rows with row_len <= min_len pass through unchanged (the reference's short-input rule,
+ * utils/model.py:186-187) and the padding is copied.  This is what a batched caller of app.py:76-77 needs. */
+int pttspp_iir_filtfilt_ragged(const float* x, float* y, float* scratch, int rows, int T, const int64_t* row_len,
+                               int min_len, const float* b_coeffs, const float* a_coeffs, int ntaps,
+                               pttspp_stream_t stream);
+
+/* Log-mel spectrogram front end of the reference-mel path: promptttspp/transforms/mel.py:18-34 (torchaudio
+ * MelSpectrogram as configured by conf/transforms/mel.yaml; callers app.py:93-100, egs/proposed/bin/synthesize.py:172-175).
+ * wav [B][L] -> frames = 1 + L / hop columns; frame t covers samples t*hop - n_fft/2 .. + n_fft (reflect padding at both
+ * ends, torch.stft(center=True, pad_mode="reflect")), multiplied by window[n_fft] (the analysis window already
+ * zero-padded to n_fft), |DFT|^power (power 1 or 2) over n_fft/2 + 1 bins -> spec_out [B][n_fft/2+1][frames] (optional);
+ * mel_out [B][n_mels][frames] = log(max(fb^T spec, log_floor)) with fb [n_fft/2+1][n_mels] (optional). */
+int pttspp_mel_spectrogram(const float* wav, int B, int L, int n_fft, int hop, const float* window, const float* fb,
+                           int n_mels, int power, float log_floor, float* spec_out, float* mel_out,
+                           pttspp_stream_t stream);
+/* spec_to_mel alone (transforms/mel.py:23-26): spec [B][n_freq][frames] -> mel_out [B][n_mels][frames]. */
+int pttspp_mel_from_spec(const float* spec, int B, int n_freq, int frames, const float* fb, int n_mels, float log_floor,
+                         float* mel_out, pttspp_stream_t stream);
 
 /* Reference-mel style path (promptttspp/modules/reference_encoder.py:95-124, style_encoder.py:82-171).
  * conv2d_bn_relu: one [Conv2d KxK stride pad (no bias) -> BatchNorm2d(eval, folded to scale/shift) -> ReLU] block on

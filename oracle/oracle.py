@@ -131,6 +131,49 @@ def lowpass_filter(x, fs=100, cutoff=20, N=5):
     return filtfilt(x, torch.from_numpy(a).float(), torch.from_numpy(b).float(), clamp=False)
 
 
+MEL_CFG = dict(sample_rate=24000, n_fft=512, win_length=480, hop_length=240, power=1, f_min=63, f_max=12000, n_mels=80,
+               mel_scale="slaney", norm="slaney", center=True)  # egs/proposed/bin/conf/transforms/mel.yaml
+
+
+def mel_filterbank(n_freqs, f_min, f_max, n_mels, sample_rate):
+    """Slaney-scale, slaney-normalised triangular filters [n_freqs, n_mels] -- torchaudio.functional.melscale_fbanks
+    (third-party: torchaudio, unpinned in the reference's setup.py; the MelScale buffer of transforms/mel.py:23-24)."""
+    f_sp, min_log_hz, logstep = 200.0 / 3, 1000.0, math.log(6.4) / 27.0
+
+    def hz_to_mel(f):
+        return min_log_hz / f_sp + math.log(f / min_log_hz) / logstep if f >= min_log_hz else f / f_sp
+
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_pts = torch.linspace(hz_to_mel(f_min), hz_to_mel(f_max), n_mels + 2)
+    f_pts = f_sp * m_pts
+    log_t = m_pts >= min_log_hz / f_sp
+    f_pts[log_t] = min_log_hz * torch.exp(logstep * (m_pts[log_t] - min_log_hz / f_sp))
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    fb = torch.clamp(torch.min(-slopes[:, :-2] / f_diff[:-1], slopes[:, 2:] / f_diff[1:]), min=0.0)
+    return fb * (2.0 / (f_pts[2:n_mels + 2] - f_pts[:n_mels])).unsqueeze(0)
+
+
+def mel_spectrogram(wav, cfg=None):
+    """transforms/mel.py:18-34: wav [B, L] -> (|STFT| [B, n_fft/2+1, frames], log-mel [B, n_mels, frames]).  Explicit
+    framing (reflect padding of n_fft/2, periodic Hann of win_length centred in the n_fft frame, hop) + rfft per frame,
+    magnitude, filterbank contraction, clamp_min(1e-5).log()."""
+    cfg = cfg or MEL_CFG
+    n_fft, win, hop = cfg["n_fft"], cfg["win_length"], cfg["hop_length"]
+    x = F.pad(wav.unsqueeze(1), (n_fft // 2, n_fft // 2), mode="reflect").squeeze(1)
+    frames = x.unfold(-1, n_fft, hop)                                    # [B, frames, n_fft]
+    window = torch.zeros(n_fft)
+    left = (n_fft - win) // 2
+    window[left:left + win] = torch.hann_window(win)
+    spec = torch.fft.rfft(frames * window, dim=-1).abs()
+    if cfg["power"] == 2:
+        spec = spec ** 2
+    spec = spec.transpose(1, 2)                                          # [B, n_freq, frames]
+    fb = mel_filterbank(n_fft // 2 + 1, cfg["f_min"], cfg["f_max"], cfg["n_mels"], cfg["sample_rate"])
+    mel = torch.matmul(spec.transpose(-1, -2), fb).transpose(-1, -2)
+    return spec, mel.clamp_min(1e-5).log()
+
+
 def nsf_source(sd, f0_up, rand_ini, noise, sampling_rate=24000.0, harmonic_num=8, sine_amp=0.1, noise_std=0.003,
                voiced_threshold=0.0):
     """SourceModuleHnNSF.forward (vocoders/nsf.py:193-206) over SineGen.forward (:116-148) and SineGen._f02sine

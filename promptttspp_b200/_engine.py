@@ -51,6 +51,11 @@ class NativeHandle:
         _abi.check(getattr(self._lib, f"pttspp_{self.kind}_finalize")(self._h, stream))
         self._sig = sig
 
+    def invalidate(self):
+        """Forget the upload signature: the next sync() re-packs every tensor (for writes through `.data`, which do not
+        bump the version counters the signature watches)."""
+        self._sig = None
+
     def workspace(self, nbytes, device):
         """Grow-only scratch buffer from torch's caching allocator."""
         if self._ws is None or self._ws.numel() < nbytes or self._ws.device != device:

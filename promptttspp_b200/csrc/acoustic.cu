@@ -783,7 +783,7 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
       r.done = w.done; r.epoch = (unsigned)(c.K_step - step); r.dbg_z = nullptr;
       const double flops = 2.0 * B * (double)Ty * c.diff_layers * (3.0 * DC * 2 * DC + (double)DC * 2 * DC) -
                            2.0 * B * (double)Ty * DC * DC;  // the last layer has no residual half
-      ProfScope prof(PROF_CONV_UMMA, s, flops, 0.0);
+      ProfScope prof(PROF_DIFFNET, s, flops, 0.0);
       h->diffnet.run(r, s);
     }
     for (int l = 0; l < (fused ? 0 : c.diff_layers); ++l) {

@@ -409,10 +409,22 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(float* __restrict__ x,
 // short (a few thousand 10-ms frames), so one thread owns one row and a ring of the last NT-1 inputs / outputs.
 constexpr int IIR_MAX_TAPS = 8;
 __global__ void __launch_bounds__(64) iir_filtfilt_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                          float* __restrict__ tmp, int rows, int T,
-                                                          const float* __restrict__ bc, const float* __restrict__ ac, int nt) {
+                                                          float* __restrict__ tmp, int rows, int Tfull,
+                                                          const float* __restrict__ bc, const float* __restrict__ ac, int nt,
+                                                          const int64_t* __restrict__ row_len, int min_len) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
+  // ragged batch: row r holds row_len[r] samples; both recursions run over exactly those (the backward pass starts at
+  // the row's own last sample with zero state, as a per-utterance call would) and the padding is copied through
+  int T = Tfull;
+  if (row_len) {
+    T = (int)min((int64_t)Tfull, max((int64_t)0, row_len[r]));
+    const float* xs = x + (int64_t)r * Tfull;
+    float* ys = y + (int64_t)r * Tfull;
+    const int keep_from = (T <= min_len) ? 0 : T;  // rows too short for the filter pass through unchanged
+    for (int n = keep_from; n < Tfull; ++n) ys[n] = xs[n];
+    if (T <= min_len) return;
+  }
   float b[IIR_MAX_TAPS], a[IIR_MAX_TAPS];
   const float a0 = ac[0];
 #pragma unroll
@@ -420,9 +432,9 @@ __global__ void __launch_bounds__(64) iir_filtfilt_kernel(const float* __restric
     b[k] = (k < nt) ? bc[k] / a0 : 0.f;  // lfilter normalises both coefficient sets by a[0]
     a[k] = (k < nt) ? ac[k] / a0 : 0.f;
   }
-  const float* xr = x + (int64_t)r * T;
-  float* t1 = tmp + (int64_t)r * T;
-  float* yr = y + (int64_t)r * T;
+  const float* xr = x + (int64_t)r * Tfull;
+  float* t1 = tmp + (int64_t)r * Tfull;
+  float* yr = y + (int64_t)r * Tfull;
   for (int pass = 0; pass < 2; ++pass) {
     // pass 0: forward over x -> t1; pass 1: backward over t1 -> y (a forward filter of the flipped signal)
     float xin[IIR_MAX_TAPS], yo[IIR_MAX_TAPS];
@@ -591,11 +603,12 @@ extern "C" int pttspp_length_regulate(const float* x, const int64_t* dur, int B,
 
 namespace pttspp {
 void iir_filtfilt(const float* x, float* y, float* tmp, int rows, int T, const float* b, const float* a, int ntaps,
+                  const int64_t* row_len, int min_len,
                   cudaStream_t s) {
   PT_CHECK(x && y && tmp && b && a, "iir_filtfilt: null pointer");
   PT_CHECK(ntaps >= 1 && ntaps <= IIR_MAX_TAPS, "iir_filtfilt: 1..%d coefficients supported", IIR_MAX_TAPS);
   if (rows <= 0 || T <= 0) return;
-  iir_filtfilt_kernel<<<ceil_div(rows, 64), 64, 0, s>>>(x, y, tmp, rows, T, b, a, ntaps);
+  iir_filtfilt_kernel<<<ceil_div(rows, 64), 64, 0, s>>>(x, y, tmp, rows, T, b, a, ntaps, row_len, min_len);
   PT_LAUNCHED();
 }
 }  // namespace pttspp
@@ -603,6 +616,15 @@ void iir_filtfilt(const float* x, float* y, float* tmp, int rows, int T, const f
 extern "C" int pttspp_iir_filtfilt(const float* x, float* y, float* scratch, int rows, int T, const float* b_coeffs,
                                    const float* a_coeffs, int ntaps, pttspp_stream_t stream) {
   PT_API_BEGIN
-  pttspp::iir_filtfilt(x, y, scratch, rows, T, b_coeffs, a_coeffs, ntaps, (cudaStream_t)stream);
+  pttspp::iir_filtfilt(x, y, scratch, rows, T, b_coeffs, a_coeffs, ntaps, nullptr, 0, (cudaStream_t)stream);
+  PT_API_END
+}
+
+extern "C" int pttspp_iir_filtfilt_ragged(const float* x, float* y, float* scratch, int rows, int T, const int64_t* row_len,
+                                          int min_len, const float* b_coeffs, const float* a_coeffs, int ntaps,
+                                          pttspp_stream_t stream) {
+  PT_API_BEGIN
+  PT_CHECK(row_len != nullptr && min_len >= 0, "iir_filtfilt_ragged: row_len is required");
+  pttspp::iir_filtfilt(x, y, scratch, rows, T, b_coeffs, a_coeffs, ntaps, row_len, min_len, (cudaStream_t)stream);
   PT_API_END
 }

@@ -66,7 +66,7 @@ struct Error : std::runtime_error {
 // When enabled, a ProfScope records a CUDA event pair around the launches issued inside it and
 // accounts the ALGORITHMIC work of the call (flops / bytes as defined in DESIGN.md).
 enum ProfTag { PROF_CONV_SIMT = 0, PROF_CONV_UMMA = 1, PROF_AA_SNAKE = 2, PROF_LAYERNORM = 3, PROF_ATTENTION = 4,
-               PROF_OTHER = 5, PROF_NUM_TAGS = 6 };
+               PROF_OTHER = 5, PROF_DIFFNET = 6, PROF_NUM_TAGS = 7 };
 struct ProfScope {
   int tag;
   cudaStream_t s;

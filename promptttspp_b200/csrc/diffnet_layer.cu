@@ -711,7 +711,7 @@ extern "C" int pttspp_diffnet_run(pttspp_diffnet_t* h, const pttspp_diffnet_run_
   q.skip = r->skip; q.skip_hi = r->skip_hi; q.skip_lo = r->skip_lo;
   q.done = r->done; q.epoch = r->epoch; q.dbg_z = r->dbg_z; q.dbg_prof = (unsigned long long*)r->dbg_prof;
   const double rows = (double)r->B * r->T * (r->layer_end - r->layer_begin);
-  pttspp::ProfScope prof(pttspp::PROF_CONV_UMMA, (cudaStream_t)stream, rows * 2.0 * (3 * 256 * 512 + 256 * 512), 0.0);
+  pttspp::ProfScope prof(pttspp::PROF_DIFFNET, (cudaStream_t)stream, rows * 2.0 * (3 * 256 * 512 + 256 * 512), 0.0);
   h->stack.run(q, (cudaStream_t)stream);
   PT_API_END
 }

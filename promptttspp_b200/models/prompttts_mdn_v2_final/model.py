@@ -69,6 +69,7 @@ class PromptTTSMDNDurCFG(nn.Module):
         if style_mdn is None or not style_mdn.dim_wise:
             raise NotImplementedError("style_mdn with dim_wise=True is required (shipped configs)")
         self._native = None
+        self._tensor_view = None
         self._pe_cache = {}
 
     # ---- training forward: out of the accelerated path ------------------------------------
@@ -121,13 +122,27 @@ class PromptTTSMDNDurCFG(nn.Module):
     def _handle(self, device):
         if self._native is None:
             self._native = NativeHandle("acoustic", self._config())
-        tensors = {
-            k: v for k, v in self.state_dict(keep_vars=True).items()
-            if not k.startswith("prompt_encoder.bert.") and not k.startswith("reference_encoder.")
-            and v.dtype.is_floating_point
-        }
-        self._native.sync(tensors, device)
+        # the {key: tensor} view of the module tree is rebuilt only when the tree changed (load_state_dict keeps the
+        # Parameter objects, .to() / remove_weight_norm_ replace them): cheap identity probe instead of a state_dict()
+        # per call on the B=1 latency path
+        probe = tuple(id(p) for p in self.parameters(recurse=True)) + tuple(id(b) for b in self.buffers(recurse=True))
+        if self._tensor_view is None or self._tensor_view[0] != probe:
+            tensors = {
+                k: v for k, v in self.state_dict(keep_vars=True).items()
+                if not k.startswith("prompt_encoder.bert.") and not k.startswith("reference_encoder.")
+                and v.dtype.is_floating_point
+            }
+            self._tensor_view = (probe, tensors)
+        self._native.sync(self._tensor_view[1], device)
         return self._native
+
+    def refresh_weights(self):
+        """Force a re-upload of the packed native weights on the next call.  Needed only after writes that bypass
+        autograd's version counter (`param.data.copy_(...)`, e.g. an EMA swap): load_state_dict, `.to()`, in-place ops
+        on the parameters and remove_weight_norm_ are detected automatically."""
+        self._tensor_view = None
+        if self._native is not None:
+            self._native.invalidate()
 
     def _pos_table(self, kind, T, device):
         """Positional tables built on the host in fp32 exactly like the reference, cached per length."""
@@ -244,6 +259,55 @@ class PromptTTSMDNDurCFG(nn.Module):
         self.last_log_durations = log_dur
         # the reference returns frame_mask.sum(dim=(1, 2)): a float tensor (model.py:311)
         return mel, log_cf0, vuv, frame_len.to(torch.float32)
+
+    @torch.no_grad()
+    def generate_style_emb(self, style_prompt, reference_mel, use_max=True, noise_scale=1.0, *,
+                           noise: Optional[InferNoise] = None):
+        """(prompt_emb, ref_emb), both [B, C, 1] -- model.py:327-344: the style vector the prompt path would add to the
+        encoder output (adaptor -> normalise -> style MDN -> sample -> normalise) and the reference-mel style encoder's,
+        normalised.  The prompt side runs the text-side native call on a one-phoneme dummy (its `style_emb` output)."""
+        _abi.require_cuda(reference_mel, "PromptTTSMDNDurCFG.generate_style_emb")
+        device = reference_mel.device
+        Cc = self.phoneme_emb.channels
+        with torch.cuda.device(device):
+            nat = self._handle(device)
+            lib = _abi.lib()
+            stream = _abi.stream_ptr(device)
+            cls = self.prompt_encoder.sentence_embedding(style_prompt, device).float().contiguous()
+            B = cls.shape[0]
+            z_style = noise.z_style if noise is not None else torch.randn(B, 1, Cc, device=device)
+            z_style = z_style.to(device=device, dtype=torch.float32).reshape(B, Cc).contiguous()
+            phoneme = torch.ones(B, 1, dtype=torch.int64, device=device)
+            lengths = torch.ones(B, dtype=torch.int64, device=device)
+            legacy = self.encoder.rel_pos_type == "legacy"
+            pos = self._pos_table("legacy" if legacy else "new", 1, device)
+            enc_state = torch.empty(B, 1, Cc, device=device)
+            dur = torch.empty(B, 1, dtype=torch.int64, device=device)
+            frame_len = torch.empty(B, dtype=torch.int64, device=device)
+            style = torch.empty(B, Cc, device=device)
+            ws = nat.workspace(lib.pttspp_acoustic_encode_workspace_bytes(nat.h, B, 1), device)
+            if use_max:
+                _abi.check(lib.pttspp_acoustic_encode(
+                    nat.h, _abi.ptr(phoneme), _abi.ptr(lengths), B, 1, _abi.ptr(pos), pos.shape[0], _abi.ptr(cls),
+                    _abi.ptr(z_style), float(noise_scale), 1, _abi.ptr(enc_state), _abi.ptr(dur), _abi.ptr(frame_len),
+                    None, _abi.ptr(style), _abi.ptr(ws), C.c_size_t(ws.numel()), stream))
+            else:
+                comp_u = getattr(noise, "comp_u", None) if noise is not None else None
+                if comp_u is None:
+                    comp_u = torch.rand(B, Cc, device=device)
+                comp_u = comp_u.to(device=device, dtype=torch.float32).reshape(B, Cc).contiguous()
+                _abi.check(lib.pttspp_acoustic_encode_sampled(
+                    nat.h, _abi.ptr(phoneme), _abi.ptr(lengths), B, 1, _abi.ptr(pos), pos.shape[0], _abi.ptr(cls),
+                    _abi.ptr(z_style), _abi.ptr(comp_u), float(noise_scale), _abi.ptr(enc_state), _abi.ptr(dur),
+                    _abi.ptr(frame_len), None, _abi.ptr(style), _abi.ptr(ws), C.c_size_t(ws.numel()), stream))
+            prompt_emb = style.unsqueeze(-1)
+            if self.norm_style_emb:  # the second normalisation of model.py:338-339 (a no-op up to rounding)
+                prompt_emb = torch.nn.functional.normalize(prompt_emb, dim=1)
+            ref_lengths = torch.full((reference_mel.shape[0],), reference_mel.shape[-1], dtype=torch.int64, device=device)
+            ref_emb = self.reference_encoder(reference_mel, ref_lengths).float()
+            if self.norm_style_emb:
+                ref_emb = torch.nn.functional.normalize(ref_emb, dim=1)
+        return prompt_emb, ref_emb
 
     def infer(self, x, style_prompt=None, reference_mel=None, use_max=True, noise_scale=1.0, return_f0=False,
               *, noise: Optional[InferNoise] = None):

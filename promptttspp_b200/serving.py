@@ -80,7 +80,8 @@ class BatchedSynthesizer:
             dec = mel * self.stats.std + self.stats.mean                       # app.py:80
             if self.f0_aware:
                 if self.use_lowpass:
-                    log_cf0 = lowpass_filter(log_cf0, self.frame_rate, cutoff=20)  # app.py:76-77
+                    # app.py:76-77, per utterance: every row is filtered over its own frames only
+                    log_cf0 = lowpass_filter(log_cf0, self.frame_rate, cutoff=20, lengths=frame_len)
                 f0 = log_cf0.exp()
                 f0[vuv < 0.5] = 0                                              # app.py:78-79
                 wav = self.vocoder(dec, f0)

@@ -41,16 +41,21 @@ def butter_lowpass(N, Wn):
     return b, a
 
 
-def lowpass_filter(x, fs=100, cutoff=20, N=5):
+def lowpass_filter(x, fs=100, cutoff=20, N=5, lengths=None):
     """Zero-phase low-pass of a CUDA tensor along its last axis -- promptttspp/utils/model.py:164-196 (app.py:77
     smooths log-f0 with it before the vocoder).  Same short-input pass-through; the filtering itself is
-    pttspp_iir_filtfilt (torchaudio.functional.filtfilt semantics)."""
+    pttspp_iir_filtfilt (torchaudio.functional.filtfilt semantics).
+
+    `lengths` (not in the reference, which is only ever called per utterance): valid samples per row of a zero-padded
+    batch.  Each row is then filtered exactly as a call on x[r, ..., :lengths[r]] would be -- without it the backward
+    pass of a short row would start inside the padding and smear the step at the row's end over its last frames."""
     from .. import _abi
 
     nyquist = fs // 2
     b, a = butter_lowpass(N, cutoff / nyquist)
     x_len = x.shape[-1]
-    if x_len <= max(len(a), len(b)) * (N // 2 + 1):
+    min_len = max(len(a), len(b)) * (N // 2 + 1)
+    if x_len <= min_len:
         return x
     if not isinstance(x, torch.Tensor):
         raise NotImplementedError("lowpass_filter: only torch CUDA tensors are supported (no host fallback)")
@@ -62,6 +67,15 @@ def lowpass_filter(x, fs=100, cutoff=20, N=5):
     bd = torch.tensor(b, dtype=torch.float32, device=x.device)
     ad = torch.tensor(a, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        _abi.check(_abi.lib().pttspp_iir_filtfilt(_abi.ptr(xf), _abi.ptr(y), _abi.ptr(tmp), rows, x_len, _abi.ptr(bd),
-                                                  _abi.ptr(ad), len(b), _abi.stream_ptr(x.device)))
+        if lengths is None:
+            _abi.check(_abi.lib().pttspp_iir_filtfilt(_abi.ptr(xf), _abi.ptr(y), _abi.ptr(tmp), rows, x_len, _abi.ptr(bd),
+                                                      _abi.ptr(ad), len(b), _abi.stream_ptr(x.device)))
+        else:
+            lens = lengths.to(device=x.device, dtype=torch.int64).reshape(-1)
+            if lens.numel() != x.shape[0]:
+                raise ValueError(f"{lens.numel()} lengths for {x.shape[0]} batch rows")
+            lens = lens.repeat_interleave(rows // x.shape[0]).contiguous()  # one entry per filtered row
+            _abi.check(_abi.lib().pttspp_iir_filtfilt_ragged(
+                _abi.ptr(xf), _abi.ptr(y), _abi.ptr(tmp), rows, x_len, _abi.ptr(lens), min_len, _abi.ptr(bd),
+                _abi.ptr(ad), len(b), _abi.stream_ptr(x.device)))
     return y.view(x.shape)

@@ -62,6 +62,7 @@ class BigVGAN(nn.Module):
         self.act_post = AntiAliasActivation(last)
         self.conv_post = weight_norm(nn.Conv1d(last, 1, kernel_size=7, stride=1, padding=3))
         self._native = None
+        self._tensor_view = None
 
     # -- native handle -------------------------------------------------------------------
     def _config(self):
@@ -83,9 +84,17 @@ class BigVGAN(nn.Module):
     def _handle(self, device):
         if self._native is None:
             self._native = NativeHandle("bigvgan", self._config())
-        tensors = dict(self.state_dict(keep_vars=True))
-        self._native.sync(tensors, device)
+        probe = tuple(id(p) for p in self.parameters(recurse=True)) + tuple(id(b) for b in self.buffers(recurse=True))
+        if self._tensor_view is None or self._tensor_view[0] != probe:
+            self._tensor_view = (probe, dict(self.state_dict(keep_vars=True)))
+        self._native.sync(self._tensor_view[1], device)
         return self._native
+
+    def refresh_weights(self):
+        """Force a re-upload of the packed native weights (after writes through `.data`, see NativeHandle.invalidate)."""
+        self._tensor_view = None
+        if self._native is not None:
+            self._native.invalidate()
 
     @property
     def hop(self):

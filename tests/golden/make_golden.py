@@ -264,6 +264,24 @@ def make_lowpass():
     print("lowpass", {k: v.shape for k, v in out.items()})
 
 
+def make_mel():
+    """promptttspp.transforms.MelSpectrogramTransform with the kwargs of conf/transforms/mel.yaml on seeded waveforms."""
+    sys.path.insert(0, str(REF))
+    import yaml
+    from promptttspp.transforms import MelSpectrogramTransform
+    from golden_cases import mel_inputs
+
+    kw = yaml.safe_load(open(REF / "egs/proposed/bin/conf/transforms/mel.yaml"))
+    kw.pop("_target_")
+    to_mel = MelSpectrogramTransform(**kw).eval()
+    out = {}
+    for i, w in enumerate(mel_inputs()):
+        out[f"mel{i}"] = to_mel(w).numpy()
+        out[f"spec{i}"] = to_mel.to_spec(w).numpy()
+    np.savez_compressed(OUT / "mel_transform.npz", **out)
+    print("mel", {k: v.shape for k, v in out.items()})
+
+
 def make_style(ns):
     """Reference StyleEncoder on a ragged batch, and infer_batch(reference_mel=...) end to end."""
     from golden_cases import ACOUSTIC_REFMEL_CASE, STYLE_CASE, style_inputs
@@ -416,7 +434,7 @@ def make_ops():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops", "vocoder", "vocoder_f0", "lowpass", "style", "sampled", "bert", "acoustic"]
+    which = sys.argv[1:] or ["ops", "vocoder", "vocoder_f0", "lowpass", "mel", "style", "sampled", "bert", "acoustic"]
     if "ops" in which:
         make_ops()
     if "vocoder" in which:
@@ -425,6 +443,8 @@ if __name__ == "__main__":
         make_vocoder_f0()
     if "lowpass" in which:
         make_lowpass()
+    if "mel" in which:
+        make_mel()
     if "style" in which:
         make_style(reference_namespace())
     if "sampled" in which:

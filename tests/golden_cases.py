@@ -107,6 +107,21 @@ def lowpass_inputs():
             torch.randn(2, 1, 17, generator=g)]
 
 
+def mel_inputs():
+    """Speech-like waveforms [B, L] in [-1, 1]: harmonic stacks + noise; one L a multiple of the hop, one not, one with a
+    silent stretch (exercises the 1e-5 log floor)."""
+    g = torch.Generator().manual_seed(88)
+    out = []
+    for B, L in ((2, 24000), (1, 5003), (3, 1300)):
+        t = torch.arange(L) / 24000.0
+        f0 = 90.0 + 120.0 * torch.rand(B, 1, generator=g)
+        w = sum(torch.sin(2 * torch.pi * f0 * h * t[None]) / h for h in range(1, 9)) * 0.2
+        w = w + 0.02 * _randn(B, L, generator=g)
+        w[:, L // 3: L // 3 + 700] = 0.0
+        out.append(w.clamp(-1, 1).contiguous())
+    return out
+
+
 # reference-mel style path (SURVEY.md 8f3): ragged batch of normalised reference mels
 STYLE_CASE = dict(weight_seed=1234, input_seed=11, lengths=[200, 133, 64], rel_pos_type="legacy")
 ACOUSTIC_REFMEL_CASE = dict(api="infer_batch", rel_pos_type="legacy", lengths=[9, 6], weight_seed=1234,

@@ -262,3 +262,24 @@ def test_lowpass_filter_matches_reference_golden(golden_dir):
         assert err < 2e-5
     with pytest.raises(RuntimeError):
         lowpass_filter(torch.zeros(1, 1, 100))  # CPU tensor: no host fallback
+
+
+def test_lowpass_filter_ragged_rows_equal_per_utterance_calls():
+    """a zero-padded batch filtered with `lengths` must give every row what a per-utterance call
+    (app.py:76-77) gives on its own frames, incl. the short-input pass-through; the padding is left untouched."""
+    from promptttspp_b200.utils.model import lowpass_filter
+
+    g = torch.Generator().manual_seed(5)
+    lens = [400, 131, 18, 19, 1, 257]
+    B, T = len(lens), max(lens)
+    x = torch.zeros(B, 1, T)
+    for b, n in enumerate(lens):
+        x[b, 0, :n] = 5.0 + 0.3 * torch.randn(n, generator=g)  # log-f0 like: a step of ~5 at the end of the row
+    y = lowpass_filter(x.cuda(), 100, cutoff=20, lengths=torch.tensor(lens).cuda()).cpu()
+    for b, n in enumerate(lens):
+        single = lowpass_filter(x[b:b + 1, :, :n].contiguous().cuda(), 100, cutoff=20).cpu()
+        assert torch.equal(y[b:b + 1, :, :n], single), (b, n, float((y[b:b + 1, :, :n] - single).abs().max()))
+        assert torch.equal(y[b, :, n:], x[b, :, n:])
+    # without lengths the tail of a short row is contaminated by the step into the padding (what the advice flagged)
+    bad = lowpass_filter(x.cuda(), 100, cutoff=20).cpu()
+    assert float((bad[1, 0, :131] - y[1, 0, :131]).abs().max()) > 0.5

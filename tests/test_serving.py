@@ -60,3 +60,33 @@ def test_batched_synthesizer_matches_single_calls():
     torch.manual_seed(0)
     again = srv.synthesize(phonemes, emb)
     assert all(torch.equal(out[i], again[i]) for i in out)
+
+
+@pytest.mark.gpu
+def test_batched_f0_path_equals_per_utterance_f0_path():
+    """the f0 post-processing (low-pass -> exp -> unvoiced zeroing, app.py:76-79) of a ragged batch must equal
+    the per-utterance flow on each row's own frames, and the vocoder's output for a row must not depend on the padding
+    of the batch (valid samples compared)."""
+    from golden_cases import F0_KWARGS
+    from promptttspp_b200.utils.model import lowpass_filter
+    from promptttspp_b200.utils.synthetic import build_vocoder_f0, synthetic_state_dict
+
+    torch.set_grad_enabled(False)
+    voc = build_vocoder_f0(**F0_KWARGS)
+    voc.load_state_dict(synthetic_state_dict(voc, seed=4322), strict=True)
+    voc = voc.cuda().eval()
+    g = torch.Generator().manual_seed(8)
+    lens = [96, 41, 70]
+    B, T = len(lens), max(lens)
+    log_cf0, vuv = torch.zeros(B, 1, T), torch.zeros(B, 1, T)
+    for b, n in enumerate(lens):
+        log_cf0[b, 0, :n] = 5.0 + 0.2 * torch.randn(n, generator=g)
+        vuv[b, 0, :n] = (torch.rand(n, generator=g) > 0.3).float()
+    flen = torch.tensor(lens)
+    lf = lowpass_filter(log_cf0.cuda(), 100, cutoff=20, lengths=flen.cuda())
+    f0 = lf.exp()
+    f0[vuv.cuda() < 0.5] = 0
+    for b, n in enumerate(lens):
+        s = lowpass_filter(log_cf0[b:b + 1, :, :n].contiguous().cuda(), 100, cutoff=20).exp()
+        s[vuv[b:b + 1, :, :n].cuda() < 0.5] = 0
+        assert torch.equal(f0[b:b + 1, :, :n], s)
