@@ -105,7 +105,9 @@ typedef struct {
   float alpha, beta;
   float out_div; /* 0 = no division */
   int32_t B;
-  int32_t impl; /* 0 = auto, 1 = force SIMT fp32, 2 = force tcgen05 split-fp16 */
+  int32_t impl; /* 0 = auto, 1 = force SIMT fp32, 2 = force tcgen05 split-fp16, 3 = tcgen05 split-fp16 with chunked
+                 * near-fp32 accumulation (<= 16 tensor-core accumulations per accumulator, chunk sums added in
+                 * round-to-nearest fp32 registers): the text side, whose outputs decide integer durations */
   /* ---- split-fp16 operands (tcgen05 path) -------------------------------------------------
    * An fp32 value v travels as two fp16 planes hi = fp16(v), lo = fp16(v - hi); the tensor cores
    * compute hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM (~2^-22 relative, fp32 class).

@@ -77,6 +77,8 @@ struct pttspp_acoustic {
   std::vector<pttspp::DiffLayerW> diff;
   float* step_table = nullptr;  // [K_step][layers][C]
   bool use_umma = true;         // tcgen05 split-fp16 path for the DiffNet contractions (PTTSPP_DISABLE_UMMA=1: off)
+  // text side (encoder feed-forward k9 convs) on the chunked near-fp32 tcgen05 path; PTTSPP_TEXT_TC=0: fp32 CUDA cores
+  bool text_tc = true;
   // all residual layers of one diffusion step in ONE persistent kernel (csrc/diffnet_layer.cu); PTTSPP_DIFFNET_FUSED=0
   // keeps the two-launches-per-layer path (the only one for other channel counts / kernel sizes)
   pttspp::DiffNetStack diffnet;
@@ -196,6 +198,7 @@ std::vector<float> build_step_table(const TensorStore& st, const pttspp_acoustic
 
 struct EncodeWs {
   float *x, *y, *hff, *qkv, *att, *pw, *cm, *p, *bd, *e1, *e2, *e3, *lp, *ls, *mu, *style, *logd;
+  uint16_t *yh, *yl, *fh, *fl;  // operand planes of the feed-forward input [B][Tx][C] and hidden layer [B][Tx][units]
 };
 
 EncodeWs carve_encode(const pttspp_acoustic_config& c, int B, int Tx, int Tp, Carver& cv) {
@@ -219,6 +222,10 @@ EncodeWs carve_encode(const pttspp_acoustic_config& c, int B, int Tx, int Tp, Ca
   w.mu = cv.take<float>((int64_t)B * c.style_gaussians * C);
   w.style = cv.take<float>((int64_t)B * C);
   w.logd = cv.take<float>(n);
+  w.yh = cv.take<uint16_t>(n * C);
+  w.yl = cv.take<uint16_t>(n * C);
+  w.fh = cv.take<uint16_t>(n * c.enc_linear_units);
+  w.fl = cv.take<uint16_t>(n * c.enc_linear_units);
   return w;
 }
 
@@ -316,6 +323,12 @@ extern "C" int pttspp_acoustic_finalize(pttspp_acoustic_t* h, pttspp_stream_t) {
     b.mac_w2 = load_conv1d(st, dev, p + "feed_forward_macaron.w_2", C, U, kf, 1, (kf - 1) / 2);
     b.ff_w1 = load_conv1d(st, dev, p + "feed_forward.w_1", U, C, kf, 1, (kf - 1) / 2);
     b.ff_w2 = load_conv1d(st, dev, p + "feed_forward.w_2", C, U, kf, 1, (kf - 1) / 2);
+    if (C % 64 == 0 && U % 64 == 0) {  // split-fp16 planes for the chunked (near-fp32) tcgen05 path of the text side
+      attach_split_weights(st, dev, p + "feed_forward_macaron.w_1", b.mac_w1, false);
+      attach_split_weights(st, dev, p + "feed_forward_macaron.w_2", b.mac_w2, false);
+      attach_split_weights(st, dev, p + "feed_forward.w_1", b.ff_w1, false);
+      attach_split_weights(st, dev, p + "feed_forward.w_2", b.ff_w2, false);
+    }
     b.qkv = load_concat(st, dev, {p + "self_attn.linear_q", p + "self_attn.linear_k", p + "self_attn.linear_v"}, C, C, 1,
                         false, true);
     b.pos = load_linear(st, dev, p + "self_attn.linear_pos", C, C, false);
@@ -434,6 +447,8 @@ extern "C" int pttspp_acoustic_finalize(pttspp_acoustic_t* h, pttspp_stream_t) {
     const char* e = getenv("PTTSPP_DISABLE_UMMA");
     h->use_umma = !(e && e[0] == '1') && DC % 64 == 0;
     h->h_fp32 = getenv("PTTSPP_H_FP32") != nullptr;
+    const char* tt = getenv("PTTSPP_TEXT_TC");
+    h->text_tc = h->use_umma && !(tt && tt[0] == '0') && !h->blocks.empty() && h->blocks[0].mac_w1.w_hi != nullptr;
     const char* f = getenv("PTTSPP_DIFFNET_FUSED");
     const int max_dil = 1 << (std::min(c.diff_dilation_cycle, c.diff_layers) - 1);
     h->use_fused = h->use_umma && !(f && f[0] == '0') && !h->h_fp32 && h->in_proj_tc.w_hi != nullptr &&
@@ -492,17 +507,33 @@ static void acoustic_encode_impl(pttspp_acoustic_t* h, const int64_t* phoneme, c
   // esp/transformer/embedding.py:253)
   embedding_cl(phoneme, len, h->emb, B, Tx, C, c.num_vocab, c.emb_do_scale ? sqrtf((float)C) : 1.f, w.x, s);
 
-  for (const EncBlockW& b : h->blocks) {
-    // macaron feed-forward: x += 0.5 * w_2(relu(w_1(LN(x) * m)) * m) * m
-    run_ln(b.norm_ff_macaron, w.x, nullptr, w.y, B, Tx, C, 1e-12f, nullptr, nullptr, 1.f, nullptr, s);
-    {
-      auto d = conv_desc(b.mac_w1, w.y, B, Tx, w.hff);
-      d.in_len = len; d.out_len = len; d.act = PTTSPP_ACT_RELU;
-      conv1d_cl(d, s);
-      auto e = conv_desc(b.mac_w2, w.hff, B, Tx, w.x);
-      e.out_len = len; e.res = w.x; e.res_bs = (int64_t)Tx * C; e.res_ld = C; e.alpha = 0.5f;
-      conv1d_cl(e, s);
+  // positionwise feed-forward (multi_layer_conv.py:52-67): x += 0.5 * w_2(relu(w_1(y * m)) * m) * m with y = LN(x).
+  // tcgen05 path: the masked LN output travels as split-fp16 planes, w_1 emits the masked hidden layer directly as planes,
+  // both contractions accumulate in chunks of 16 tensor-core steps summed in round-to-nearest fp32 (conv1d impl 3).
+  const int U = c.enc_linear_units;
+  auto feed_forward = [&](const PackedConv& w1, const PackedConv& w2) {
+    auto d = conv_desc(w1, w.y, B, Tx, w.hff);
+    d.out_len = len; d.act = PTTSPP_ACT_RELU;
+    auto e = conv_desc(w2, w.hff, B, Tx, w.x);
+    e.out_len = len; e.res = w.x; e.res_bs = (int64_t)Tx * C; e.res_ld = C; e.alpha = 0.5f;
+    if (h->text_tc) {
+      split_f16_rows(w.y, B, Tx, C, len, w.yh, w.yl, s);
+      d.in_hi = w.yh; d.in_lo = w.yl; d.in_bs = (int64_t)Tx * C; d.in_ld = C;
+      d.w_hi = w1.w_hi; d.w_lo = w1.w_lo; d.w_scale_inv = w1.w_scale_inv; d.impl = 3;
+      d.out = nullptr;
+      d.out_hi = w.fh; d.out_lo = w.fl; d.out_plane_bs = (int64_t)Tx * U; d.out_plane_ld = U;
+      e.in_hi = w.fh; e.in_lo = w.fl; e.in_bs = (int64_t)Tx * U; e.in_ld = U;
+      e.w_hi = w2.w_hi; e.w_lo = w2.w_lo; e.w_scale_inv = w2.w_scale_inv; e.impl = 3;
+    } else {
+      d.in_len = len;
     }
+    conv1d_cl(d, s);
+    conv1d_cl(e, s);
+  };
+  for (const EncBlockW& b : h->blocks) {
+    // macaron feed-forward
+    run_ln(b.norm_ff_macaron, w.x, nullptr, w.y, B, Tx, C, 1e-12f, nullptr, nullptr, 1.f, nullptr, s);
+    feed_forward(b.mac_w1, b.mac_w2);
     // relative-position self-attention
     run_ln(b.norm_mha, w.x, nullptr, w.y, B, Tx, C, 1e-12f, nullptr, nullptr, 1.f, nullptr, s);
     {
@@ -529,14 +560,7 @@ static void acoustic_encode_impl(pttspp_acoustic_t* h, const int64_t* phoneme, c
     }
     // feed-forward
     run_ln(b.norm_ff, w.x, nullptr, w.y, B, Tx, C, 1e-12f, nullptr, nullptr, 1.f, nullptr, s);
-    {
-      auto d = conv_desc(b.ff_w1, w.y, B, Tx, w.hff);
-      d.in_len = len; d.out_len = len; d.act = PTTSPP_ACT_RELU;
-      conv1d_cl(d, s);
-      auto e = conv_desc(b.ff_w2, w.hff, B, Tx, w.x);
-      e.out_len = len; e.res = w.x; e.res_bs = (int64_t)Tx * C; e.res_ld = C; e.alpha = 0.5f;
-      conv1d_cl(e, s);
-    }
+    feed_forward(b.ff_w1, b.ff_w2);
     run_ln(b.norm_final, w.x, nullptr, w.x, B, Tx, C, 1e-12f, nullptr, len, 1.f, nullptr, s);
   }
   run_ln(h->after_norm, w.x, nullptr, enc_state, B, Tx, C, 1e-12f, nullptr, len, 1.f, nullptr, s);

@@ -543,7 +543,12 @@ __device__ __forceinline__ void umma_tile_epilogue(const pttspp_conv1d_desc& de,
 // Persistent, warp-specialised: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA and MMA warps
 // run ahead into the next tile while the eight epilogue warps drain the previous accumulator: TMEM holds two
 // accumulator buffers of (main | cross-term) x BN columns.
-// EPI: 0 = TMA bulk-store / direct epilogue, 1 = coalescing epilogue.  DUAL: the launch carries a second epilogue
+// EPI: 0 = TMA bulk-store / direct epilogue, 1 = coalescing epilogue, 2 = CHUNKED near-fp32 accumulation: the K loop is
+// cut into chunks of `chunk_iters` (slab, tap) iterations, every chunk accumulates into a FRESH accumulator buffer
+// (<= 16 * chunk_iters / 4 truncating tensor-core accumulations each) and the epilogue warps add the chunk results in
+// round-to-nearest fp32 registers while the next chunk runs -- the contraction stays in the fp32 error class however
+// long K is (the text encoder's k9 feed-forward convs, whose outputs decide integer durations).
+// DUAL: the launch carries a second epilogue
 // descriptor.  Both are compile-time so that a kernel holds exactly one epilogue body per descriptor (with both
 // variants inlined the 96-register budget spilled ~2 KB per thread and the narrow kernel lost 25 %).
 template <int BN, int STAGES, int NACC, int EPI, bool DUAL>
@@ -552,7 +557,7 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
                    const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                    const __grid_constant__ OutMaps om, const __grid_constant__ OutMaps om2,
                    const pttspp_conv1d_desc d, const pttspp_conv1d_desc d2, const int cout1, const int vec_ok,
-                   const int tma_out, const int n_mt, const int n_nt, const int n_tiles) {
+                   const int tma_out, const int n_mt, const int n_nt, const int n_tiles, const int chunk_iters) {
   // d describes the contraction (shared by all tiles) and the epilogue of output columns [0, cout1); d2 (dual mode,
   // cout1 < d.Cout) the epilogue of columns [cout1, d.Cout) -- e.g. the residual and skip halves of one projection.
   using SM = UmmaSmem<BN>;
@@ -634,47 +639,117 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
       const uint64_t desc0 = umma_desc_k_sw128(base);
       uint32_t g = 0;
       int i = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
-        const int u = i & 1;
-        mbar_wait_warp(tempty_bar(u), (((uint32_t)i >> 1) & 1u) ^ 1u);  // epilogue has drained this buffer
-        tc_fence_after();
-        // The tensor core truncates when it adds into the fp32 accumulator, so the error grows linearly with the
-        // number of accumulations into one accumulator: the 2^-11 smaller cross terms (hi*lo, lo*hi) get their
-        // own accumulator, the epilogue adds the two in round-to-nearest fp32.
-        // NACC - 1 main accumulators are used round-robin by K iteration: the truncation bias of one accumulator
-        // grows with the number of MMAs that add into it.
-        const uint32_t acc0 = tmem_base + (uint32_t)(u * NACC * BN);
-        const uint32_t acc_cross = acc0 + (uint32_t)((NACC - 1) * BN);
-        for (int it = 0; it < n_iter; ++it, ++g) {
-          const int s = g % STAGES;
-          const uint32_t ph = (g / STAGES) & 1u;
-          mbar_wait_warp(full_bar(s), ph);
+      const int chunk = (EPI == 2) ? chunk_iters : n_iter;  // iterations per accumulator buffer
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int it0 = 0; it0 < n_iter; it0 += chunk, ++i) {
+          const int u = i & 1;
+          const int it1 = min(n_iter, it0 + chunk);
+          mbar_wait_warp(tempty_bar(u), (((uint32_t)i >> 1) & 1u) ^ 1u);  // epilogue has drained this buffer
           tc_fence_after();
-          // descriptors of this stage: only the 14-bit start-address field differs from the stage-0 descriptor
-          const uint64_t dAh = desc0 + (uint64_t)((uint32_t)s * (uint32_t)(SM::STAGE_BYTES >> 4));
-          const uint64_t dAl = dAh + (uint64_t)(SM::A_BYTES >> 4);
-          const uint64_t dBh = dAh + (uint64_t)((2 * SM::A_BYTES) >> 4);
-          const uint64_t dBl = dAh + (uint64_t)((2 * SM::A_BYTES + SM::B_BYTES) >> 4);
-          const uint32_t acc_main = acc0 + (uint32_t)((it % (NACC - 1)) * BN);
-          const uint32_t first_main = (it >= NACC - 1) ? 1u : 0u;
-          if (elect_one()) {
+          // The tensor core truncates when it adds into the fp32 accumulator, so the error grows linearly with the
+          // number of accumulations into one accumulator: the 2^-11 smaller cross terms (hi*lo, lo*hi) get their
+          // own accumulator, the epilogue adds the two in round-to-nearest fp32.
+          // NACC - 1 main accumulators are used round-robin by K iteration: the truncation bias of one accumulator
+          // grows with the number of MMAs that add into it.
+          const uint32_t acc0 = tmem_base + (uint32_t)(u * NACC * BN);
+          const uint32_t acc_cross = acc0 + (uint32_t)((NACC - 1) * BN);
+          for (int it = it0; it < it1; ++it, ++g) {
+            const int s = g % STAGES;
+            const uint32_t ph = (g / STAGES) & 1u;
+            mbar_wait_warp(full_bar(s), ph);
+            tc_fence_after();
+            // descriptors of this stage: only the 14-bit start-address field differs from the stage-0 descriptor
+            const uint64_t dAh = desc0 + (uint64_t)((uint32_t)s * (uint32_t)(SM::STAGE_BYTES >> 4));
+            const uint64_t dAl = dAh + (uint64_t)(SM::A_BYTES >> 4);
+            const uint64_t dBh = dAh + (uint64_t)((2 * SM::A_BYTES) >> 4);
+            const uint64_t dBl = dAh + (uint64_t)((2 * SM::A_BYTES + SM::B_BYTES) >> 4);
+            const int rel = it - it0;
+            const uint32_t acc_main = acc0 + (uint32_t)((rel % (NACC - 1)) * BN);
+            const uint32_t first_main = (rel >= NACC - 1) ? 1u : 0u;
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < UM_BK / 16; ++kk) {
-              const uint64_t adv = (uint64_t)(kk * 2);  // 16 halves = 32 bytes along K inside the swizzle span
-              umma_f16(acc_cross, dAl + adv, dBh + adv, idesc, (kk != 0) ? 1u : (it != 0 ? 1u : 0u));
-              umma_f16(acc_cross, dAh + adv, dBl + adv, idesc, 1u);
-              umma_f16(acc_main, dAh + adv, dBh + adv, idesc, (kk != 0) ? 1u : first_main);
+              for (int kk = 0; kk < UM_BK / 16; ++kk) {
+                const uint64_t adv = (uint64_t)(kk * 2);  // 16 halves = 32 bytes along K inside the swizzle span
+                umma_f16(acc_cross, dAl + adv, dBh + adv, idesc, (kk != 0) ? 1u : (rel != 0 ? 1u : 0u));
+                umma_f16(acc_cross, dAh + adv, dBl + adv, idesc, 1u);
+                umma_f16(acc_main, dAh + adv, dBh + adv, idesc, (kk != 0) ? 1u : first_main);
+              }
+              umma_commit(empty_bar(s));  // frees the stage once these MMAs have read it
+              if (it + 1 == it1) umma_commit(tfull_bar(u));  // accumulator buffer u complete
             }
-            umma_commit(empty_bar(s));  // frees the stage once these MMAs have read it
-            if (it + 1 == n_iter) umma_commit(tfull_bar(u));  // accumulator buffer u complete
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
   } else {
     // ================= epilogue: warps 0-15 =================
     int i = 0;
+    if constexpr (EPI == 2) {
+      // chunked accumulation: this warp owns CW columns of 32 rows; running sums live in registers
+      constexpr int CW = BN / (UM_EPI_WARPS / 4);
+      static_assert(CW == 32, "chunked epilogue: 32 columns per warp");
+      const int q = warp & 3, cgrp = warp >> 2;
+      const int cbeg = cgrp * CW;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int nt = tile % n_nt, mt = (tile / n_nt) % n_mt, b = tile / (n_nt * n_mt);
+        const int n0 = nt * BN;
+        const int m = d.m_begin + mt * UM_BM + q * 32 + lane;
+        const int row = m * d.out_mul + d.out_off;
+        const bool row_ok = (m < d.m_begin + d.M) && row >= 0 && row < d.T_out;
+        float mask = 1.f;
+        if (d.out_len && row_ok) mask = ((long long)row < (long long)d.out_len[b]) ? 1.f : 0.f;
+        EpiOps16 ops0, ops1;
+        const bool v0 = vec_ok && row_ok && n0 + cbeg + 16 <= d.Cout;
+        const bool v1 = vec_ok && row_ok && n0 + cbeg + 32 <= d.Cout;
+        if (v0) conv_epilogue16_load(d, b, row, n0 + cbeg, ops0);
+        if (v1) conv_epilogue16_load(d, b, row, n0 + cbeg + 16, ops1);
+        float sum[CW];
+#pragma unroll
+        for (int e = 0; e < CW; ++e) sum[e] = 0.f;
+        for (int it0 = 0; it0 < n_iter; it0 += chunk_iters, ++i) {
+          const int u = i & 1;
+          const int nm = min(min(n_iter - it0, chunk_iters), NACC - 1);
+          mbar_wait_warp(tfull_bar(u), ((uint32_t)i >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * NACC * BN);
+#pragma unroll
+          for (int c = 0; c < CW; c += 16) {
+            float v[16], t[16];
+            tmem_ld16(tbase + (uint32_t)((NACC - 1) * BN + cbeg + c), v);  // cross terms
+            for (int a = 0; a < nm; ++a) {
+              tmem_ld16(tbase + (uint32_t)(a * BN + cbeg + c), t);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] += t[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) sum[c + e] += v[e];  // round-to-nearest fp32 across chunks
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(u));
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int c = 0; c < CW; c += 16) {
+            const int col0 = cbeg + c;
+            if (n0 + col0 >= d.Cout) continue;
+            float v[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = sum[c + e];
+            if (c == 0 ? v0 : v1) {
+              conv_epilogue16_finish(d, b, row, mask, n0 + col0, v, c == 0 ? ops0 : ops1);
+            } else {
+#pragma unroll
+              for (int gq = 0; gq < 4; ++gq) {
+                const float a4[4] = {v[gq * 4 + 0], v[gq * 4 + 1], v[gq * 4 + 2], v[gq * 4 + 3]};
+                conv_epilogue4(d, b, row, mask, n0 + col0 + gq * 4, a4);
+              }
+            }
+          }
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
       const int nt = tile % n_nt, mt = (tile / n_nt) % n_mt, b = tile / (n_nt * n_mt);
       const int nm = n_iter < NACC - 1 ? n_iter : NACC - 1;
@@ -1397,6 +1472,7 @@ struct UmmaEnv {
   char pair = 0, rl = 0, nacc = 0, epi = 0;  // first character of the variable, 0 when unset
   bool no_tma_store = false, debug = false, no_wres64 = false, a_stationary = false;
   int order = 0;
+  int chunk_iters = 4;  // chunked mode: (slab, tap) iterations per accumulator buffer (4 x 64 channels = 16 MMA steps)
   void load() {
     auto first = [](const char* name) -> char { const char* e = getenv(name); return e ? e[0] : (char)0; };
     pair = first("PTTSPP_UMMA_PAIR");
@@ -1409,6 +1485,8 @@ struct UmmaEnv {
     a_stationary = getenv("PTTSPP_UMMA_AS") != nullptr;
     const char* oe = getenv("PTTSPP_UMMA_ORDER");  // experiments: bits 0-1 MMA order, 4 no operand loads, 8 no stores, 16 no L2 prefetch
     order = oe ? atoi(oe) : 0;
+    const char* ce = getenv("PTTSPP_UMMA_CHUNK");
+    chunk_iters = ce ? std::max(1, atoi(ce)) : 4;
   }
 };
 std::mutex g_env_mutex;
@@ -1796,7 +1874,7 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
   const int num_sms = device_num_sms();
   const int total_cout = d.Cout;
   if (d2_in) d.Cout = cout1;  // the epilogue of the first half sees its own column count again
-  if (conv1d_umma_pair_launch(d, d2, d2_in != nullptr, cout1, total_cout, s, num_sms)) return;
+  if (d_in.impl != 3 && conv1d_umma_pair_launch(d, d2, d2_in != nullptr, cout1, total_cout, s, num_sms)) return;
   PT_CHECK(!d.res_hi && !(d2_in && d2.res_hi),
            "conv1d: a residual from operand planes (res_hi) is only supported by the CTA-pair kernel, which this shape "
            "does not qualify for");
@@ -1839,6 +1917,23 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
   const uint32_t abox[3] = {UM_BK, UM_BM, 1};
   const CUtensorMap mAh = make_map(d.in_hi, 3, adims, astr, abox);
   const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox);
+  if (d_in.impl == 3) {
+    // near-fp32 chunked accumulation (see the kernel comment): 4 (slab, tap) iterations = 16 accumulations per chunk
+    PT_CHECK(!d2_in, "conv1d: the chunked tcgen05 mode has no dual-epilogue form");
+    using SMc = UmmaSmem<UM_BN>;
+    const size_t smem = (size_t)UM_STAGES * SMc::STAGE_BYTES + 256 + UM_EPI_WARPS * 2048 + 1024;
+    auto kern = conv1d_umma_kernel<UM_BN, UM_STAGES, UM_NACC, 2, false>;
+    ensure_smem_optin((const void*)kern, (int)smem);
+    const long long n_tiles = (long long)n_mt * n_nt * d.B;
+    PT_CHECK(n_tiles < (1ll << 30), "conv1d: too many tiles");
+    const int grid = (int)std::min<long long>(n_tiles, num_sms);
+    OutMaps om0;
+    memset(&om0, 0, sizeof(om0));
+    kern<<<grid, UM_THREADS, smem, s>>>(mAh, mAl, mBh, mBl, om0, om0, d, d2, total_cout, vec ? 1 : 0, 0, n_mt, n_nt,
+                                        (int)n_tiles, umma_env().chunk_iters);
+    PT_LAUNCHED();
+    return;
+  }
   // epilogue output maps (per descriptor, with its own column count)
   pttspp_conv1d_desc e1 = d, e2 = d2;
   if (d2_in) e1.Cout = cout1;
@@ -1878,7 +1973,7 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
     PT_CHECK(n_tiles < (1ll << 30), "conv1d: too many tiles");
     const int grid = (int)std::min<long long>(n_tiles, num_sms);
     kern<<<grid, UM_THREADS, smem, s>>>(mAh, mAl, mBh64, mBl64, om, om2, d, d2, total_cout, vec ? 1 : 0, tma_out, n_mt,
-                                        nnt, (int)n_tiles);
+                                        nnt, (int)n_tiles, 0);
     PT_LAUNCHED();
     return;
   }
@@ -1893,7 +1988,7 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
   PT_CHECK(n_tiles < (1ll << 30), "conv1d: too many tiles");
   const int grid = (int)std::min<long long>(n_tiles, num_sms);
   kern<<<grid, UM_THREADS, smem, s>>>(mAh, mAl, mBh, mBl, om, om2, d, d2, d2_in ? cout1 : total_cout, vec ? 1 : 0, tma_out,
-                                      n_mt, n_nt, (int)n_tiles);
+                                      n_mt, n_nt, (int)n_tiles, 0);
   PT_LAUNCHED();
 }
 

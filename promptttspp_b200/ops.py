@@ -161,7 +161,7 @@ def pack_conv_weight_split(weight, g=None, interleave_halves=False, device=None)
 def conv1d_umma_cl(x_planes, w_split, Cout, bias=None, K=1, dil=1, pad=0, act=ACT_NONE, out_len=None, addend=None,
                    res=None, res_scale=1.0, alpha=1.0, beta=0.0, out=None, acc_scale=1.0, out_div=0.0,
                    emit_planes=False, plane_add=None, write_f32=True, _desc_only=False, res_planes=None,
-                   res_plane_sub=None, out_planes=None):
+                   res_plane_sub=None, out_planes=None, impl=2):
     """tcgen05 path on pre-split operands.  x_planes = (hi, lo) [B, T, Cin] fp16; w_split from
     pack_conv_weight_split.  Returns out (fp32) and/or (out_hi, out_lo)."""
     xh, xl = x_planes
@@ -191,7 +191,7 @@ def conv1d_umma_cl(x_planes, w_split, Cout, bias=None, K=1, dil=1, pad=0, act=AC
         d.res_plane_bs = res_planes[0].stride(0); d.res_plane_ld = res_planes[0].stride(1)
         d.res_plane_sub = None if res_plane_sub is None else res_plane_sub.data_ptr()
     d.res_scale = res_scale; d.alpha = alpha; d.beta = beta; d.out_div = out_div
-    d.B = B; d.impl = 2
+    d.B = B; d.impl = impl  # 2 = tcgen05, 3 = tcgen05 with chunked near-fp32 accumulation
     planes = None
     if emit_planes:
         if out_planes is not None:  # caller-provided (e.g. in place over the residual planes)

@@ -254,3 +254,35 @@ def test_conv1d_umma_dual_residual_from_planes(ops, monkeypatch, B, T):
     y_next = yp[0].float() + yp[1].float()
     assert float((_bct(y_next) - (h_ref + nxt[None, :, None])).abs().max()) < 3e-5
     assert float((_bct(sbuf) - skip_ref).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("Cin,Cout", [(256, 1024), (1024, 256)])
+def test_conv1d_umma_chunked_accumulation_is_fp32_class(ops, Cin, Cout):
+    """conv1d impl 3 (the text encoder's k9 feed-forward convs, multi_layer_conv.py:52-67): chunks of 16 tensor-core
+    accumulations summed in round-to-nearest fp32.  Against a float64 reference its error must be in the class of the
+    fp32 CUDA-core kernel's (it feeds the integer duration rounding) and well below the plain tcgen05 accumulation's."""
+    g = torch.Generator().manual_seed(Cin)
+    B, T, K = 4, 256, 9
+    lens = torch.tensor([256, 131, 200, 77])
+    x = torch.randn(B, Cin, T, generator=g)
+    x = x * (torch.arange(T)[None, None] < lens[:, None, None])
+    w = torch.randn(Cout, Cin, K, generator=g) / math.sqrt(Cin * K)
+    b = torch.randn(Cout, generator=g) * 0.1
+    ref = torch.relu(F.conv1d(x.double(), w.double(), b.double(), padding=4)) * (torch.arange(T)[None, None] < lens[:, None, None])
+    planes = ops.split_f16(_cl(x))
+    ws = ops.pack_conv_weight_split(w, device="cuda")
+    kw = dict(bias=b.cuda(), K=K, dil=1, pad=4, act=ops.ACT_RELU, out_len=lens.cuda())
+    out3, pl3 = ops.conv1d_umma_cl(planes, ws, Cout, impl=3, emit_planes=True, **kw)
+    out2, _ = ops.conv1d_umma_cl(planes, ws, Cout, impl=2, **kw)
+    out1 = ops.conv1d_cl(_cl(x), ops.pack_conv_weight(w, device="cuda"), Cout, impl=1, **kw)
+    e3 = float((_bct(out3).double() - ref).abs().max())
+    e2 = float((_bct(out2).double() - ref).abs().max())
+    e1 = float((_bct(out1).double() - ref).abs().max())
+    m3 = float((_bct(out3).double() - ref).abs().mean())
+    m1 = float((_bct(out1).double() - ref).abs().mean())
+    print(f"k9 {Cin}->{Cout}: max-abs err vs float64: fp32 CUDA cores {e1:.2e} (mean {m1:.2e}), tcgen05 chunked {e3:.2e} "
+          f"(mean {m3:.2e}), tcgen05 plain {e2:.2e}")
+    assert e3 < 3.0 * e1 + 2e-7 and m3 < 3.0 * m1 + 5e-8
+    rec = pl3[0].float() + pl3[1].float()
+    assert float((rec - out3).abs().max()) < 1e-6          # the emitted operand planes carry the same values
+    assert float(_bct(out3)[1, :, 131:].abs().max()) == 0  # rows past the utterance are zero (out_len mask)
