@@ -183,6 +183,10 @@ __global__ void __launch_bounds__(256) relpos_attn_kernel(const float* __restric
 
 }  // namespace
 
+bool relpos_attention_umma(const float* q, const float* k, const float* v, const float* p, const float* bias_u,
+                           const float* bias_v, const int64_t* lens, int B, int T, int H, int dk, int legacy, float* out,
+                           int ld_qkv, cudaStream_t s);  // attention_umma.cu
+
 void relpos_attention(const float* q, const float* k, const float* v, const float* p, const float* bias_u,
                       const float* bias_v, const int64_t* lens, int B, int T, int H, int dk, int legacy,
                       float* scratch, float* out, int ld_qkv, cudaStream_t s) {
@@ -192,6 +196,8 @@ void relpos_attention(const float* q, const float* k, const float* v, const floa
   if (B == 0 || T == 0) return;
   const int Tp = legacy ? T : 2 * T - 1;
   ProfScope prof(PROF_ATTENTION, s, 2.0 * B * H * (double)T * dk * (2.0 * T + Tp), 4.0 * 4.0 * B * (double)T * H * dk);
+  // fused tcgen05 kernel (d_k = 128, T <= 256): no scratch matrix, one launch
+  if (relpos_attention_umma(q, k, v, p, bias_u, bias_v, lens, B, T, H, dk, legacy, out, ld_qkv, s)) return;
   {
     const size_t smem = (size_t)2 * 32 * (dk + 1) * sizeof(float);
     if (smem > 48 * 1024)

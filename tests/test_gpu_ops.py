@@ -221,8 +221,10 @@ def test_duration_quantize_and_length_regulator_bit_exact(ops):
 
 
 @pytest.mark.parametrize("legacy", [True, False])
-@pytest.mark.parametrize("T,lens", [(64, [64, 33, 5]), (37, [37, 36, 1]), (256, [256, 129, 17])])
+@pytest.mark.parametrize("T,lens", [(64, [64, 33, 5]), (37, [37, 36, 1]), (256, [256, 129, 17]), (200, [131, 200, 128, 129]),
+                                    (129, [129, 2]), (300, [300, 77])])
 def test_relpos_attention(ops, legacy, T, lens):
+    """T <= 256: the fused tcgen05 kernel (csrc/attention_umma.cu); T = 300: the CUDA-core fallback (csrc/attention.cu)."""
     g = torch.Generator().manual_seed(T + int(legacy))
     H, dk = 2, 128
     B = len(lens)
@@ -243,7 +245,9 @@ def test_relpos_attention(ops, legacy, T, lens):
     attn = torch.softmax(scores, dim=-1).masked_fill(m, 0.0)
     ref = torch.matmul(attn, vh).transpose(1, 2).reshape(B, T, H * dk)
     out = ops.relpos_attention(q.cuda(), k.cuda(), v.cuda(), p.cuda(), bu.cuda(), bv.cuda(), lens.cuda(), H, legacy)
-    assert torch.allclose(out.cpu(), ref, atol=5e-5), float((out.cpu() - ref).abs().max())
+    err = float((out.cpu() - ref).abs().max())
+    print(f"relpos attention T={T} legacy={legacy}: max-abs err {err:.2e}")
+    assert torch.isfinite(out).all() and err < 2e-5, err
 
 
 def test_lowpass_filter_matches_reference_golden(golden_dir):
