@@ -196,6 +196,12 @@ int pttspp_layernorm_cl(const pttspp_layernorm_desc* d, pttspp_stream_t stream);
  * checkpoint's `up.filter` / `down.lowpass.filter` buffers); log_alpha: [C]. */
 int pttspp_aa_snake_cl(const float* x, float* y, int B, int L, int C, const float* log_alpha,
                        const float* up_filter, const float* down_filter, pttspp_stream_t stream);
+/* The same activation through the channel-pair kernel (two adjacent channels per thread in packed fp32x2 registers, a
+ * rolling strip without halo recomputation): what the BigVGAN handle uses.  PRECONDITION: both filters are exactly
+ * symmetric, f[k] == f[11-k] (true for the reference's Kaiser sinc, layers/activations.py:36-71); C even.  Every
+ * channel's result is then bit-identical to pttspp_aa_snake_cl's. */
+int pttspp_aa_snake_pair_cl(const float* x, float* y, int B, int L, int C, const float* log_alpha,
+                            const float* up_filter, const float* down_filter, pttspp_stream_t stream);
 
 /* Duration quantisation + length regulator.
  *   dur[b][i] = (i < len[b]) ? max(rint(exp(log_d[b][i])), 1) : 0    (variance_adaptor.py:179-181)

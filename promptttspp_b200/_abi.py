@@ -123,6 +123,8 @@ SIGNATURES = {
     "pttspp_layernorm_cl": (C.c_int, [C.POINTER(LayerNormDesc), C.c_void_p]),
     "pttspp_aa_snake_cl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
+    "pttspp_aa_snake_pair_cl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
     "pttspp_duration_quantize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                            C.c_void_p]),
     "pttspp_length_regulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

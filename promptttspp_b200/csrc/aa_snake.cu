@@ -118,15 +118,190 @@ __global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__
   else aa_snake_strip<true>(xb, y, y_hi, y_lo, ob, t0, L, C, f2, g, a2, inv_alpha);
 }
 
+
+// ---- channel-pair kernel (the production path) ----------------------------------------------------------------------
+// Same arithmetic, two adjacent channels per thread in packed fp32x2 registers (Blackwell's FFMA2 / FMUL2 / FADD2 halve the
+// instruction count of this instruction-bound kernel) and a ROLLING strip: a thread walks AP_NB blocks of AP_TB outputs,
+// carrying the 10 up-sampled values and 5 inputs that neighbouring blocks share instead of recomputing / reloading the
+// halo (the strip kernel above re-reads 26 inputs and recomputes 42 up-sampled values per 16 outputs: 1.6x read
+// amplification).  Needs exactly symmetric filters, f[k] == f[11-k] (true for the reference's Kaiser sinc: checked on the
+// host where the filters are loaded): 6 + 6 packed coefficients stay in registers.  With symmetric filters every
+// channel's result is bit-identical to the strip kernel's (same operation order).
+constexpr int AP_TB = 8;            // outputs per block
+constexpr int AP_NB = 8;            // blocks per thread
+constexpr int AP_STRIP = AP_TB * AP_NB;
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// s = u + sin^2(alpha * u) / (alpha + 1e-9), both channels (same operations as the strip kernel, packed where possible)
+__device__ __forceinline__ f32x2 snake2(f32x2 u, f32x2 a2, f32x2 inv_alpha) {
+  const f32x2 r = mul2(u, a2);
+  float r0, r1;
+  upk2(r, r0, r1);
+  const f32x2 frac = fma2(pk2(rintf(r0), rintf(r1)), pk2(-1.f, -1.f), r);  // r - rint(r): exact
+  float f0, f1;
+  upk2(mul2(frac, pk2(6.28318530717958648f, 6.28318530717958648f)), f0, f1);
+  const f32x2 sn = pk2(__sinf(f0), __sinf(f1));
+  return fma2(mul2(inv_alpha, sn), sn, u);
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void aa_pair_block(const float* __restrict__ xb, float* __restrict__ y, __half* __restrict__ y_hi,
+                                              __half* __restrict__ y_lo, int64_t ob, int tb, int L, int C,
+                                              f32x2 (&sv)[2 * AP_TB + 10], f32x2 (&xw)[AP_TB + 5], const f32x2 (&e)[6],
+                                              const f32x2 (&g)[6], f32x2 a2, f32x2 inv_alpha) {
+  // new inputs x[tb + 5 .. tb + TB + 4]
+#pragma unroll
+  for (int i = 0; i < AP_TB; ++i) {
+    int l = tb + 5 + i;
+    if (EDGE) l = l > L - 1 ? L - 1 : l;
+    xw[5 + i] = *reinterpret_cast<const f32x2*>(xb + (int64_t)l * C);
+  }
+  // new up-sampled values: sv[i] <-> index 2*tb - 5 + i, i = 10 .. 2*TB + 9
+#pragma unroll
+  for (int i = 10; i < 2 * AP_TB + 10; ++i) {
+    f32x2 u = pk2(0.f, 0.f);
+    if ((i & 1) == 0) {
+#pragma unroll
+      for (int dd = 0; dd < 6; ++dd) u = fma2(xw[i / 2 + dd - 5], e[dd], u);          // f2[10 - 2d]
+    } else {
+#pragma unroll
+      for (int dd = 0; dd < 6; ++dd) u = fma2(xw[(i - 1) / 2 + dd - 5], e[5 - dd], u);  // f2[11 - 2d] == f2[2d]
+    }
+    sv[i] = snake2(u, a2, inv_alpha);
+  }
+  if (EDGE) {
+    const int imax = 2 * (L - tb) + 4;  // strip index of up-sampled sample 2L-1: later ones repeat it
+#pragma unroll
+    for (int i = 10; i < 2 * AP_TB + 10; ++i)
+      if (i > imax) sv[i] = sv[i - 1];
+  }
+#pragma unroll
+  for (int t = 0; t < AP_TB; ++t) {
+    if (!EDGE || tb + t < L) {
+      f32x2 acc = pk2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 12; ++k) acc = fma2(sv[2 * t + k], g[k < 6 ? k : 11 - k], acc);
+      float a0, a1;
+      upk2(acc, a0, a1);
+      const int64_t o = ob + (int64_t)t * C;
+      if (y) *reinterpret_cast<float2*>(y + o) = make_float2(a0, a1);
+      if (y_hi) {
+        const __half2 h = __floats2half2_rn(a0, a1);
+        const float2 hf = __half22float2(h);
+        *reinterpret_cast<__half2*>(y_hi + o) = h;
+        *reinterpret_cast<__half2*>(y_lo + o) = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+      }
+    }
+  }
+  // carry the shared halo into the next block
+#pragma unroll
+  for (int i = 0; i < 10; ++i) sv[i] = sv[2 * AP_TB + i];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) xw[i] = xw[AP_TB + i];
+}
+
+__global__ void __launch_bounds__(256) aa_snake_pair_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                            __half* __restrict__ y_hi, __half* __restrict__ y_lo, int L,
+                                                            int C, int n_strips, const float* __restrict__ log_alpha,
+                                                            const float* __restrict__ up_f,
+                                                            const float* __restrict__ down_f) {
+  const int half_c = C >> 1;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cp = (int)(gid % half_c);
+  const long long strip_ll = gid / half_c;  // blockIdx.y = utterance
+  if (strip_ll >= n_strips) return;
+  const int strip = (int)strip_ll;
+  const int c = 2 * cp;
+  const int t0 = strip * AP_STRIP;
+  f32x2 e[6], g[6];
+#pragma unroll
+  for (int d = 0; d < 6; ++d) {
+    const float ef = 2.f * up_f[10 - 2 * d];
+    e[d] = pk2(ef, ef);
+    g[d] = pk2(down_f[d], down_f[d]);
+  }
+  const float al0 = expf(log_alpha[c]), al1 = expf(log_alpha[c + 1]);
+  const f32x2 inv_alpha = pk2(1.f / (al0 + 1e-9f), 1.f / (al1 + 1e-9f));
+  const f32x2 a2 = pk2(al0 * 0.15915494309189535f, al1 * 0.15915494309189535f);
+  const float* xb = x + (int64_t)blockIdx.y * L * C + c;
+  f32x2 sv[2 * AP_TB + 10], xw[AP_TB + 5];
+  // prologue: the 10 up-sampled values in front of the strip (indices 2*t0 - 5 .. 2*t0 + 4) from x[t0 - 5 .. t0 + 4]
+  {
+    f32x2 xs[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      int l = t0 - 5 + i;
+      l = l < 0 ? 0 : (l > L - 1 ? L - 1 : l);
+      xs[i] = *reinterpret_cast<const f32x2*>(xb + (int64_t)l * C);
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      f32x2 u = pk2(0.f, 0.f);
+      if ((i & 1) == 0) {
+#pragma unroll
+        for (int dd = 0; dd < 6; ++dd) u = fma2(xs[i / 2 + dd], e[dd], u);
+      } else {
+#pragma unroll
+        for (int dd = 0; dd < 6; ++dd) u = fma2(xs[(i - 1) / 2 + dd], e[5 - dd], u);
+      }
+      sv[i] = snake2(u, a2, inv_alpha);
+    }
+    // replicate padding of the up-sampled signal at both ends of the utterance
+#pragma unroll
+    for (int i = 4; i >= 0; --i)
+      if (2 * t0 - 5 + i < 0) sv[i] = sv[i + 1];
+    const int imax = 2 * (L - t0) + 4;
+#pragma unroll
+    for (int i = 1; i < 10; ++i)
+      if (i > imax) sv[i] = sv[i - 1];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) xw[i] = xs[5 + i];
+  }
+  const int64_t ob0 = (int64_t)blockIdx.y * L * C + c;
+#pragma unroll 1
+  for (int blk = 0; blk < AP_NB; ++blk) {
+    const int tb = t0 + blk * AP_TB;
+    if (tb >= L) break;
+    const int64_t ob = ob0 + (int64_t)tb * C;
+    if (tb + AP_TB + 4 <= L - 1) aa_pair_block<false>(xb, y, y_hi, y_lo, ob, tb, L, C, sv, xw, e, g, a2, inv_alpha);
+    else aa_pair_block<true>(xb, y, y_hi, y_lo, ob, tb, L, C, sv, xw, e, g, a2, inv_alpha);
+  }
+}
+
 }  // namespace
 
 void aa_snake_cl(const float* x, float* y, int B, int L, int C, const float* log_alpha, const float* up_f,
-                 const float* down_f, cudaStream_t s, void* y_hi, void* y_lo) {
+                 const float* down_f, cudaStream_t s, void* y_hi, void* y_lo, int symmetric_filters) {
   PT_CHECK(x && (y || y_hi) && log_alpha && up_f && down_f, "aa_snake: null pointer");
   PT_CHECK(!y_hi || y_lo, "aa_snake: y_hi without y_lo");
   PT_CHECK(x != y, "aa_snake: in-place operation is not supported");
   PT_CHECK(B >= 1 && B <= 65535 && L >= 1 && C >= 1, "aa_snake: bad shape");
   ProfScope prof(PROF_AA_SNAKE, s, 0.0, 2.0 * 4.0 * B * (double)L * C);
+  auto a8 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7) == 0; };
+  if (symmetric_filters && C % 2 == 0 && a8(x) && (!y || a8(y)) && (!y_hi || (a8(y_hi) && a8(y_lo)))) {
+    const int n_strips = ceil_div(L, AP_STRIP);
+    const long long threads = (long long)(C / 2) * n_strips;
+    dim3 grid((unsigned)ceil_div64(threads, 256), B);
+    aa_snake_pair_kernel<<<grid, 256, 0, s>>>(x, y, (__half*)y_hi, (__half*)y_lo, L, C, n_strips, log_alpha, up_f, down_f);
+    PT_LAUNCHED();
+    return;
+  }
   dim3 block(32, 8);
   dim3 grid(ceil_div(C, 32), ceil_div(L, 8 * TT), B);
   PT_CHECK(grid.y <= 65535, "aa_snake: L=%d too long for one launch", L);
@@ -140,5 +315,13 @@ extern "C" int pttspp_aa_snake_cl(const float* x, float* y, int B, int L, int C,
                                   const float* up_filter, const float* down_filter, pttspp_stream_t stream) {
   PT_API_BEGIN
   pttspp::aa_snake_cl(x, y, B, L, C, log_alpha, up_filter, down_filter, (cudaStream_t)stream);
+  PT_API_END
+}
+
+extern "C" int pttspp_aa_snake_pair_cl(const float* x, float* y, int B, int L, int C, const float* log_alpha,
+                                       const float* up_filter, const float* down_filter, pttspp_stream_t stream) {
+  PT_API_BEGIN
+  PT_CHECK(C % 2 == 0, "aa_snake_pair: the channel-pair kernel needs an even channel count (got %d)", C);
+  pttspp::aa_snake_cl(x, y, B, L, C, log_alpha, up_filter, down_filter, (cudaStream_t)stream, nullptr, nullptr, 1);
   PT_API_END
 }

@@ -14,6 +14,7 @@ struct AAParams {
   float* log_alpha = nullptr;
   float* up_f = nullptr;
   float* down_f = nullptr;
+  int sym = 0;  // both filters exactly symmetric (f[k] == f[11-k]): the channel-pair AA kernel applies
 };
 
 struct AMPLayerW {
@@ -60,6 +61,11 @@ AAParams load_aa(const TensorStore& st, DeviceBuffers& dev, const std::string& p
   a.log_alpha = dev.upload(st.get(prefix + ".act.alpha", C).data);
   a.up_f = dev.upload(st.get(prefix + ".up.filter", 12).data);
   a.down_f = dev.upload(st.get(prefix + ".down.lowpass.filter", 12).data);
+  const auto& uf = st.get(prefix + ".up.filter", 12).data;
+  const auto& df = st.get(prefix + ".down.lowpass.filter", 12).data;
+  a.sym = 1;
+  for (int k = 0; k < 6; ++k)
+    if (uf[k] != uf[11 - k] || df[k] != df[11 - k]) a.sym = 0;
   return a;
 }
 
@@ -507,15 +513,15 @@ static void bigvgan_forward_impl(pttspp_bigvgan_t* h, const float* mel, const fl
         auto use_planes = [&](pttspp_conv1d_desc& q, const PackedConv& pc) {
           q.in_hi = ph; q.in_lo = pl; q.w_hi = pc.w_hi; q.w_lo = pc.w_lo; q.w_scale_inv = pc.w_scale_inv; q.impl = 2;
         };
-        if (um) aa_snake_cl(cur, nullptr, B, L, C, w.act1.log_alpha, w.act1.up_f, w.act1.down_f, s, ph, pl);
-        else aa_snake_cl(cur, t1, B, L, C, w.act1.log_alpha, w.act1.up_f, w.act1.down_f, s);
+        if (um) aa_snake_cl(cur, nullptr, B, L, C, w.act1.log_alpha, w.act1.up_f, w.act1.down_f, s, ph, pl, w.act1.sym);
+        else aa_snake_cl(cur, t1, B, L, C, w.act1.log_alpha, w.act1.up_f, w.act1.down_f, s, nullptr, nullptr, w.act1.sym);
         {
           auto d = conv_desc(w.conv1, t1, B, L, t2);
           if (um) use_planes(d, w.conv1);
           conv1d_cl(d, s);
         }
-        if (um) aa_snake_cl(t2, nullptr, B, L, C, w.act2.log_alpha, w.act2.up_f, w.act2.down_f, s, ph, pl);
-        else aa_snake_cl(t2, t1, B, L, C, w.act2.log_alpha, w.act2.up_f, w.act2.down_f, s);
+        if (um) aa_snake_cl(t2, nullptr, B, L, C, w.act2.log_alpha, w.act2.up_f, w.act2.down_f, s, ph, pl, w.act2.sym);
+        else aa_snake_cl(t2, t1, B, L, C, w.act2.log_alpha, w.act2.up_f, w.act2.down_f, s, nullptr, nullptr, w.act2.sym);
         const bool last = (l == c.num_dilations - 1);
         float* dst = last ? bxs : ((cur == bA) ? bB : bA);
         auto d = conv_desc(w.conv2, t1, B, L, dst);
@@ -541,7 +547,8 @@ static void bigvgan_forward_impl(pttspp_bigvgan_t* h, const float* mel, const fl
     // the next stage's transposed conv reads bxs and writes bx: no aliasing
   }
   const int Cl = c.upsample_initial_channel >> c.num_upsamples;
-  aa_snake_cl(hcur, t1, B, L, Cl, h->act_post.log_alpha, h->act_post.up_f, h->act_post.down_f, s);
+  aa_snake_cl(hcur, t1, B, L, Cl, h->act_post.log_alpha, h->act_post.up_f, h->act_post.down_f, s, nullptr, nullptr,
+              h->act_post.sym);
   if (h->post_w && Cl == 32) {
     conv_post_tanh(t1, h->post_w, h->conv_post.bias, wav, B, L, 7, s);
   } else {

@@ -95,8 +95,10 @@ void pack_convtr_weight(const float* v, const float* g, int Cin, int Cout, int K
 void conv1d_umma_dual_cl(const pttspp_conv1d_desc& d1, const pttspp_conv1d_desc& d2, cudaStream_t s);
 void layernorm_cl(const pttspp_layernorm_desc& d, cudaStream_t s);
 // y (fp32) and/or y_hi/y_lo (split-fp16 planes, same indexing) receive the result
+// symmetric_filters: the caller has checked f[k] == f[11-k] for both filters on the host (selects the channel-pair kernel)
 void aa_snake_cl(const float* x, float* y, int B, int L, int C, const float* log_alpha, const float* up_f,
-                 const float* down_f, cudaStream_t s, void* y_hi = nullptr, void* y_lo = nullptr);
+                 const float* down_f, cudaStream_t s, void* y_hi = nullptr, void* y_lo = nullptr,
+                 int symmetric_filters = 0);
 void duration_quantize(const float* log_d, const int64_t* phone_len, int B, int Tx, int64_t* dur,
                        int64_t* frame_len, cudaStream_t s);
 void length_regulate(const float* x, const int64_t* dur, int B, int Tx, int C, int Ty, float* out,

@@ -1472,6 +1472,7 @@ struct UmmaEnv {
   char pair = 0, rl = 0, nacc = 0, epi = 0;  // first character of the variable, 0 when unset
   bool no_tma_store = false, debug = false, no_wres64 = false, a_stationary = false;
   int order = 0;
+  bool longk_narrow = false;
   int chunk_iters = 4;  // chunked mode: (slab, tap) iterations per accumulator buffer (4 x 64 channels = 16 MMA steps)
   void load() {
     auto first = [](const char* name) -> char { const char* e = getenv(name); return e ? e[0] : (char)0; };
@@ -1485,6 +1486,8 @@ struct UmmaEnv {
     a_stationary = getenv("PTTSPP_UMMA_AS") != nullptr;
     const char* oe = getenv("PTTSPP_UMMA_ORDER");  // experiments: bits 0-1 MMA order, 4 no operand loads, 8 no stores, 16 no L2 prefetch
     order = oe ? atoi(oe) : 0;
+    const char* lk = getenv("PTTSPP_UMMA_LONGK");
+    longk_narrow = lk && lk[0] == 'n';
     const char* ce = getenv("PTTSPP_UMMA_CHUNK");
     chunk_iters = ce ? std::max(1, atoi(ce)) : 4;
   }
@@ -1917,7 +1920,11 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
   const uint32_t abox[3] = {UM_BK, UM_BM, 1};
   const CUtensorMap mAh = make_map(d.in_hi, 3, adims, astr, abox);
   const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox);
-  if (d_in.impl == 3) {
+  // Long contractions (> 64 tensor-core accumulations per accumulator) with >= 128 output columns also take the chunked
+  // kernel: 128-column tiles (half the activation re-reads of the 64-column round-robin variant below) and a bounded
+  // truncation bias.  PTTSPP_UMMA_LONGK=narrow keeps the old choice (A/B measurements).
+  const bool long_k_chunked = !d2_in && total_cout >= 128 && d.K * d.Cin / 16 > 64 && vec && !umma_env().longk_narrow;
+  if (d_in.impl == 3 || long_k_chunked) {
     // near-fp32 chunked accumulation (see the kernel comment): 4 (slab, tap) iterations = 16 accumulations per chunk
     PT_CHECK(!d2_in, "conv1d: the chunked tcgen05 mode has no dual-epilogue form");
     using SMc = UmmaSmem<UM_BN>;

@@ -245,7 +245,7 @@ class PromptTTSMDNDurCFG(nn.Module):
                 x_T = torch.randn((B, M, Ty), device=device)
                 z = torch.empty(K, B, M, Ty, device=device)
                 for i in range(K):
-                    z[i] = torch.randn((B, M, Ty), device=device)
+                    z[i].normal_()  # the same Philox draw as torch.randn((B, M, Ty)), written in place (no copy)
             mel = torch.empty(B, M, Ty, device=device)
             log_cf0 = torch.empty(B, 1, Ty, device=device)
             vuv = torch.empty(B, 1, Ty, device=device)

@@ -86,11 +86,13 @@ def layernorm_cl(x, gamma, beta, eps, in2=None, row_add=None, in_scale=1.0, in_l
     return out
 
 
-def aa_snake_cl(x, log_alpha, up_filter, down_filter):
+def aa_snake_cl(x, log_alpha, up_filter, down_filter, pair=False):
+    """pair=True: the channel-pair kernel (symmetric filters, even C) the BigVGAN handle runs."""
     _abi.require_cuda(x, "aa_snake_cl")
     B, L, Cc = x.shape
     y = torch.empty_like(x)
-    _abi.check(_abi.lib().pttspp_aa_snake_cl(_abi.ptr(x), _abi.ptr(y), B, L, Cc, _abi.ptr(log_alpha),
+    fn = _abi.lib().pttspp_aa_snake_pair_cl if pair else _abi.lib().pttspp_aa_snake_cl
+    _abi.check(fn(_abi.ptr(x), _abi.ptr(y), B, L, Cc, _abi.ptr(log_alpha),
                                              _abi.ptr(up_filter), _abi.ptr(down_filter), _abi.stream_ptr(x.device)))
     return y
 

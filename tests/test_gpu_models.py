@@ -205,6 +205,18 @@ def test_acoustic_default_rng_and_shapes():
         n = int(flen[b])
         assert torch.count_nonzero(mel[b, :, n:]) == 0 and torch.count_nonzero(log_cf0[b, :, n:]) == 0
     assert isinstance(model.infer(phoneme[:1, :10].cuda(), style_prompt="one"), torch.Tensor)
+    # the default draw consumes the CUDA generator exactly like the reference's call sequence (model.py:191 randn_like,
+    # diffusion.py:332 randn(shape), :218 one randn per step): injecting that sequence gives the same mel bit for bit
+    from promptttspp_b200.models.prompttts_mdn_v2_final.model import InferNoise
+
+    Ty = mel.shape[-1]
+    torch.manual_seed(123)
+    z_style = torch.randn(3, 1, 256, device="cuda")
+    x_T = torch.randn((3, 80, Ty), device="cuda")
+    z = torch.stack([torch.randn((3, 80, Ty), device="cuda") for _ in range(8)])
+    again = model.infer_batch(phoneme.cuda(), lengths.cuda(), style_prompt=["a", "b", "c"], return_f0=True,
+                              noise=InferNoise(z_style, x_T, z))
+    assert torch.equal(again[0], mel)
 
 
 # ---- F0-aware vocoder (the vocoder app.py / synthesize.py instantiate by default) ----

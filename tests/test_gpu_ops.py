@@ -186,6 +186,25 @@ def test_aa_snake(ops, B, C, L):
     out = ops.aa_snake_cl(_cl(x), alpha.view(-1).cuda(), act.up.filter.view(-1).cuda(),
                           act.down.lowpass.filter.view(-1).cuda())
     assert torch.allclose(_bct(out), ref, atol=2e-5), float((_bct(out) - ref).abs().max())
+    # the channel-pair kernel the BigVGAN handle runs (packed fp32x2, rolling strips): bit-identical per channel
+    pair = ops.aa_snake_cl(_cl(x), alpha.view(-1).cuda(), act.up.filter.view(-1).cuda(),
+                           act.down.lowpass.filter.view(-1).cuda(), pair=True)
+    assert torch.equal(pair, out), float((pair - out).abs().max())
+
+
+@pytest.mark.parametrize("B,C,L", [(2, 64, 63), (1, 32, 64), (3, 32, 65), (1, 128, 129), (2, 32, 4097)])
+def test_aa_snake_pair_kernel_strip_boundaries(ops, B, C, L):
+    """strip (64 outputs) and block (8 outputs) boundaries of the rolling channel-pair kernel against the oracle"""
+    from promptttspp_b200.layers.activations import AntiAliasActivation
+
+    g = torch.Generator().manual_seed(L + C)
+    act = AntiAliasActivation(C)
+    x = torch.randn(B, C, L, generator=g) * 2
+    alpha = torch.rand(1, C, 1, generator=g) - 0.5
+    ref = oracle.aa_activation(x, alpha, act.up.filter, act.down.lowpass.filter)
+    out = ops.aa_snake_cl(_cl(x), alpha.view(-1).cuda(), act.up.filter.view(-1).cuda(),
+                          act.down.lowpass.filter.view(-1).cuda(), pair=True)
+    assert torch.allclose(_bct(out), ref, atol=2e-5), float((_bct(out) - ref).abs().max())
 
 
 def test_duration_quantize_and_length_regulator_bit_exact(ops):
