@@ -5,14 +5,20 @@ utterance).  `BatchedSynthesizer` takes a list of requests, cuts it into length-
 budget (the trainer's `batch_by_size` rule, `promptttspp/datasets/utils.py:55-112`: a batch is full when
 `(n + 1) * longest > max_tokens` or `n == max_sentences`), runs acoustic model -> f0 post-processing -> vocoder per
 batch exactly as `app.py:56-81` does for one utterance, and returns the waveforms in request order.  With
-`world_size > 1` each rank serves its round-robin share of the length-sorted requests (`dist.shard_indices`).
+`world_size > 1` each rank serves its share of the BATCHES (`dist.shard_batches`), so an utterance sits in the same batch
+whatever the world size.
 """
+import csv
+import queue
+import struct
+import threading
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence
+from pathlib import Path
+from typing import Callable, Dict, Iterable, List, Optional, Sequence
 
 import torch
 
-from .dist import pad_batch, shard_indices
+from .dist import pad_batch, shard_batches
 from .utils.model import lowpass_filter
 
 
@@ -47,28 +53,157 @@ class MelStats:
     mean: float = 0.0
     std: float = 1.0
 
+    @classmethod
+    def from_yaml(cls, path) -> "MelStats":
+        """`stats.yaml` as egs/proposed/bin/compute_mel.py:60-68 writes it (keys min, max, mean, std, var) and
+        app.py:133 / synthesize.py:102 read it."""
+        import yaml
+
+        with open(path, "r") as f:
+            d = yaml.safe_load(f)
+        return cls(mean=float(d["mean"]), std=float(d["std"]))
+
+
+# ---- the evaluation-set formats of egs/proposed/bin/synthesize.py -----------------------------------------------------
+EVAL_COLUMNS = ["spk_id", "item_name", "gender", "pitch", "speaking_speed", "energy", "style_prompt", "style_prompt_key",
+                "seq"]  # synthesize.py:118-130
+
+
+def read_eval_csv(path) -> List[dict]:
+    """The label file of synthesize.py:131-135: one request per row; `seq` (space-separated phoneme ids) becomes a
+    LongTensor under "phonemes"."""
+    rows = []
+    with open(path, newline="") as f:
+        for r in csv.DictReader(f):
+            missing = [c for c in EVAL_COLUMNS if c not in r]
+            if missing:
+                raise ValueError(f"{path}: missing columns {missing}")
+            row = {c: r[c] for c in EVAL_COLUMNS}
+            row["phonemes"] = torch.tensor([int(t) for t in r["seq"].split()], dtype=torch.int64)
+            rows.append(row)
+    return rows
+
+
+def read_prompt_candidate(path) -> Dict[str, List[str]]:
+    """`style_key|prompt a; prompt b; ...` lines -> {style_key: [lower-cased prompts]} (synthesize.py:64-76)."""
+    out = {}
+    with open(path) as f:
+        for line in f:
+            line = line.rstrip("\n")
+            if not line:
+                continue
+            key, prompts = line.split("|", 1)
+            out[key] = [p.lower().strip() for p in prompts.split(";")]
+    return out
+
+
+def read_spk_prompt_candidate(path) -> Dict[str, List[str]]:
+    """`spk|word,word,...` lines -> {spk: [words]} (synthesize.py:79-84)."""
+    out = {}
+    with open(path) as f:
+        for line in f:
+            line = line.rstrip("\n")
+            if line:
+                spk, words = line.split("|", 1)
+                out[spk] = words.split(",")
+    return out
+
+
+def add_spk_prompt(style_prompt: str, words: str) -> str:
+    """synthesize.py:87-90"""
+    return f"{style_prompt}. The speaker identity can be described as {words}."
+
+
+def eval_prompts(rows: Sequence[dict], prompt_candidate, spk_prompt_candidate, use_spk_prompt=True) -> List[str]:
+    """The prompt string of every evaluation row (synthesize.py:137-150)."""
+    prompts = []
+    for r in rows:
+        style = prompt_candidate[r["style_prompt_key"]][0]
+        spk = r["spk_id"]
+        if use_spk_prompt and spk in spk_prompt_candidate:
+            style = add_spk_prompt(style, ", ".join(spk_prompt_candidate[spk]))
+        prompts.append(style)
+    return prompts
+
+
+def write_wav(path, wav: torch.Tensor, sample_rate: int):
+    """Mono float32 RIFF/WAVE (format tag 3), what torchaudio.save(path, float tensor, sr) produces by default
+    (synthesize.py:195, :214) -- written with the standard library only."""
+    data = wav.detach().to(torch.float32).reshape(-1).cpu().numpy().astype("<f4").tobytes()
+    hdr = b"RIFF" + struct.pack("<I", 50 + len(data)) + b"WAVE"
+    hdr += b"fmt " + struct.pack("<IHHIIHHH", 18, 3, 1, sample_rate, sample_rate * 4, 4, 32, 0)
+    hdr += b"fact" + struct.pack("<II", 4, len(data) // 4)
+    hdr += b"data" + struct.pack("<I", len(data))
+    with open(path, "wb") as f:
+        f.write(hdr + data)
+
+
+class WavWriter:
+    """Streamed write-back: finished waveforms are handed to a background thread that encodes and writes them while the
+    GPU already runs the next batch (the reference's loop blocks on torchaudio.save per utterance)."""
+
+    def __init__(self, out_dir, sample_rate=24000, namer: Optional[Callable[[int], str]] = None, depth: int = 64):
+        self.out_dir, self.sample_rate = Path(out_dir), sample_rate
+        self.namer = namer or (lambda i: f"{i:06d}.wav")
+        self.q: "queue.Queue" = queue.Queue(maxsize=depth)
+        self.error = None
+        self.written: List[Path] = []
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                return
+            try:
+                i, wav = item
+                path = self.out_dir / self.namer(i)
+                path.parent.mkdir(parents=True, exist_ok=True)
+                write_wav(path, wav, self.sample_rate)
+                self.written.append(path)
+            except Exception as e:  # surfaced by close()
+                self.error = e
+
+    def put(self, index: int, wav: torch.Tensor):
+        self.q.put((index, wav))
+
+    def close(self):
+        self.q.put(None)
+        self.thread.join()
+        if self.error is not None:
+            raise self.error
+        return self.written
+
 
 class BatchedSynthesizer:
     def __init__(self, model, vocoder, stats: MelStats = MelStats(), max_tokens: int = 4096,
                  max_sentences: Optional[int] = 32, use_lowpass: bool = True, noise_scale: float = 0.5,
-                 frame_rate: int = 100):
+                 frame_rate: int = 100, seed: Optional[int] = None):
         self.model, self.vocoder, self.stats = model, vocoder, stats
         self.max_tokens, self.max_sentences = max_tokens, max_sentences
         self.use_lowpass, self.noise_scale, self.frame_rate = use_lowpass, noise_scale, frame_rate
         self.f0_aware = hasattr(vocoder, "m_source")
+        # seed: every batch draws its noise from torch.manual_seed(seed + first request index of the batch), so a
+        # request's audio does not depend on which rank (or in which order) its batch is served
+        self.seed = seed
 
     @torch.no_grad()
     def synthesize(self, phonemes: Sequence[torch.Tensor], style_prompts, world_size: int = 1, rank: int = 0,
-                   device=None) -> Dict[int, torch.Tensor]:
+                   device=None, sink: Optional[Callable[[int, torch.Tensor], None]] = None) -> Dict[int, torch.Tensor]:
         """phonemes: list of 1-D LongTensors (text_to_sequence output); style_prompts: list of strings or a tensor
         [N, prompt_dim] of sentence embeddings.  Returns {request index: waveform [samples] on the host} for the requests
-        this rank owns (all of them when world_size == 1)."""
+        this rank owns (all of them when world_size == 1).  `sink(index, waveform)` -- e.g. `WavWriter.put` -- receives
+        every waveform as soon as its batch has left the device (streamed write-back)."""
         device = torch.device(device) if device is not None else next(self.model.parameters()).device
         lengths = [int(p.numel()) for p in phonemes]
-        mine = shard_indices(lengths, world_size, rank)
         hop = getattr(self.vocoder, "hop", 240)
         out: Dict[int, torch.Tensor] = {}
-        for batch in token_buckets(lengths, self.max_tokens, self.max_sentences, mine):
+        # batches are cut from ALL requests and then dealt to the ranks: their composition does not depend on world_size
+        buckets = token_buckets(lengths, self.max_tokens, self.max_sentences)
+        for batch in shard_batches(buckets, lengths, world_size, rank):
+            if self.seed is not None:
+                torch.manual_seed(self.seed + batch[0])
             padded, lens = pad_batch([phonemes[i] for i in batch])
             padded, lens = padded.pin_memory().to(device, non_blocking=True), lens.pin_memory().to(device, non_blocking=True)
             if isinstance(style_prompts, torch.Tensor):
@@ -91,4 +226,13 @@ class BatchedSynthesizer:
             n_frames = frame_len.cpu().long().tolist()
             for b, i in enumerate(batch):
                 out[i] = wav[b, : n_frames[b] * hop].clone()
+                if sink is not None:
+                    sink(i, out[i])
         return out
+
+    def synthesize_texts(self, texts: Iterable[str], style_prompts, **kw) -> Dict[int, torch.Tensor]:
+        """Phoneme strings (g2p output, `HH AH0 L OW1 ...`) instead of id tensors: text.eng.text_to_sequence per request
+        (app.py:60-62), then `synthesize`."""
+        from .text import text_to_sequence
+
+        return self.synthesize([torch.tensor(text_to_sequence(t), dtype=torch.int64) for t in texts], style_prompts, **kw)

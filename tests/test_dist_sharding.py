@@ -24,6 +24,24 @@ def test_shards_are_a_balanced_partition():
         pdist.shard_indices(lengths, 2, 2)
 
 
+def test_batch_shards_keep_composition_and_balance():
+    """The batch list is cut once; ranks get whole batches (LPT on the padded cost): same composition at every world
+    size, disjoint cover, balanced within one batch."""
+    g = torch.Generator().manual_seed(6)
+    lengths = torch.randint(64, 257, (256,), generator=g).tolist()
+    batches = pdist.make_batches(range(256), lengths, 16)
+    cost = lambda b: len(b) * max(lengths[i] for i in b)  # noqa: E731
+    for world in (1, 2, 4, 8):
+        shards = [pdist.shard_batches(batches, lengths, world, r) for r in range(world)]
+        got = sorted(tuple(b) for s in shards for b in s)
+        assert got == sorted(tuple(b) for b in batches)               # every batch exactly once, unchanged
+        loads = [sum(cost(b) for b in s) for s in shards]
+        assert max(loads) - min(loads) <= max(cost(b) for b in batches)
+        assert shards == [pdist.shard_batches(batches, lengths, world, r) for r in range(world)]
+    with pytest.raises(ValueError):
+        pdist.shard_batches(batches, lengths, 2, 2)
+
+
 def test_batches_group_neighbouring_lengths_and_ragged_tail():
     lengths = [5, 50, 7, 48, 6, 49, 100]
     batches = pdist.make_batches(range(7), lengths, 3)
@@ -70,7 +88,9 @@ def test_world_size_2_gloo_matches_single_process():
         assert p.exitcode == 0
     merged = {}
     for rank, res, counts in got:
-        assert set(res) == set(pdist.shard_indices([p.numel() for p in phonemes], 2, rank))
+        lens = [p.numel() for p in phonemes]
+        mine = pdist.shard_batches(pdist.make_batches(range(19), lens, 4), lens, 2, rank)
+        assert set(res) == {i for b in mine for i in b}
         merged.update(res)
         assert counts == [single[i][0] for i in range(19)]  # every rank sees every frame count
     assert merged == single  # sharding must not change any utterance's result

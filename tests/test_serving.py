@@ -60,6 +60,12 @@ def test_batched_synthesizer_matches_single_calls():
     torch.manual_seed(0)
     again = srv.synthesize(phonemes, emb)
     assert all(torch.equal(out[i], again[i]) for i in out)
+    # seeded per batch + batch-level sharding: the merged output of two ranks equals the single-rank output bit for bit
+    srv2 = BatchedSynthesizer(model, voc, MelStats(mean=-5.0, std=2.0), max_tokens=30, max_sentences=4, seed=77)
+    one = srv2.synthesize(phonemes, emb)
+    two = dict(srv2.synthesize(phonemes, emb, world_size=2, rank=1))
+    two.update(srv2.synthesize(phonemes, emb, world_size=2, rank=0))
+    assert sorted(two) == sorted(one) and all(torch.equal(one[i], two[i]) for i in one)
 
 
 @pytest.mark.gpu
@@ -90,3 +96,45 @@ def test_batched_f0_path_equals_per_utterance_f0_path():
         s = lowpass_filter(log_cf0[b:b + 1, :, :n].contiguous().cuda(), 100, cutoff=20).exp()
         s[vuv[b:b + 1, :, :n].cuda() < 0.5] = 0
         assert torch.equal(f0[b:b + 1, :, :n], s)
+
+
+def test_eval_formats_roundtrip(tmp_path):
+    """stats.yaml, the evaluation CSV, the prompt candidate files (synthesize.py:64-150) and the wav writer."""
+    import struct
+
+    from promptttspp_b200.serving import (EVAL_COLUMNS, MelStats, WavWriter, eval_prompts, read_eval_csv,
+                                          read_prompt_candidate, read_spk_prompt_candidate)
+
+    (tmp_path / "stats.yaml").write_text("min: -11.5\nmax: 2.0\nmean: -5.25\nstd: 2.125\nvar: 4.515625\n")
+    st = MelStats.from_yaml(tmp_path / "stats.yaml")
+    assert (st.mean, st.std) == (-5.25, 2.125)
+    (tmp_path / "eval.csv").write_text(
+        ",".join(EVAL_COLUMNS + ["extra"]) + "\n"
+        + "p1,utt_a,F,high,fast,low,calm voice,k1,1 12 40 7 2,x\n"
+        + "p9,utt_b,M,low,slow,high,angry voice,k2,1 5 2,y\n")
+    rows = read_eval_csv(tmp_path / "eval.csv")
+    assert [r["item_name"] for r in rows] == ["utt_a", "utt_b"] and rows[0]["phonemes"].tolist() == [1, 12, 40, 7, 2]
+    (tmp_path / "prompts.txt").write_text("k1|A Calm Voice ; quiet\nk2|An angry voice\n")
+    (tmp_path / "spk.txt").write_text("p1|bright,young\n")
+    pc, sc = read_prompt_candidate(tmp_path / "prompts.txt"), read_spk_prompt_candidate(tmp_path / "spk.txt")
+    assert pc["k1"] == ["a calm voice", "quiet"] and sc == {"p1": ["bright", "young"]}
+    prompts = eval_prompts(rows, pc, sc)
+    assert prompts == ["a calm voice. The speaker identity can be described as bright, young.", "an angry voice"]
+    assert eval_prompts(rows, pc, sc, use_spk_prompt=False)[0] == "a calm voice"
+    w = WavWriter(tmp_path / "out", 24000, namer=lambda i: f"{rows[i]['spk_id']}/{rows[i]['item_name']}.wav")
+    wav = torch.linspace(-1, 1, 480)
+    w.put(0, wav)
+    w.put(1, wav[:100])
+    files = w.close()
+    assert sorted(p.name for p in files) == ["utt_a.wav", "utt_b.wav"]
+    raw = (tmp_path / "out" / "p1" / "utt_a.wav").read_bytes()
+    assert raw[:4] == b"RIFF" and raw[8:12] == b"WAVE" and struct.unpack("<H", raw[20:22])[0] == 3
+    body = torch.frombuffer(bytearray(raw[-480 * 4:]), dtype=torch.float32)
+    assert torch.equal(body, wav)
+    try:
+        import torchaudio
+
+        back, sr = torchaudio.load(str(tmp_path / "out" / "p1" / "utt_a.wav"))
+        assert sr == 24000 and torch.equal(back.view(-1), wav)
+    except (ImportError, RuntimeError):
+        pass
