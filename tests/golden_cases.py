@@ -36,6 +36,11 @@ TEXT_CASES = {
                       lengths=[256, 203, 141, 187, 250, 129, 233, 176, 198, 160, 221, 149, 244, 135, 212, 169]),
 }
 
+# the same text side with the training yaml's rel-pos flavour (RelPositionalEncoding, 2T-1 position rows): exercises the
+# two-window path of the fused attention kernel at T = 256
+TEXT_CASES["cfg2_text_new"] = dict(TEXT_CASES["cfg2_text"], rel_pos_type="new", weight_seed=1235, input_seed=4,
+                                   noise_seed=123)
+
 VOCODER_CASES = {
     "b2_t12": dict(weight_seed=4321, input_seed=3, B=2, T=12, remove_weight_norm=True),
     "b1_t33": dict(weight_seed=4321, input_seed=4, B=1, T=33),

@@ -97,10 +97,12 @@ def test_bigvgan_cfg3_batch_row_matches_reference_golden(golden_dir, vocoder):
     assert err < WAV_TOL
 
 
-def test_text_side_durations_bit_exact_cfg2(golden_dir):
-    """cfg2's text side, 3063 phonemes: integer durations bit-exact against the reference (VERDICT r1 #1c)."""
-    case = TEXT_CASES["cfg2_text"]
-    gold = {k: torch.from_numpy(v) for k, v in np.load(golden_dir / "text_cfg2_text.npz").items()}
+@pytest.mark.parametrize("name", list(TEXT_CASES))
+def test_text_side_durations_bit_exact_cfg2(golden_dir, name):
+    """cfg2's text side, 3063 phonemes, both rel-pos flavours (legacy: one position window in the fused attention
+    kernel; new: two windows): integer durations bit-exact against the reference (VERDICT r1 #1c)."""
+    case = TEXT_CASES[name]
+    gold = {k: torch.from_numpy(v) for k, v in np.load(golden_dir / f"text_{name}.npz").items()}
     phoneme, lengths, cls_emb = acoustic_inputs(case)
     model = build_acoustic(rel_pos_type=case["rel_pos_type"], bert=FixedPromptEmbedding(cls_emb), K_step=1)
     model.load_state_dict(synthetic_state_dict(model, seed=case["weight_seed"],
@@ -137,7 +139,7 @@ def test_text_side_durations_bit_exact_cfg2(golden_dir):
         assert float(gap[b, i]) < 2e-5, "a duration differs where the component arg-max is NOT a near-tie"
     valid = torch.arange(phoneme.shape[1])[None] < lengths[:, None]
     lerr = float(lerr_all[same & valid].max())
-    print(f"cfg2 text side: {int(lengths.sum())} phonemes, durations differing {len(diff)} (arg-max near-ties), "
+    print(f"{name}: {int(lengths.sum())} phonemes, durations differing {len(diff)} (arg-max near-ties), "
           f"log_d max err elsewhere {lerr:.3e}")
     assert len(diff) <= 3 and lerr < 1e-4
     if not diff:

@@ -71,12 +71,13 @@ def test_bigvgan_oracle_matches_reference(golden_dir, name):
         assert float((wav - torch.from_numpy(gold["wav_nowm"])).pow(2).mean().sqrt()) < 2e-6
 
 
-def test_text_side_oracle_matches_reference_cfg2(golden_dir):
+@pytest.mark.parametrize("name", list(TEXT_CASES))
+def test_text_side_oracle_matches_reference_cfg2(golden_dir, name):
     """cfg2's text side (B=16, 3063 phonemes): the oracle's integer durations are bit-exact against the reference."""
     from __graft_entry__ import _oracle_enc_state
 
-    case = TEXT_CASES["cfg2_text"]
-    gold = {k: torch.from_numpy(v) for k, v in np.load(golden_dir / "text_cfg2_text.npz").items()}
+    case = TEXT_CASES[name]
+    gold = {k: torch.from_numpy(v) for k, v in np.load(golden_dir / f"text_{name}.npz").items()}
     model = build_acoustic(rel_pos_type=case["rel_pos_type"], bert=FixedPromptEmbedding(torch.zeros(1, 768)), K_step=2)
     sd = synthetic_state_dict(model, seed=case["weight_seed"], frames_per_phoneme=case["frames_per_phoneme"])
     phoneme, lengths, cls_emb = acoustic_inputs(case)
