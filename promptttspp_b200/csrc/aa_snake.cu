@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__
 // amplification).  Needs exactly symmetric filters, f[k] == f[11-k] (true for the reference's Kaiser sinc: checked on the
 // host where the filters are loaded): 6 + 6 packed coefficients stay in registers.  With symmetric filters every
 // channel's result is bit-identical to the strip kernel's (same operation order).
-constexpr int AP_TB = 4;            // outputs per block
-constexpr int AP_NB = 16;           // blocks per thread
+constexpr int AP_TB = 8;            // outputs per block
+constexpr int AP_NB = 8;            // blocks per thread
 constexpr int AP_STRIP = AP_TB * AP_NB;
 typedef unsigned long long f32x2;
 

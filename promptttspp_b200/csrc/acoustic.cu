@@ -83,6 +83,10 @@ struct pttspp_acoustic {
   // keeps the two-launches-per-layer path (the only one for other channel counts / kernel sizes)
   pttspp::DiffNetStack diffnet;
   bool use_fused = false;
+  // the step boundary (skip projection -> output projection -> DDPM update -> next input projection) as one kernel
+  // (csrc/diffnet_tail.cu); PTTSPP_DIFFNET_TAIL=0 keeps the four separate launches
+  pttspp::DiffNetTail tail;
+  bool use_tail = false;
   bool h_fp32 = false;          // PTTSPP_H_FP32=1: fp32 copy of the residual stream (two-launch path, A/B measurements)
   std::vector<float> c_recip, c_recipm1, coef1, coef2, logvar;
 };
@@ -461,6 +465,21 @@ extern "C" int pttspp_acoustic_finalize(pttspp_acoustic_t* h, pttspp_stream_t) {
                                    w.dilated.w_scale_inv, w.outp.w_scale_inv, w.dilated.dil});
       }
       h->diffnet.set_layers(hl);
+      const char* tl = getenv("PTTSPP_DIFFNET_TAIL");
+      h->use_tail = !(tl && tl[0] == '0') && DC == 256 && c.mel_dim <= 128 && c.mel_dim % 8 == 0 &&
+                    round_up(c.mel_dim, 64) == 128 && h->skip_proj.w_hi && h->out_proj.w_hi;
+      if (h->use_tail) {
+        DiffTailHost th;
+        th.wsp_hi = h->skip_proj.w_hi; th.wsp_lo = h->skip_proj.w_lo;
+        th.wop_hi = h->out_proj.w_hi; th.wop_lo = h->out_proj.w_lo;
+        th.wip_hi = h->in_proj_tc.w_hi; th.wip_lo = h->in_proj_tc.w_lo;
+        th.bias_sp = h->skip_proj.bias; th.bias_op = h->out_proj.bias; th.bias_ip = h->in_proj_tc.bias;
+        th.scale_sp = h->skip_proj.w_scale_inv / sqrtf((float)c.diff_layers);
+        th.scale_op = h->out_proj.w_scale_inv;
+        th.scale_ip = h->in_proj_tc.w_scale_inv;
+        th.mel = c.mel_dim; th.mel_pad = round_up(c.mel_dim, 64);
+        h->tail.set_weights(th);
+      }
     }
   }
   h->step_table = dev.upload(build_step_table(st, c));
@@ -786,9 +805,10 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
   auto planes_out = [&](pttspp_conv1d_desc& q, uint16_t* hi, uint16_t* lo, const float* add) {
     q.out_hi = hi; q.out_lo = lo; q.out_plane_bs = bsD; q.out_plane_ld = DC; q.out_plane_add = add;
   };
+  const bool tail = fused && h->use_tail && tc_inproj && h_planes;
   for (int step = c.K_step - 1; step >= 0; --step) {
     const float* step_emb = h->step_table + (size_t)step * c.diff_layers * DC;
-    {
+    if (!tail || step == c.K_step - 1) {  // with the fused step boundary the previous step's tail wrote these planes
       auto d = conv_desc(tc_inproj ? h->in_proj_tc : h->in_proj, w.xt, B, Ty, w.h);
       d.act = PTTSPP_ACT_RELU;
       if (tc_inproj) tc_in(d, w.xh, w.xl, h->in_proj_tc);
@@ -855,6 +875,20 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
         conv1d_cl(k, s);
       }
     }
+    const float sigma = (step > 0) ? expf(0.5f * h->logvar[step]) : 0.f;
+    const float* z_step = z + (size_t)(c.K_step - 1 - step) * B * M * Ty;
+    if (tail) {
+      DiffTailRun tr;
+      tr.B = B; tr.T = Ty; tr.skip_hi = w.sh; tr.skip_lo = w.sl; tr.x = w.xt; tr.z = z_step;
+      tr.c_recip = h->c_recip[step]; tr.c_recipm1 = h->c_recipm1[step]; tr.coef1 = h->coef1[step]; tr.coef2 = h->coef2[step];
+      tr.sigma = sigma;
+      tr.step_next = (step > 0) ? h->step_table + (size_t)(step - 1) * c.diff_layers * DC : nullptr;
+      tr.y_hi = w.yh; tr.y_lo = w.yl;
+      const double rows = (double)B * Ty;
+      ProfScope prof(PROF_CONV_UMMA, s, rows * 2.0 * (DC * DC + (double)DC * M + (step > 0 ? (double)M * DC : 0.0)), 0.0);
+      h->tail.run(tr, s);
+      continue;
+    }
     {
       auto d = conv_desc(h->skip_proj, w.skip, B, Ty, w.s);
       d.acc_scale = inv_sqrt_layers; d.act = PTTSPP_ACT_RELU;
@@ -868,8 +902,7 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
       if (um) planes_in(e, w.ph, w.pl, h->out_proj, 0);
       conv1d_cl(e, s);
     }
-    const float sigma = (step > 0) ? expf(0.5f * h->logvar[step]) : 0.f;
-    ddpm_update(w.xt, w.eps, z + (size_t)(c.K_step - 1 - step) * B * M * Ty, B, Ty, M, h->c_recip[step],
+    ddpm_update(w.xt, w.eps, z_step, B, Ty, M, h->c_recip[step],
                 h->c_recipm1[step], h->coef1[step], h->coef2[step], sigma, s, tc_inproj ? w.xh : nullptr,
                 tc_inproj ? w.xl : nullptr, Mp);
   }

@@ -73,4 +73,52 @@ struct DiffNetStack {
   static bool supported(int channels, int kernel, int max_dil) { return channels == 256 && kernel == 3 && max_dil <= 8; }
 };
 
+// ---- step boundary (csrc/diffnet_tail.cu): skip projection -> output projection -> DDPM update -> next input projection ----
+struct alignas(64) DiffTailConst {
+  CUtensorMap wsp_h, wsp_l;  // skip_projection planes [256][256], box {64, 64}
+  CUtensorMap wop_h, wop_l;  // output_projection planes [mel][256] (rows >= mel zero-filled by TMA)
+  CUtensorMap wip_h, wip_l;  // input_projection planes [256][mel padded to 128]
+  const float *bias_sp, *bias_op, *bias_ip;
+  float scale_sp, scale_op, scale_ip;  // accumulator scales: 2^-s of the weight scale (x 1/sqrt(layers) for the skip sum)
+};
+
+struct DiffTailArgs {
+  const DiffTailConst* c;
+  int B, T, n_mt, n_units, M;
+  float* x;                // [B][T][M] x_t in, x_{t-1} out
+  const float* z;          // [B][M][T] Gaussian noise of this step, or NULL (sigma = 0)
+  float c_recip, c_recipm1, coef1, coef2, sigma;
+  const float* step_next;  // [256] step embedding (layer 0) of the NEXT diffusion step; NULL: no input projection
+  __half *y_hi, *y_lo;     // [B][T][256] operand planes of the next step's first layer
+};
+
+struct DiffTailHost {
+  const void *wsp_hi, *wsp_lo, *wop_hi, *wop_lo, *wip_hi, *wip_lo;  // device pointers
+  const float *bias_sp, *bias_op, *bias_ip;
+  float scale_sp, scale_op, scale_ip;
+  int mel, mel_pad;
+};
+
+struct DiffTailRun {
+  int B, T;
+  const void *skip_hi, *skip_lo;
+  float* x;
+  const float* z;
+  float c_recip, c_recipm1, coef1, coef2, sigma;
+  const float* step_next;
+  void *y_hi, *y_lo;
+};
+
+struct DiffNetTail {
+  void* d_const = nullptr;
+  int mel = 0;
+  int setup_dev = -1, max_clusters = 0;
+  CUtensorMap s_maps[2];
+  const void* s_key[2] = {nullptr, nullptr};
+  int s_B = 0, s_T = 0;
+  ~DiffNetTail();
+  void set_weights(const DiffTailHost& h);
+  void run(const DiffTailRun& r, cudaStream_t s);
+};
+
 }  // namespace pttspp

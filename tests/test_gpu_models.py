@@ -221,6 +221,26 @@ def test_acoustic_default_rng_and_shapes():
     assert torch.equal(again[0], mel)
 
 
+def test_fused_step_boundary_kernel_equals_separate_launches(monkeypatch):
+    """csrc/diffnet_tail.cu (skip projection -> output projection -> DDPM update -> next input projection in one TS-MMA
+    kernel) against the four separate launches it replaces (PTTSPP_DIFFNET_TAIL=0), ragged batch, 12 diffusion steps."""
+    case = dict(ACOUSTIC_CASES["legacy_b3"], K_step=12)
+    phoneme, lengths, cls_emb = acoustic_inputs(case)
+    outs = []
+    for tail in ("1", "0"):
+        monkeypatch.setenv("PTTSPP_DIFFNET_TAIL", tail)
+        model = build_acoustic(bert=FixedPromptEmbedding(cls_emb), K_step=12)
+        model.load_state_dict(synthetic_state_dict(model, seed=case["weight_seed"], frames_per_phoneme=6.0), strict=True)
+        model = model.cuda().eval()
+        torch.manual_seed(5)
+        outs.append(model.infer_batch(phoneme.cuda(), lengths.cuda(), style_prompt=["a", "b", "c"], noise_scale=1.0))
+    (mel_a, len_a), (mel_b, len_b) = outs
+    assert torch.equal(len_a, len_b) and mel_a.shape == mel_b.shape
+    err = float((mel_a - mel_b).abs().max())
+    print(f"fused step boundary vs separate launches: mel max-abs diff {err:.2e} over {int(len_a.sum())} frames")
+    assert err < 5e-5 and float(mel_a.abs().max()) > 0.5
+
+
 # ---- F0-aware vocoder (SURVEY.md section 8 row a25: the vocoder app.py / synthesize.py instantiate by default) ----
 
 @pytest.fixture(scope="module")
