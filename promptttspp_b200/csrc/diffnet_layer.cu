@@ -231,9 +231,14 @@ diffnet_layers_kernel(const __grid_constant__ CUtensorMap mapY0h, const __grid_c
             const uint32_t dst = ring + (uint32_t)st * DL_BST;
             const int wrow = tap * (2 * DL_C) + nt * 128 + (int)rank * 64;
             if (elect_one()) {
-              if (rank == 0) mbar_expect_tx(fullB(st), 2u * DL_BST);
-              tma_load_2d_pair(dst, &L->wd_h, fullB(st), slab * 64, wrow);
-              tma_load_2d_pair(dst + DL_BHALF, &L->wd_l, fullB(st), slab * 64, wrow);
+              if (a.dbg_flags & 256) {  // experiment: half the weight traffic (lo planes not loaded; results invalid)
+                if (rank == 0) mbar_expect_tx(fullB(st), (uint32_t)DL_BST);
+                tma_load_2d_pair(dst, &L->wd_h, fullB(st), slab * 64, wrow);
+              } else {
+                if (rank == 0) mbar_expect_tx(fullB(st), 2u * DL_BST);
+                tma_load_2d_pair(dst, &L->wd_h, fullB(st), slab * 64, wrow);
+                tma_load_2d_pair(dst + DL_BHALF, &L->wd_l, fullB(st), slab * 64, wrow);
+              }
             }
             __syncwarp();
           }
@@ -245,9 +250,14 @@ diffnet_layers_kernel(const __grid_constant__ CUtensorMap mapY0h, const __grid_c
           const uint32_t dst = ring + (uint32_t)st * DL_BST;
           const int wrow = nt * 128 + (int)rank * 64;
           if (elect_one()) {
-            if (rank == 0) mbar_expect_tx(fullB(st), 2u * DL_BST);
-            tma_load_2d_pair(dst, &L->wo_h, fullB(st), slab * 64, wrow);
-            tma_load_2d_pair(dst + DL_BHALF, &L->wo_l, fullB(st), slab * 64, wrow);
+            if (a.dbg_flags & 256) {
+              if (rank == 0) mbar_expect_tx(fullB(st), (uint32_t)DL_BST);
+              tma_load_2d_pair(dst, &L->wo_h, fullB(st), slab * 64, wrow);
+            } else {
+              if (rank == 0) mbar_expect_tx(fullB(st), 2u * DL_BST);
+              tma_load_2d_pair(dst, &L->wo_h, fullB(st), slab * 64, wrow);
+              tma_load_2d_pair(dst + DL_BHALF, &L->wo_l, fullB(st), slab * 64, wrow);
+            }
           }
           __syncwarp();
         }

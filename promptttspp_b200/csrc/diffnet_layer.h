@@ -34,7 +34,7 @@ struct DiffNetArgs {
   float* dbg_z;           // tests: [B][T][256] gate output of the (single) layer run
   unsigned long long* dbg_prof;  // optional [clusters][16] cycle counters of the barrier waits (tools/bench_diffnet.py)
   int dbg_flags;          // timing experiments (PTTSPP_DIFFNET_DBG): 1 no epilogue global traffic, 2 one MMA per product,
-                          // 4 no output projection
+                          // 4 no output projection, 256 half the weight traffic (lo planes not loaded: results invalid)
 };
 
 struct DiffLayerHost {
