@@ -437,6 +437,22 @@ int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_state, const i
                            const float* x_T, const float* z, float* mel, float* log_cf0, float* vuv,
                            float* cond_out, void* workspace, size_t workspace_bytes, pttspp_stream_t stream);
 
+/* The same with the K_step noise tensors drawn INSIDE the loop, one [B][mel][Ty] buffer at a time, from torch's CUDA
+ * Philox stream: (rng_seed, rng_offset) = the generator's (initial_seed(), get_offset()) after x_T was drawn; every
+ * step's draw is bit-identical to the torch.randn(shape) the reference makes at diffusion.py:218, and *rng_offset_out is
+ * the offset the caller must set the generator to afterwards.  Removes the [K_step][B][mel][Ty] tensor (1.3 GB at
+ * batch 16 x 2.6 k frames). */
+int pttspp_acoustic_decode_rng(pttspp_acoustic_t* h, const float* enc_state, const int64_t* dur,
+                               const int64_t* frame_len, int B, int Tx, int Ty, const float* pe_abs,
+                               const float* x_T, uint64_t rng_seed, uint64_t rng_offset, uint64_t* rng_offset_out,
+                               float* mel, float* log_cf0, float* vuv, float* cond_out, void* workspace,
+                               size_t workspace_bytes, pttspp_stream_t stream);
+/* One torch-compatible standard-normal draw: out[numel] = what `torch.empty(numel, device="cuda").normal_()` writes when
+ * the CUDA generator holds (seed, offset); *offset_advance = how far that call moves the generator's offset
+ * (ATen/native/cuda/DistributionTemplates.h: grid-stride Philox4_32_10 + curand_normal4). */
+int pttspp_philox_normal(float* out, int64_t numel, uint64_t seed, uint64_t offset, uint64_t* offset_advance,
+                         pttspp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

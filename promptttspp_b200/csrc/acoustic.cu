@@ -239,6 +239,7 @@ struct DecodeWs {
   uint16_t *xh, *xl;                                // x_t planes [B][Ty][round_up(mel, 64)]
   uint16_t *yh2, *yl2;                              // second pair of residual-stream planes (fused stack: ping-pong)
   unsigned* done;                                   // fused stack: per (layer, unit) completion counters
+  float* znoise;                                    // [B][mel][Ty] noise of the current step (decode_rng)
 };
 
 DecodeWs carve_decode(const pttspp_acoustic_config& c, int B, int Ty, Carver& cv, size_t flags_bytes = 0) {
@@ -264,6 +265,7 @@ DecodeWs carve_decode(const pttspp_acoustic_config& c, int B, int Ty, Carver& cv
   w.xh = cv.take<uint16_t>(n * round_up(c.mel_dim, 64)); w.xl = cv.take<uint16_t>(n * round_up(c.mel_dim, 64));
   w.yh2 = cv.take<uint16_t>(flags_bytes ? n * DC : 0); w.yl2 = cv.take<uint16_t>(flags_bytes ? n * DC : 0);
   w.done = cv.take<unsigned>((int64_t)(flags_bytes / sizeof(unsigned)));
+  w.znoise = cv.take<float>(n * c.mel_dim);
   return w;
 }
 
@@ -679,13 +681,20 @@ extern "C" size_t pttspp_acoustic_decode_workspace_bytes(const pttspp_acoustic_t
   return cv.off + 512;
 }
 
-extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_state, const int64_t* dur,
-                                      const int64_t* frame_len, int B, int Tx, int Ty, const float* pe_abs,
-                                      const float* x_T, const float* z, float* mel, float* log_cf0, float* vuv,
-                                      float* cond_out, void* workspace, size_t workspace_bytes,
-                                      pttspp_stream_t stream) {
+namespace pttspp {
+uint64_t philox_normal(float* out, int64_t numel, uint64_t seed, uint64_t offset, cudaStream_t s);  // philox.cu
+}
+
+// z != nullptr: the K_step draws are given; z == nullptr: they are drawn here, step by step, from torch's Philox stream
+// (rng_seed, rng_offset) -- *rng_offset_out receives the offset after the K_step draws
+static int acoustic_decode_impl(pttspp_acoustic_t* h, const float* enc_state, const int64_t* dur,
+                                const int64_t* frame_len, int B, int Tx, int Ty, const float* pe_abs,
+                                const float* x_T, const float* z, uint64_t rng_seed, uint64_t rng_offset,
+                                uint64_t* rng_offset_out, float* mel, float* log_cf0, float* vuv,
+                                float* cond_out, void* workspace, size_t workspace_bytes,
+                                pttspp_stream_t stream) {
   PT_API_BEGIN
-  PT_CHECK(h && enc_state && dur && frame_len && pe_abs && x_T && z && mel, "null argument");
+  PT_CHECK(h && enc_state && dur && frame_len && pe_abs && x_T && mel, "null argument");
   PT_CHECK(h->finalized, "acoustic: finalize() has not been called after the last set_tensor()");
   PT_CHECK(B >= 1 && Tx >= 1 && Ty >= 1, "acoustic: empty batch (B=%d, Tx=%d, Ty=%d)", B, Tx, Ty);
   PT_CHECK(workspace && workspace_bytes >= pttspp_acoustic_decode_workspace_bytes(h, B, Tx, Ty),
@@ -876,7 +885,14 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
       }
     }
     const float sigma = (step > 0) ? expf(0.5f * h->logvar[step]) : 0.f;
-    const float* z_step = z + (size_t)(c.K_step - 1 - step) * B * M * Ty;
+    const float* z_step;
+    if (z) {
+      z_step = z + (size_t)(c.K_step - 1 - step) * B * M * Ty;
+    } else {
+      // the reference draws noise_like(x.shape) at every step, the last one included (diffusion.py:218)
+      rng_offset += philox_normal(w.znoise, (int64_t)B * M * Ty, rng_seed, rng_offset, s);
+      z_step = w.znoise;
+    }
     if (tail) {
       DiffTailRun tr;
       tr.B = B; tr.T = Ty; tr.skip_hi = w.sh; tr.skip_lo = w.sl; tr.x = w.xt; tr.z = z_step;
@@ -911,5 +927,29 @@ extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_sta
     transpose_btc_to_bct_affine(w.xt, mel, B, Ty, M, flen, c.norm_scale, 0.f, s);
   else
     transpose_btc_to_bct_affine(w.xt, mel, B, Ty, M, flen, 0.5f * (c.a_max - c.a_min), 0.5f * (c.a_max - c.a_min) + c.a_min, s);
+  if (rng_offset_out) *rng_offset_out = rng_offset;
   PT_API_END
+}
+
+extern "C" int pttspp_acoustic_decode(pttspp_acoustic_t* h, const float* enc_state, const int64_t* dur,
+                                      const int64_t* frame_len, int B, int Tx, int Ty, const float* pe_abs,
+                                      const float* x_T, const float* z, float* mel, float* log_cf0, float* vuv,
+                                      float* cond_out, void* workspace, size_t workspace_bytes,
+                                      pttspp_stream_t stream) {
+  if (!z) {
+    pttspp::set_last_error("pttspp_acoustic_decode: z is NULL (use pttspp_acoustic_decode_rng to draw the noise natively)");
+    return 1;
+  }
+  return acoustic_decode_impl(h, enc_state, dur, frame_len, B, Tx, Ty, pe_abs, x_T, z, 0, 0, nullptr, mel, log_cf0, vuv,
+                              cond_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pttspp_acoustic_decode_rng(pttspp_acoustic_t* h, const float* enc_state, const int64_t* dur,
+                                          const int64_t* frame_len, int B, int Tx, int Ty, const float* pe_abs,
+                                          const float* x_T, uint64_t rng_seed, uint64_t rng_offset,
+                                          uint64_t* rng_offset_out, float* mel, float* log_cf0, float* vuv,
+                                          float* cond_out, void* workspace, size_t workspace_bytes,
+                                          pttspp_stream_t stream) {
+  return acoustic_decode_impl(h, enc_state, dur, frame_len, B, Tx, Ty, pe_abs, x_T, nullptr, rng_seed, rng_offset,
+                              rng_offset_out, mel, log_cf0, vuv, cond_out, workspace, workspace_bytes, stream);
 }

@@ -243,18 +243,29 @@ class PromptTTSMDNDurCFG(nn.Module):
                                      f"expected {(B, M, Ty)}, {(K, B, M, Ty)}")
             else:
                 x_T = torch.randn((B, M, Ty), device=device)
-                z = torch.empty(K, B, M, Ty, device=device)
-                for i in range(K):
-                    z[i].normal_()  # the same Philox draw as torch.randn((B, M, Ty)), written in place (no copy)
+                z = None  # drawn step by step inside the native loop, from this generator's Philox stream
             mel = torch.empty(B, M, Ty, device=device)
             log_cf0 = torch.empty(B, 1, Ty, device=device)
             vuv = torch.empty(B, 1, Ty, device=device)
             if Ty > 0:
                 ws = nat.workspace(lib.pttspp_acoustic_decode_workspace_bytes(nat.h, B, Tx, Ty), device)
-                _abi.check(lib.pttspp_acoustic_decode(
-                    nat.h, _abi.ptr(enc_state), _abi.ptr(dur), _abi.ptr(frame_len), B, Tx, Ty, _abi.ptr(pe_abs),
-                    _abi.ptr(x_T), _abi.ptr(z), _abi.ptr(mel), _abi.ptr(log_cf0), _abi.ptr(vuv), None,
-                    _abi.ptr(ws), C.c_size_t(ws.numel()), stream))
+                if z is not None:
+                    _abi.check(lib.pttspp_acoustic_decode(
+                        nat.h, _abi.ptr(enc_state), _abi.ptr(dur), _abi.ptr(frame_len), B, Tx, Ty, _abi.ptr(pe_abs),
+                        _abi.ptr(x_T), _abi.ptr(z), _abi.ptr(mel), _abi.ptr(log_cf0), _abi.ptr(vuv), None,
+                        _abi.ptr(ws), C.c_size_t(ws.numel()), stream))
+                else:
+                    # the K per-step draws of diffusion.py:218, bit-identical to K x torch.randn((B, M, Ty)) from this
+                    # generator state; afterwards the generator is moved past them
+                    gen = torch.cuda.default_generators[device.index if device.index is not None
+                                                        else torch.cuda.current_device()]
+                    off_out = C.c_uint64(0)
+                    _abi.check(lib.pttspp_acoustic_decode_rng(
+                        nat.h, _abi.ptr(enc_state), _abi.ptr(dur), _abi.ptr(frame_len), B, Tx, Ty, _abi.ptr(pe_abs),
+                        _abi.ptr(x_T), C.c_uint64(gen.initial_seed()), C.c_uint64(gen.get_offset()), C.byref(off_out),
+                        _abi.ptr(mel), _abi.ptr(log_cf0), _abi.ptr(vuv), None, _abi.ptr(ws), C.c_size_t(ws.numel()),
+                        stream))
+                    gen.set_offset(off_out.value)
         self.last_durations = dur
         self.last_log_durations = log_dur
         # the reference returns frame_mask.sum(dim=(1, 2)): a float tensor (model.py:311)

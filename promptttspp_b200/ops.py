@@ -284,3 +284,14 @@ class DiffNetStack:
         r.dbg_prof = None if dbg_prof is None else dbg_prof.data_ptr()
         with torch.cuda.device(self.device):
             _abi.check(_abi.lib().pttspp_diffnet_run(self.h, C.byref(r), _abi.stream_ptr(self.device)))
+
+
+def philox_normal(numel, seed, offset, device="cuda"):
+    """What `torch.empty(numel, device=device).normal_()` writes when the CUDA generator holds (seed, offset); returns
+    (tensor, offset advance).  csrc/philox.cu."""
+    out = torch.empty(int(numel), dtype=torch.float32, device=device)
+    adv = C.c_uint64(0)
+    with torch.cuda.device(out.device):
+        _abi.check(_abi.lib().pttspp_philox_normal(_abi.ptr(out), int(numel), C.c_uint64(int(seed)), C.c_uint64(int(offset)),
+                                                   C.byref(adv), _abi.stream_ptr(out.device)))
+    return out, int(adv.value)

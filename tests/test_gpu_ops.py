@@ -306,3 +306,20 @@ def test_lowpass_filter_ragged_rows_equal_per_utterance_calls():
     # without lengths the tail of a short row is contaminated by the step into the padding (what the advice flagged)
     bad = lowpass_filter(x.cuda(), 100, cutoff=20).cpu()
     assert float((bad[1, 0, :131] - y[1, 0, :131]).abs().max()) > 0.5
+
+
+@pytest.mark.parametrize("numel", [1, 255, 4096, 80 * 519, 16 * 80 * 2582, 5_000_001])
+def test_philox_normal_is_torch_randn_bit_for_bit(ops, numel):
+    """csrc/philox.cu draws the sampler's per-step noise natively; it must be THE torch draw (same values, same advance of
+    the generator), so a seeded run is unchanged and matches a seeded GPU run of the reference (diffusion.py:218)."""
+    torch.cuda.init()  # default_generators is populated lazily
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    for seed in (0, 1234567):
+        torch.manual_seed(seed)
+        torch.randn(1000, device="cuda")                      # move the offset off zero
+        off0 = gen.get_offset()
+        want = torch.randn(numel, device="cuda")
+        off1 = gen.get_offset()
+        got, adv = ops.philox_normal(numel, gen.initial_seed(), off0)
+        assert adv == off1 - off0, (adv, off1 - off0)
+        assert torch.equal(got, want), float((got - want).abs().max())
