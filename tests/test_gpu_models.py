@@ -221,6 +221,37 @@ def test_acoustic_default_rng_and_shapes():
     assert torch.equal(again[0], mel)
 
 
+@pytest.mark.parametrize("rel_pos_type", ["legacy", "new"])
+def test_acoustic_long_text_against_oracle(rel_pos_type):
+    """Texts beyond the fused attention kernel's 256-phoneme range (CUDA-core attention fallback, chunked tcgen05 FFN at
+    Tx = 300) in a ragged batch, against the CPU oracle on the same injected noise: durations bit-exact, mel <= 1e-3."""
+    case = dict(api="infer_batch", rel_pos_type=rel_pos_type, lengths=[300, 257, 31], weight_seed=1236,
+                frames_per_phoneme=2.0, input_seed=9, noise_seed=109, noise_scale=1.0, K_step=3)
+    phoneme, lengths, cls_emb = acoustic_inputs(case)
+    model = build_acoustic(rel_pos_type=rel_pos_type, bert=FixedPromptEmbedding(cls_emb), K_step=3)
+    sd = synthetic_state_dict(model, seed=case["weight_seed"], frames_per_phoneme=2.0)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    B = 3
+    cfg = dict(oracle.ACOUSTIC_CFG, rel_pos_type=rel_pos_type, K_step=3)
+    from __graft_entry__ import _oracle_enc_state
+
+    z_style = golden_noise(case, B, None).z_style
+    pm = (torch.arange(phoneme.shape[1])[None] < lengths[:, None]).unsqueeze(1)
+    log_d = oracle.duration_log(sd, cfg, _oracle_enc_state(oracle, sd, cfg, phoneme, lengths, cls_emb, z_style), pm.float())
+    Ty = int(oracle.quantize_durations(log_d, pm.long())[1].max())
+    noise = golden_noise(case, B, Ty)
+    ref_mel, ref_cf0, ref_vuv, ref_len = oracle.acoustic_infer_batch(
+        sd, cfg, phoneme, lengths, cls_emb, noise.z_style, noise.x_T, noise.z, noise_scale=1.0)
+    mel, cf0, vuv, flen = model.infer_batch(phoneme.cuda(), lengths.cuda(), style_prompt=["p"] * B, use_max=True,
+                                            noise_scale=1.0, return_f0=True, noise=noise)
+    assert torch.equal(flen.cpu(), ref_len)
+    err = float((mel.cpu() - ref_mel).abs().max())
+    print(f"long text ({rel_pos_type}): {int(flen.sum())} frames, mel max-abs err {err:.3e}, "
+          f"log_cf0 {float((cf0.cpu() - ref_cf0).abs().max()):.3e}")
+    assert err < 1e-3
+
+
 def test_fused_step_boundary_kernel_equals_separate_launches(monkeypatch):
     """csrc/diffnet_tail.cu (skip projection -> output projection -> DDPM update -> next input projection in one TS-MMA
     kernel) against the four separate launches it replaces (PTTSPP_DIFFNET_TAIL=0), ragged batch, 12 diffusion steps."""
