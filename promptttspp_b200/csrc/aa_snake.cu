@@ -12,6 +12,7 @@
 #include <cuda_fp16.h>
 
 #include "common.h"
+#include "aa_math.cuh"
 
 namespace pttspp {
 namespace {
@@ -56,12 +57,11 @@ __device__ __forceinline__ void aa_snake_strip(const float* __restrict__ xb, flo
 #pragma unroll
       for (int dd = 0; dd < 6; ++dd) u = fmaf(xs[(i - 1) / 2 + dd], f2[11 - 2 * dd], u);
     }
-    // sin(alpha*u) with the argument reduced in REVOLUTIONS: r = u * alpha/(2*pi), frac = r - rint(r) is exact, and
-    // the MUFU sine of 2*pi*frac in [-pi, pi] is accurate to 2^-21 -- |error| < 1e-6 over the activations' range, far
-    // inside the 1e-4 RMS waveform bar (libm sinf's slow path made this kernel instruction bound)
-    const float r = u * a2;
-    const float frac = r - rintf(r);
-    const float sn = __sinf(frac * 6.28318530717958648f);
+    // sin(alpha*u): the fast sine (x * 1/2pi rounded toward zero, then the SFU's sine of the fractional revolution) --
+    // |error| ~ ulp(alpha*u / 2pi) * 2pi < 1e-5 over the activations' range, far inside the 1e-4 RMS waveform bar; libm
+    // sinf's slow path made this kernel instruction bound, and an explicit r - rint(r) reduction costs two more FP32-pipe
+    // operations plus an FRND on the quarter-rate XU pipe for the same argument error (ncu: FMA pipe 60 %, XU 52 %)
+    const float sn = __sinf(u * a2);
     sv[i] = fmaf(inv_alpha * sn, sn, u);
   }
   if (EDGE) {
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__
   }
   const float alpha = expf(log_alpha[c]);
   const float inv_alpha = 1.f / (alpha + 1e-9f);
-  const float a2 = alpha * 0.15915494309189535f;
+  const float a2 = alpha;
   const float* xb = x + (int64_t)b * L * C + c;
   const int64_t ob = (int64_t)b * L * C + c + (int64_t)t0 * C;
   // warp-uniform: a warp spans 32 channels of ONE strip
@@ -130,47 +130,23 @@ __global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__
 constexpr int AP_TB = 8;            // outputs per block
 constexpr int AP_NB = 8;            // blocks per thread
 constexpr int AP_STRIP = AP_TB * AP_NB;
-typedef unsigned long long f32x2;
-
-__device__ __forceinline__ f32x2 pk2(float a, float b) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-// s = u + sin^2(alpha * u) / (alpha + 1e-9), both channels (same operations as the strip kernel, packed where possible)
-__device__ __forceinline__ f32x2 snake2(f32x2 u, f32x2 a2, f32x2 inv_alpha) {
-  const f32x2 r = mul2(u, a2);
-  float r0, r1;
-  upk2(r, r0, r1);
-  const f32x2 frac = fma2(pk2(rintf(r0), rintf(r1)), pk2(-1.f, -1.f), r);  // r - rint(r): exact
-  float f0, f1;
-  upk2(mul2(frac, pk2(6.28318530717958648f, 6.28318530717958648f)), f0, f1);
-  const f32x2 sn = pk2(__sinf(f0), __sinf(f1));
-  return fma2(mul2(inv_alpha, sn), sn, u);
-}
-
 template <bool EDGE>
 __device__ __forceinline__ void aa_pair_block(const float* __restrict__ xb, float* __restrict__ y, __half* __restrict__ y_hi,
                                               __half* __restrict__ y_lo, int64_t ob, int tb, int L, int C,
-                                              f32x2 (&sv)[2 * AP_TB + 10], f32x2 (&xw)[AP_TB + 5], const f32x2 (&e)[6],
-                                              const f32x2 (&g)[6], f32x2 a2, f32x2 inv_alpha) {
-  // new inputs x[tb + 5 .. tb + TB + 4]
+                                              f32x2 (&sv)[2 * AP_TB + 10], f32x2 (&xw)[AP_TB + 5], f32x2 (&xn)[AP_TB],
+                                              bool more, const f32x2 (&e)[6], const f32x2 (&g)[6], f32x2 a2,
+                                              f32x2 inv_alpha) {
+  // new inputs x[tb + 5 .. tb + TB + 4]: requested one block earlier (ncu: the kernel stalled on these loads --
+  // long-scoreboard was the largest stall reason at 4 warps per scheduler); now request the next block's
 #pragma unroll
-  for (int i = 0; i < AP_TB; ++i) {
-    int l = tb + 5 + i;
-    if (EDGE) l = l > L - 1 ? L - 1 : l;
-    xw[5 + i] = *reinterpret_cast<const f32x2*>(xb + (int64_t)l * C);
+  for (int i = 0; i < AP_TB; ++i) xw[5 + i] = xn[i];
+  if (more) {
+#pragma unroll
+    for (int i = 0; i < AP_TB; ++i) {
+      int l = tb + AP_TB + 5 + i;
+      l = l > L - 1 ? L - 1 : l;
+      xn[i] = *reinterpret_cast<const f32x2*>(xb + (int64_t)l * C);
+    }
   }
   // new up-sampled values: sv[i] <-> index 2*tb - 5 + i, i = 10 .. 2*TB + 9
 #pragma unroll
@@ -238,7 +214,7 @@ __global__ void __launch_bounds__(256) aa_snake_pair_kernel(const float* __restr
   }
   const float al0 = expf(log_alpha[c]), al1 = expf(log_alpha[c + 1]);
   const f32x2 inv_alpha = pk2(1.f / (al0 + 1e-9f), 1.f / (al1 + 1e-9f));
-  const f32x2 a2 = pk2(al0 * 0.15915494309189535f, al1 * 0.15915494309189535f);
+  const f32x2 a2 = pk2(al0, al1);
   const float* xb = x + (int64_t)blockIdx.y * L * C + c;
   f32x2 sv[2 * AP_TB + 10], xw[AP_TB + 5];
   // prologue: the 10 up-sampled values in front of the strip (indices 2*t0 - 5 .. 2*t0 + 4) from x[t0 - 5 .. t0 + 4]
@@ -273,14 +249,22 @@ __global__ void __launch_bounds__(256) aa_snake_pair_kernel(const float* __restr
 #pragma unroll
     for (int i = 0; i < 5; ++i) xw[i] = xs[5 + i];
   }
+  f32x2 xn[AP_TB];  // inputs of the next block, in flight while the current one is computed
+#pragma unroll
+  for (int i = 0; i < AP_TB; ++i) {
+    int l = t0 + 5 + i;
+    l = l > L - 1 ? L - 1 : l;
+    xn[i] = *reinterpret_cast<const f32x2*>(xb + (int64_t)l * C);
+  }
   const int64_t ob0 = (int64_t)blockIdx.y * L * C + c;
 #pragma unroll 1
   for (int blk = 0; blk < AP_NB; ++blk) {
     const int tb = t0 + blk * AP_TB;
     if (tb >= L) break;
     const int64_t ob = ob0 + (int64_t)tb * C;
-    if (tb + AP_TB + 4 <= L - 1) aa_pair_block<false>(xb, y, y_hi, y_lo, ob, tb, L, C, sv, xw, e, g, a2, inv_alpha);
-    else aa_pair_block<true>(xb, y, y_hi, y_lo, ob, tb, L, C, sv, xw, e, g, a2, inv_alpha);
+    const bool more = (blk + 1 < AP_NB) && (tb + AP_TB < L);
+    if (tb + AP_TB + 4 <= L - 1) aa_pair_block<false>(xb, y, y_hi, y_lo, ob, tb, L, C, sv, xw, xn, more, e, g, a2, inv_alpha);
+    else aa_pair_block<true>(xb, y, y_hi, y_lo, ob, tb, L, C, sv, xw, xn, more, e, g, a2, inv_alpha);
   }
 }
 

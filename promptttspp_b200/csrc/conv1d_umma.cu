@@ -1317,9 +1317,9 @@ conv1d_umma_c32_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_c
     // ================= TMA producer =================
     if (elect_one()) {
       mbar_expect_tx(fullW, w_bytes);
-      for (int tap = 0; tap < d.K; ++tap) {
-        tma_load_2d(base + (uint32_t)tap * (US_C * ROWB), &mapBh, fullW, 0, tap * US_C);
-        tma_load_2d(base + w_plane + (uint32_t)tap * (US_C * ROWB), &mapBl, fullW, 0, tap * US_C);
+      for (int tap = 0; tap < d.K; ++tap) {  // per tap: the hi rows directly followed by the lo rows (one N = 2C operand)
+        tma_load_2d(base + (uint32_t)tap * (2 * US_C * ROWB), &mapBh, fullW, 0, tap * US_C);
+        tma_load_2d(base + (uint32_t)tap * (2 * US_C * ROWB) + US_C * ROWB, &mapBl, fullW, 0, tap * US_C);
       }
     }
     __syncwarp();
@@ -1339,6 +1339,7 @@ conv1d_umma_c32_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_c
   } else if (warp == W_MMA) {
     // ================= MMA issuer =================
     constexpr uint32_t idesc = umma_idesc_f16(UM_BM, US_C);
+    constexpr uint32_t idesc2 = umma_idesc_f16(UM_BM, 2 * US_C);  // [W_hi | W_lo] stacked along N: main | cross accumulators
     const uint64_t descW = (US_C == 32) ? umma_desc_k_sw64(base) : umma_desc_k_sw128(base);
     mbar_wait_warp(fullW, 0);
     tc_fence_after();
@@ -1356,15 +1357,16 @@ conv1d_umma_c32_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_c
         for (int tap = 0; tap < d.K; ++tap) {
           const uint64_t dAh = descA + (uint64_t)(((uint32_t)(tap * d.dil) * ROWB) >> 4);  // taps share the halo block
           const uint64_t dAl = dAh + (uint64_t)(a_plane >> 4);
-          const uint64_t dBh = descW + (uint64_t)(((uint32_t)tap * (US_C * ROWB)) >> 4);
-          const uint64_t dBl = dBh + (uint64_t)(w_plane >> 4);
+          const uint64_t dBh = descW + (uint64_t)(((uint32_t)tap * (2 * US_C * ROWB)) >> 4);
 #pragma unroll
           for (int kk = 0; kk < US_C / 16; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 2);  // 16 halves = 32 bytes inside the swizzle span
             const uint32_t acc = (tap | kk) ? 1u : 0u;
-            umma_f16(acc_cross, dAl + adv, dBh + adv, idesc, acc);
-            umma_f16(acc_cross, dAh + adv, dBl + adv, idesc, 1u);
-            umma_f16(acc_main, dAh + adv, dBh + adv, idesc, acc);
+            // the kernel is bound by the tensor core's shared-memory operand reads (ncu: tc wavefronts 76 % of peak, a
+            // 128-row A tile per instruction): x_hi . [W_hi | W_lo] as ONE N = 2C instruction (main | cross columns are
+            // adjacent) + x_lo . W_hi -- the A planes are read twice instead of three times per k step
+            umma_f16(acc_main, dAh + adv, dBh + adv, idesc2, acc);
+            umma_f16(acc_cross, dAl + adv, dBh + adv, idesc, 1u);
           }
         }
         umma_commit(emptyA(st));
