@@ -203,6 +203,15 @@ int pttspp_aa_snake_cl(const float* x, float* y, int B, int L, int C, const floa
 int pttspp_aa_snake_pair_cl(const float* x, float* y, int B, int L, int C, const float* log_alpha,
                             const float* up_filter, const float* down_filter, pttspp_stream_t stream);
 
+/* AA-Snake fused into the conv that consumes it (BigVGAN's AMP layer, vocoders/bigvgan.py:42-47: `conv(act(x))`):
+ * d->in is the fp32 PRE-activation tensor [B][T][C]; activation-producer warps inside the tcgen05 conv kernel run the
+ * anti-aliased Snake (same arithmetic and order as pttspp_aa_snake_pair_cl) and write the split-fp16 operand planes
+ * straight into shared memory, so the activated tensor never exists in HBM.  Result is bit-identical to
+ * pttspp_aa_snake_pair_cl followed by pttspp_conv1d_cl on the planes.  Supported: Cin == Cout == 32 (K <= 11) or 64
+ * (K <= 7), stride 1, split-fp16 weights (w_hi / w_lo / w_scale_inv), 32-byte aligned out / res, symmetric filters. */
+int pttspp_aa_conv1d_cl(const pttspp_conv1d_desc* d, const float* log_alpha, const float* up_filter,
+                        const float* down_filter, pttspp_stream_t stream);
+
 /* Duration quantisation + length regulator.
  *   dur[b][i] = (i < len[b]) ? max(rint(exp(log_d[b][i])), 1) : 0    (variance_adaptor.py:179-181)
  *   frame_len[b] = sum_i dur[b][i]                                   (variance_adaptor.py:183)

@@ -125,6 +125,7 @@ SIGNATURES = {
                                      C.c_void_p, C.c_void_p]),
     "pttspp_aa_snake_pair_cl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
+    "pttspp_aa_conv1d_cl": (C.c_int, [C.POINTER(Conv1dDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pttspp_duration_quantize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                            C.c_void_p]),
     "pttspp_length_regulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

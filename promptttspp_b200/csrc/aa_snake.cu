@@ -85,9 +85,9 @@ __device__ __forceinline__ void aa_snake_strip(const float* __restrict__ xb, flo
       for (int k = 0; k < 12; ++k) acc = fmaf(sv[2 * t + k], g[k], acc);
       if (yp) yp[(int64_t)t * C] = acc;
       if (hp) {
-        const __half h = __float2half_rn(acc);
+        const __half h = pt_f2h_sat(acc);
         hp[(int64_t)t * C] = h;
-        lp[(int64_t)t * C] = __float2half_rn(acc - __half2float(h));
+        lp[(int64_t)t * C] = pt_f2h_sat(acc - __half2float(h));
       }
     }
   }
@@ -127,10 +127,8 @@ __global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__
 // amplification).  Needs exactly symmetric filters, f[k] == f[11-k] (true for the reference's Kaiser sinc: checked on the
 // host where the filters are loaded): 6 + 6 packed coefficients stay in registers.  With symmetric filters every
 // channel's result is bit-identical to the strip kernel's (same operation order).
-constexpr int AP_TB = 8;            // outputs per block
-constexpr int AP_NB = 8;            // blocks per thread
-constexpr int AP_STRIP = AP_TB * AP_NB;
-template <bool EDGE>
+constexpr int AP_STRIP = 64;        // outputs per thread; AP_TB outputs per block (template), AP_STRIP / AP_TB blocks
+template <bool EDGE, int AP_TB>
 __device__ __forceinline__ void aa_pair_block(const float* __restrict__ xb, float* __restrict__ y, __half* __restrict__ y_hi,
                                               __half* __restrict__ y_lo, int64_t ob, int tb, int L, int C,
                                               f32x2 (&sv)[2 * AP_TB + 10], f32x2 (&xw)[AP_TB + 5], f32x2 (&xn)[AP_TB],
@@ -178,10 +176,10 @@ __device__ __forceinline__ void aa_pair_block(const float* __restrict__ xb, floa
       const int64_t o = ob + (int64_t)t * C;
       if (y) *reinterpret_cast<float2*>(y + o) = make_float2(a0, a1);
       if (y_hi) {
-        const __half2 h = __floats2half2_rn(a0, a1);
+        const __half2 h = pt_f2h2_sat(a0, a1);
         const float2 hf = __half22float2(h);
         *reinterpret_cast<__half2*>(y_hi + o) = h;
-        *reinterpret_cast<__half2*>(y_lo + o) = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+        *reinterpret_cast<__half2*>(y_lo + o) = pt_f2h2_sat(a0 - hf.x, a1 - hf.y);
       }
     }
   }
@@ -192,7 +190,8 @@ __device__ __forceinline__ void aa_pair_block(const float* __restrict__ xb, floa
   for (int i = 0; i < 5; ++i) xw[i] = xw[AP_TB + i];
 }
 
-__global__ void __launch_bounds__(256) aa_snake_pair_kernel(const float* __restrict__ x, float* __restrict__ y,
+template <int AP_TB, int MINB>
+__global__ void __launch_bounds__(256, MINB) aa_snake_pair_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                             __half* __restrict__ y_hi, __half* __restrict__ y_lo, int L,
                                                             int C, int n_strips, const float* __restrict__ log_alpha,
                                                             const float* __restrict__ up_f,
@@ -258,13 +257,14 @@ __global__ void __launch_bounds__(256) aa_snake_pair_kernel(const float* __restr
   }
   const int64_t ob0 = (int64_t)blockIdx.y * L * C + c;
 #pragma unroll 1
+  constexpr int AP_NB = AP_STRIP / AP_TB;
   for (int blk = 0; blk < AP_NB; ++blk) {
     const int tb = t0 + blk * AP_TB;
     if (tb >= L) break;
     const int64_t ob = ob0 + (int64_t)tb * C;
     const bool more = (blk + 1 < AP_NB) && (tb + AP_TB < L);
-    if (tb + AP_TB + 4 <= L - 1) aa_pair_block<false>(xb, y, y_hi, y_lo, ob, tb, L, C, sv, xw, xn, more, e, g, a2, inv_alpha);
-    else aa_pair_block<true>(xb, y, y_hi, y_lo, ob, tb, L, C, sv, xw, xn, more, e, g, a2, inv_alpha);
+    if (tb + AP_TB + 4 <= L - 1) aa_pair_block<false, AP_TB>(xb, y, y_hi, y_lo, ob, tb, L, C, sv, xw, xn, more, e, g, a2, inv_alpha);
+    else aa_pair_block<true, AP_TB>(xb, y, y_hi, y_lo, ob, tb, L, C, sv, xw, xn, more, e, g, a2, inv_alpha);
   }
 }
 
@@ -282,7 +282,14 @@ void aa_snake_cl(const float* x, float* y, int B, int L, int C, const float* log
     const int n_strips = ceil_div(L, AP_STRIP);
     const long long threads = (long long)(C / 2) * n_strips;
     dim3 grid((unsigned)ceil_div64(threads, 256), B);
-    aa_snake_pair_kernel<<<grid, 256, 0, s>>>(x, y, (__half*)y_hi, (__half*)y_lo, L, C, n_strips, log_alpha, up_f, down_f);
+    // PTTSPP_AA_TB (experiments): outputs per rolling block; 8 -> 101 registers, 2 CTAs per SM; 4 -> 80 registers, 3 CTAs
+    static const int tb = [] { const char* e = getenv("PTTSPP_AA_TB"); return e ? atoi(e) : 8; }();
+    if (tb == 4)
+      aa_snake_pair_kernel<4, 3><<<grid, 256, 0, s>>>(x, y, (__half*)y_hi, (__half*)y_lo, L, C, n_strips, log_alpha, up_f, down_f);
+    else if (tb == 2)
+      aa_snake_pair_kernel<2, 4><<<grid, 256, 0, s>>>(x, y, (__half*)y_hi, (__half*)y_lo, L, C, n_strips, log_alpha, up_f, down_f);
+    else
+      aa_snake_pair_kernel<8, 2><<<grid, 256, 0, s>>>(x, y, (__half*)y_hi, (__half*)y_lo, L, C, n_strips, log_alpha, up_f, down_f);
     PT_LAUNCHED();
     return;
   }

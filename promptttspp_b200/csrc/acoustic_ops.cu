@@ -394,9 +394,9 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(float* __restrict__ x,
       x[idx] = xn;
       if (xp_hi) {
         const int64_t pidx = ((int64_t)b * T + t) * Mp + m;
-        const __half hh = __float2half_rn(xn);
+        const __half hh = pt_f2h_sat(xn);
         xp_hi[pidx] = hh;
-        xp_lo[pidx] = __float2half_rn(xn - __half2float(hh));
+        xp_lo[pidx] = pt_f2h_sat(xn - __half2float(hh));
       }
     }
   }

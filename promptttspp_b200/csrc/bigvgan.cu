@@ -39,6 +39,11 @@ struct pttspp_bigvgan {
   pttspp::DeviceBuffers dev;
   bool finalized = false;
   bool use_umma = true;  // PTTSPP_DISABLE_UMMA=1: every conv on the fp32 CUDA-core path
+  // PTTSPP_AA_FUSE=1: the activation inside the conv kernel's producer warps on the 32 / 64-channel stages.  Bit-identical,
+  // but measured SLOWER (48.0 vs 42.9 ms per cfg3 forward: the activation is FP32-pipe / latency bound and needs all 16
+  // resident warps of an SM, the 7-8 producer warps of the fused kernel take 2.8x the stand-alone kernel's time --
+  // profiles/r02_aa_conv_fusion_experiment.txt), so it stays opt-in.
+  bool fuse_aa = false;
   pttspp::PackedConv conv_pre, conv_post;
   std::vector<pttspp::UpsampleW> ups;
   std::vector<std::vector<std::vector<pttspp::AMPLayerW>>> mrfs;  // [stage][kernel][layer]
@@ -326,6 +331,8 @@ extern "C" int pttspp_bigvgan_finalize(pttspp_bigvgan_t* h, pttspp_stream_t) {
   {
     const char* e = getenv("PTTSPP_DISABLE_UMMA");
     h->use_umma = !(e && e[0] == '1');
+    const char* f = getenv("PTTSPP_AA_FUSE");
+    h->fuse_aa = (f && f[0] == '1');
   }
   h->conv_pre = load_conv1d(h->store, h->dev, "conv_pre", C0, c.in_channel, 7, 1, 3);
   for (int i = 0; i < c.num_upsamples; ++i) {
@@ -451,8 +458,10 @@ static void bigvgan_forward_impl(pttspp_bigvgan_t* h, const float* mel, const fl
   transpose_bct_to_btc(mel, t1, B, c.in_channel, T, s);
   // operand planes of the current stage input (for the tensor-core transposed convs) live in the t2 region, which
   // is free whenever a stage's last conv or conv_pre runs: hi = first half, lo = second half
+  // (a FUSED last conv reads its fp32 input from t2, so its output planes go to the t1 region, unused in fused layers)
+  float* plane_region = t2;
   auto stage_planes = [&](int64_t n_elems, uint16_t*& ph, uint16_t*& pl) {
-    ph = reinterpret_cast<uint16_t*>(t2);
+    ph = reinterpret_cast<uint16_t*>(plane_region);
     pl = ph + n_elems;
   };
   {
@@ -513,19 +522,35 @@ static void bigvgan_forward_impl(pttspp_bigvgan_t* h, const float* mel, const fl
         auto use_planes = [&](pttspp_conv1d_desc& q, const PackedConv& pc) {
           q.in_hi = ph; q.in_lo = pl; q.w_hi = pc.w_hi; q.w_lo = pc.w_lo; q.w_scale_inv = pc.w_scale_inv; q.impl = 2;
         };
-        if (um) aa_snake_cl(cur, nullptr, B, L, C, w.act1.log_alpha, w.act1.up_f, w.act1.down_f, s, ph, pl, w.act1.sym);
-        else aa_snake_cl(cur, t1, B, L, C, w.act1.log_alpha, w.act1.up_f, w.act1.down_f, s, nullptr, nullptr, w.act1.sym);
-        {
+        // narrow stages (32 / 64 channels): the activation runs inside the conv kernel's producer warps, the activated
+        // tensor never exists in HBM (conv1d_umma.cu: aa_conv_wres_kernel); bit-identical to the two-launch path
+        auto fused_desc = [&](const PackedConv& pc, const float* in, float* out) {
+          auto q = conv_desc(pc, in, B, L, out);
+          q.w_hi = pc.w_hi; q.w_lo = pc.w_lo; q.w_scale_inv = pc.w_scale_inv; q.impl = 2;
+          return q;
+        };
+        bool fuse1 = false, fuse2 = false;
+        if (um && h->fuse_aa && w.act1.sym && w.act2.sym) {
+          fuse1 = aa_conv1d_supported(fused_desc(w.conv1, cur, t2));
+          fuse2 = aa_conv1d_supported(fused_desc(w.conv2, t2, t1));
+        }
+        if (fuse1) {
+          aa_conv1d_cl(fused_desc(w.conv1, cur, t2), w.act1.log_alpha, w.act1.up_f, w.act1.down_f, s);
+        } else {
+          if (um) aa_snake_cl(cur, nullptr, B, L, C, w.act1.log_alpha, w.act1.up_f, w.act1.down_f, s, ph, pl, w.act1.sym);
+          else aa_snake_cl(cur, t1, B, L, C, w.act1.log_alpha, w.act1.up_f, w.act1.down_f, s, nullptr, nullptr, w.act1.sym);
           auto d = conv_desc(w.conv1, t1, B, L, t2);
           if (um) use_planes(d, w.conv1);
           conv1d_cl(d, s);
         }
-        if (um) aa_snake_cl(t2, nullptr, B, L, C, w.act2.log_alpha, w.act2.up_f, w.act2.down_f, s, ph, pl, w.act2.sym);
-        else aa_snake_cl(t2, t1, B, L, C, w.act2.log_alpha, w.act2.up_f, w.act2.down_f, s, nullptr, nullptr, w.act2.sym);
+        if (!fuse2) {
+          if (um) aa_snake_cl(t2, nullptr, B, L, C, w.act2.log_alpha, w.act2.up_f, w.act2.down_f, s, ph, pl, w.act2.sym);
+          else aa_snake_cl(t2, t1, B, L, C, w.act2.log_alpha, w.act2.up_f, w.act2.down_f, s, nullptr, nullptr, w.act2.sym);
+        }
         const bool last = (l == c.num_dilations - 1);
         float* dst = last ? bxs : ((cur == bA) ? bB : bA);
-        auto d = conv_desc(w.conv2, t1, B, L, dst);
-        if (um) use_planes(d, w.conv2);
+        auto d = fuse2 ? fused_desc(w.conv2, t2, dst) : conv_desc(w.conv2, t1, B, L, dst);
+        if (um && !fuse2) use_planes(d, w.conv2);
         d.res = cur; d.res_bs = (int64_t)L * C; d.res_ld = C;
         if (last) {  // xs = (j ? xs : 0) + (x + y); the last block divides by num_kernels (bigvgan.py:124-127)
           d.beta = (j == 0) ? 0.f : 1.f;
@@ -534,12 +559,14 @@ static void bigvgan_forward_impl(pttspp_bigvgan_t* h, const float* mel, const fl
             if (i + 1 < c.num_upsamples && !h->ups[i + 1].w_hi.empty()) {
               // the finished stage output also leaves as operand planes for the next transposed conv
               uint16_t *oh, *ol;
+              plane_region = fuse2 ? t1 : t2;
               stage_planes((int64_t)B * L * C, oh, ol);
               d.out_hi = oh; d.out_lo = ol; d.out_plane_bs = (int64_t)L * C; d.out_plane_ld = C;
             }
           }
         }
-        conv1d_cl(d, s);
+        if (fuse2) aa_conv1d_cl(d, w.act2.log_alpha, w.act2.up_f, w.act2.down_f, s);
+        else conv1d_cl(d, s);
         cur = dst;
       }
     }

@@ -1,5 +1,8 @@
 // Shared helpers for the pttspp_b200 CUDA sources (sm_100a only).
 #pragma once
+#ifdef __CUDACC__
+#include <cuda_fp16.h>
+#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -75,6 +78,22 @@ struct ProfScope {
   ~ProfScope();
 };
 
+#ifdef __CUDACC__
+// fp32 -> fp16 with saturation to the largest finite half (one F2FP.SATFINITE, the cost of the plain conversion): the
+// hi plane of a split-fp16 operand never becomes inf, so an activation beyond fp16's range (|v| >= 65520) degrades to a
+// clipped value (exact up to 2 * 65504 through the lo plane) instead of inf - inf = NaN downstream.
+__device__ __forceinline__ __half pt_f2h_sat(float v) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return __ushort_as_half(r);
+}
+__device__ __forceinline__ __half2 pt_f2h2_sat(float a, float b) {  // .x = a, .y = b
+  unsigned r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return *reinterpret_cast<__half2*>(&r);
+}
+#endif
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
@@ -99,6 +118,11 @@ void layernorm_cl(const pttspp_layernorm_desc& d, cudaStream_t s);
 void aa_snake_cl(const float* x, float* y, int B, int L, int C, const float* log_alpha, const float* up_f,
                  const float* down_f, cudaStream_t s, void* y_hi = nullptr, void* y_lo = nullptr,
                  int symmetric_filters = 0);
+// Fused AA-Snake -> conv (conv1d_umma.cu): d.in = fp32 PRE-activation rows [B][T][C]; the activated operand planes are
+// produced inside the conv kernel.  Needs exactly symmetric filters (as the channel-pair activation kernel).
+bool aa_conv1d_supported(const pttspp_conv1d_desc& d);
+void aa_conv1d_cl(const pttspp_conv1d_desc& d, const float* log_alpha, const float* up_f, const float* down_f,
+                  cudaStream_t s);
 void duration_quantize(const float* log_d, const int64_t* phone_len, int B, int Tx, int64_t* dur,
                        int64_t* frame_len, cudaStream_t s);
 void length_regulate(const float* x, const int64_t* dur, int B, int Tx, int C, int Ty, float* out,

@@ -22,6 +22,7 @@
 #include <mutex>
 #include <unordered_map>
 
+#include "aa_math.cuh"
 #include "common.h"
 #include "conv_epilogue.cuh"
 #include "umma_ptx.cuh"
@@ -667,12 +668,26 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
             const uint32_t acc_main = acc0 + (uint32_t)((rel % (NACC - 1)) * BN);
             const uint32_t first_main = (rel >= NACC - 1) ? 1u : 0u;
             if (elect_one()) {
+              if constexpr (NACC == 2) {
+                // one main accumulator directly followed by the cross accumulator, and the stage holds [W_hi | W_lo] back
+                // to back: x_hi . [W_hi | W_lo] is ONE N = 2*BN instruction (main | cross), then x_lo . W_hi -- the A planes
+                // are fetched from shared memory twice instead of three times per k step (the operand fetch path, not the
+                // tensor pipe, bounds the narrow tiles: ncu tc wavefronts 76 % on the weight-resident kernel)
+                constexpr uint32_t idesc2 = umma_idesc_f16(UM_BM, 2 * BN);
+#pragma unroll
+                for (int kk = 0; kk < UM_BK / 16; ++kk) {
+                  const uint64_t adv = (uint64_t)(kk * 2);
+                  umma_f16(acc0, dAh + adv, dBh + adv, idesc2, (kk != 0) ? 1u : (rel != 0 ? 1u : 0u));
+                  umma_f16(acc_cross, dAl + adv, dBh + adv, idesc, 1u);
+                }
+              } else {
 #pragma unroll
               for (int kk = 0; kk < UM_BK / 16; ++kk) {
                 const uint64_t adv = (uint64_t)(kk * 2);  // 16 halves = 32 bytes along K inside the swizzle span
                 umma_f16(acc_cross, dAl + adv, dBh + adv, idesc, (kk != 0) ? 1u : (rel != 0 ? 1u : 0u));
                 umma_f16(acc_cross, dAh + adv, dBl + adv, idesc, 1u);
                 umma_f16(acc_main, dAh + adv, dBh + adv, idesc, (kk != 0) ? 1u : first_main);
+              }
               }
               umma_commit(empty_bar(s));  // frees the stage once these MMAs have read it
               if (it + 1 == it1) umma_commit(tfull_bar(u));  // accumulator buffer u complete
@@ -1145,8 +1160,10 @@ conv1d_umma_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
 #pragma unroll
                 for (int kk = 0; kk < UM_BK / 16; ++kk) {
                   const uint64_t adv = (uint64_t)(kk * 2);
-                  umma_f16_pair(acc_cross, dAl + adv, dBh + adv, idesc, kk ? 1u : first);
-                  umma_f16_pair(acc_cross, dAh + adv, dBl + adv, idesc, 1u);
+                  // cross terms in the order of the streaming kernel's stacked issue (hi.lo, then lo.hi): a conv gives
+                  // the same bits whichever of the two kernels its batch size selects
+                  umma_f16_pair(acc_cross, dAh + adv, dBl + adv, idesc, kk ? 1u : first);
+                  umma_f16_pair(acc_cross, dAl + adv, dBh + adv, idesc, 1u);
                   umma_f16_pair(acc_main, dAh + adv, dBh + adv, idesc, (kk || NACC == 1) ? 1u : first);
                 }
               } else if ((mma_order & 3) == 1) {
@@ -1386,6 +1403,295 @@ conv1d_umma_c32_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(u));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- fused anti-aliased Snake -> weight-resident conv -------------------------------------------------------------
+// BigVGAN's AMP layer is  x -> AA-Snake -> conv1 -> AA-Snake -> conv2 (+x)  (vocoders/bigvgan.py:42-47,
+// layers/activations.py:22-138).  With the activation as its own launch the activated tensor makes a round trip through
+// HBM as split-fp16 operand planes (write 4 B + read 4 B per element, 18 times per stage).  Here the conv kernel's TMA
+// producer is replaced by ACTIVATION-PRODUCER warps: they read the fp32 pre-activation rows of the tile (128 rows + the
+// conv halo + the activation's own +-5 rows), run the 2x up-sample -> Snake -> 2x down-sample in packed fp32x2 registers
+// (aa_math.cuh, the arithmetic of aa_snake_pair_kernel in the same order: results are bit-identical to the two-launch
+// path) and write the result straight into the swizzled K-major operand stage that the MMA descriptors read; the
+// activated tensor never exists in HBM.  Rows outside [0, L) are the conv's zero padding (written as zeros), the
+// activation's own replicate padding is applied on the up-sampled signal exactly as in the stand-alone kernel.
+//   warps [0, EW)         epilogue (TMEM -> registers -> bias / residual / MRF average -> HBM)
+//   warp  EW              weight TMA (once) + MMA issuer
+//   warps (EW, EW + G*NG] NG producer groups of G warps; group j produces tiles j, j + NG, ... of this CTA into the
+//                         operand ring (stage = tile sequence number % NST); a thread owns one channel pair and one
+//                         contiguous strip of the tile's rows
+
+// one strip of activated rows [t_lo, t_hi) of one channel pair -> operand planes in shared memory
+template <int ROWB, int AF_TB>
+__device__ __forceinline__ void aa_strip_to_stage(const float* __restrict__ xb, const int ld, const int L, const int t_lo,
+                                                  const int t_hi, const int row0, const uint32_t s_hi,
+                                                  const uint32_t plane_bytes, const int cp, const f32x2 (&e)[6],
+                                                  const f32x2 (&g)[6], const f32x2 a2, const f32x2 inv_alpha) {
+  constexpr uint32_t SWZ = (ROWB == 128) ? 7u : 3u;  // SWIZZLE_128B / SWIZZLE_64B: 16-byte chunk ^= address bits 7..
+  f32x2 sv[2 * AF_TB + 10], xw[AF_TB + 5], xn[AF_TB];
+  {
+    // the 10 up-sampled values in front of the strip (indices 2*t_lo - 5 .. 2*t_lo + 4) from x[t_lo - 5 .. t_lo + 4]
+    f32x2 xs[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      int l = t_lo - 5 + i;
+      l = l < 0 ? 0 : (l > L - 1 ? L - 1 : l);
+      xs[i] = *reinterpret_cast<const f32x2*>(xb + (int64_t)l * ld);
+    }
+#pragma unroll
+    for (int i = 0; i < AF_TB; ++i) {
+      int l = t_lo + 5 + i;
+      l = l > L - 1 ? L - 1 : l;
+      xn[i] = *reinterpret_cast<const f32x2*>(xb + (int64_t)l * ld);
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      f32x2 u = pk2(0.f, 0.f);
+      if ((i & 1) == 0) {
+#pragma unroll
+        for (int dd = 0; dd < 6; ++dd) u = fma2(xs[i / 2 + dd], e[dd], u);
+      } else {
+#pragma unroll
+        for (int dd = 0; dd < 6; ++dd) u = fma2(xs[(i - 1) / 2 + dd], e[5 - dd], u);
+      }
+      sv[i] = snake2(u, a2, inv_alpha);
+    }
+    // replicate padding of the up-sampled signal at both ends of the utterance
+#pragma unroll
+    for (int i = 4; i >= 0; --i)
+      if (2 * t_lo - 5 + i < 0) sv[i] = sv[i + 1];
+    const int imax = 2 * (L - t_lo) + 4;
+#pragma unroll
+    for (int i = 1; i < 10; ++i)
+      if (i > imax) sv[i] = sv[i - 1];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) xw[i] = xs[5 + i];
+  }
+#pragma unroll 1
+  for (int tb = t_lo; tb < t_hi; tb += AF_TB) {
+#pragma unroll
+    for (int i = 0; i < AF_TB; ++i) xw[5 + i] = xn[i];
+    if (tb + AF_TB < t_hi) {  // request the next block's inputs now
+#pragma unroll
+      for (int i = 0; i < AF_TB; ++i) {
+        int l = tb + AF_TB + 5 + i;
+        l = l > L - 1 ? L - 1 : l;
+        xn[i] = *reinterpret_cast<const f32x2*>(xb + (int64_t)l * ld);
+      }
+    }
+    // new up-sampled values: sv[i] <-> index 2*tb - 5 + i, i = 10 .. 2*TB + 9
+#pragma unroll
+    for (int i = 10; i < 2 * AF_TB + 10; ++i) {
+      f32x2 u = pk2(0.f, 0.f);
+      if ((i & 1) == 0) {
+#pragma unroll
+        for (int dd = 0; dd < 6; ++dd) u = fma2(xw[i / 2 + dd - 5], e[dd], u);
+      } else {
+#pragma unroll
+        for (int dd = 0; dd < 6; ++dd) u = fma2(xw[(i - 1) / 2 + dd - 5], e[5 - dd], u);
+      }
+      sv[i] = snake2(u, a2, inv_alpha);
+    }
+    if (tb + AF_TB + 4 > L - 1) {
+      const int imax = 2 * (L - tb) + 4;  // block index of up-sampled sample 2L-1: later ones repeat it
+#pragma unroll
+      for (int i = 10; i < 2 * AF_TB + 10; ++i)
+        if (i > imax) sv[i] = sv[i - 1];
+    }
+#pragma unroll
+    for (int t = 0; t < AF_TB; ++t) {
+      if (tb + t < t_hi) {
+        f32x2 acc = pk2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc = fma2(sv[2 * t + k], g[k < 6 ? k : 11 - k], acc);
+        float a0, a1;
+        upk2(acc, a0, a1);
+        uint32_t hw, lw;
+        split2_f16(a0, a1, hw, lw);
+        uint32_t off = (uint32_t)(tb + t - row0) * ROWB + (uint32_t)cp * 4u;
+        off ^= ((off >> 7) & SWZ) << 4;
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(s_hi + off), "r"(hw) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(s_hi + plane_bytes + off), "r"(lw) : "memory");
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) sv[i] = sv[2 * AF_TB + i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) xw[i] = xw[AF_TB + i];
+  }
+}
+
+template <int US_C, int EW, int G, int NG, int TB>
+__global__ void __launch_bounds__((EW + 1 + G * NG) * 32, 1)
+aa_conv_wres_kernel(const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
+                    const pttspp_conv1d_desc d, const float* __restrict__ log_alpha, const float* __restrict__ up_f,
+                    const float* __restrict__ down_f, const int n_mt, const int n_tiles, const int rowsA, const int nst,
+                    const int dbg) {
+  constexpr int NBUF = 512 / (2 * US_C);  // accumulator buffers (main | cross): all 512 TMEM columns
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t ROWB = US_C * 2;  // bytes per operand row
+  constexpr int MAX_NST = 6;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t w_bytes = 2u * (uint32_t)d.K * US_C * ROWB;  // per tap: C hi rows followed by C lo rows
+  const uint32_t a_plane = (uint32_t)rowsA * ROWB;
+  const uint32_t a_stage = ((2u * a_plane) + 1023u) & ~1023u;
+  const uint32_t ring = base + ((w_bytes + 1023u) & ~1023u);
+  const uint32_t bars_off = ((w_bytes + 1023u) & ~1023u) + (uint32_t)nst * a_stage;
+  const uint32_t bars = base + bars_off;
+  // fullW, fullA[MAX_NST], emptyA[MAX_NST], tfull[NBUF], tempty[NBUF]
+  constexpr int NBARS = 1 + 2 * MAX_NST + 2 * NBUF;
+  const uint32_t fullW = bars;
+  auto fullA = [&](int st) { return bars + (1 + st) * 8; };
+  auto emptyA = [&](int st) { return bars + (1 + MAX_NST + st) * 8; };
+  auto tfull_bar = [&](int u) { return bars + (1 + 2 * MAX_NST + u) * 8; };
+  auto tempty_bar = [&](int u) { return bars + (1 + 2 * MAX_NST + NBUF + u) * 8; };
+  const uint32_t tmem_slot = bars + NBARS * 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + bars_off + NBARS * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int W_MMA = EW;
+  if (threadIdx.x == 0) {
+    mbar_init(fullW, 1);
+    for (int st = 0; st < MAX_NST; ++st) {
+      mbar_init(fullA(st), G);  // one arrival per producer warp of the group
+      mbar_init(emptyA(st), 1);
+    }
+    for (int u = 0; u < NBUF; ++u) {
+      mbar_init(tfull_bar(u), 1);
+      mbar_init(tempty_bar(u), EW);
+    }
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) {
+    if (lane == 0) {
+      tma_prefetch_desc(&mapBh);
+      tma_prefetch_desc(&mapBl);
+    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == W_MMA) {
+    // ================= weights (once) + MMA issuer =================
+    if (elect_one()) {
+      mbar_expect_tx(fullW, w_bytes);
+      for (int tap = 0; tap < d.K; ++tap) {
+        tma_load_2d(base + (uint32_t)tap * (2 * US_C * ROWB), &mapBh, fullW, 0, tap * US_C);
+        tma_load_2d(base + (uint32_t)tap * (2 * US_C * ROWB) + US_C * ROWB, &mapBl, fullW, 0, tap * US_C);
+      }
+    }
+    __syncwarp();
+    constexpr uint32_t idesc = umma_idesc_f16(UM_BM, US_C);
+    constexpr uint32_t idesc2 = umma_idesc_f16(UM_BM, 2 * US_C);
+    const uint64_t descW = (US_C == 32) ? umma_desc_k_sw64(base) : umma_desc_k_sw128(base);
+    mbar_wait_warp(fullW, 0);
+    tc_fence_after();
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++g) {
+      const int st = (int)(g % (uint32_t)nst), u = g % NBUF;
+      mbar_wait_warp(tempty_bar(u), ((g / NBUF) & 1u) ^ 1u);
+      mbar_wait_warp_sleep(fullA(st), (g / (uint32_t)nst) & 1u, 64);
+      tc_fence_after();
+      const uint32_t acc_main = tmem_base + (uint32_t)(u * 2 * US_C);
+      const uint32_t acc_cross = acc_main + (uint32_t)US_C;
+      const uint64_t descA = (US_C == 32) ? umma_desc_k_sw64(ring + (uint32_t)st * a_stage)
+                                          : umma_desc_k_sw128(ring + (uint32_t)st * a_stage);
+      if (elect_one()) {
+        for (int tap = 0; tap < d.K; ++tap) {
+          const uint64_t dAh = descA + (uint64_t)(((uint32_t)(tap * d.dil) * ROWB) >> 4);  // taps share the halo block
+          const uint64_t dAl = dAh + (uint64_t)(a_plane >> 4);
+          const uint64_t dBh = descW + (uint64_t)(((uint32_t)tap * (2 * US_C * ROWB)) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < US_C / 16; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 2);
+            const uint32_t acc = (tap | kk) ? 1u : 0u;
+            umma_f16(acc_main, dAh + adv, dBh + adv, idesc2, acc);  // x_hi . [W_hi | W_lo] -> main | cross
+            umma_f16(acc_cross, dAl + adv, dBh + adv, idesc, 1u);   // x_lo . W_hi
+          }
+        }
+        umma_commit(emptyA(st));
+        umma_commit(tfull_bar(u));
+      }
+      __syncwarp();
+    }
+  } else if (warp < EW) {
+    // ================= epilogue =================
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++g) {
+      const int mt = tile % n_mt, b = tile / n_mt;
+      const int u = g % NBUF;
+      // the producers are issue bound and this warp has NBUF accumulator buffers of slack: request the tile's residual
+      // rows into L2, then sleep-poll (the epilogue's own wait below passes at once)
+      epi_rl_prefetch_tile<US_C, EW>(d, 0, mt, b, warp, lane);
+      mbar_wait_warp_sleep(tfull_bar(u), (g / NBUF) & 1u, 256);
+      umma_tile_epilogue_rl<US_C, 2, EW>(d, 0, mt, b, u, (g / NBUF) & 1u, warp, lane, tmem_base, tfull_bar(u), 1,
+                                         (dbg & 2) ? 64 : 0);  // timing experiment: no epilogue work
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(u));
+    }
+  } else {
+    // ================= activation producers =================
+    const int aw = warp - (EW + 1);
+    const int grp = aw / G;
+    const int tid_g = (aw % G) * 32 + lane;
+    constexpr int P = US_C / 2;  // channel pairs
+    constexpr int NSTRIPS = G * 32 / P;
+    const int cp = tid_g % P, strip = tid_g / P;
+    const int L = d.T_in;
+    const int RN = UM_BM + (d.K - 1) * d.dil;  // operand rows the taps read
+    const int slen = (RN + NSTRIPS - 1) / NSTRIPS;
+    f32x2 e[6], gd[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const float ef = 2.f * up_f[10 - 2 * q];
+      e[q] = pk2(ef, ef);
+      gd[q] = pk2(down_f[q], down_f[q]);
+    }
+    const float al0 = expf(log_alpha[2 * cp]), al1 = expf(log_alpha[2 * cp + 1]);
+    const f32x2 inv_alpha = pk2(1.f / (al0 + 1e-9f), 1.f / (al1 + 1e-9f));
+    const f32x2 a2 = pk2(al0, al1);
+    for (uint32_t g = (uint32_t)grp;; g += NG) {
+      const long long tile_ll = (long long)blockIdx.x + (long long)g * gridDim.x;
+      if (tile_ll >= n_tiles) break;
+      const int tile = (int)tile_ll;
+      const int st = (int)(g % (uint32_t)nst);
+      mbar_wait_warp(emptyA(st), ((g / (uint32_t)nst) & 1u) ^ 1u);
+      const int mt = tile % n_mt, b = tile / n_mt;
+      const int row0 = d.m_begin + mt * UM_BM - d.pad;  // utterance row of operand row 0
+      const int t_begin = row0 + strip * slen;
+      const int t_end = min(row0 + RN, t_begin + slen);
+      const int t_lo = max(t_begin, 0), t_hi = min(t_end, L);
+      const uint32_t s_hi = ring + (uint32_t)st * a_stage;
+      // rows outside the utterance: the conv's zero padding
+      for (int t = t_begin; t < t_end; ++t) {
+        if (t >= t_lo && t < t_hi) continue;
+        uint32_t off = (uint32_t)(t - row0) * ROWB + (uint32_t)cp * 4u;
+        off ^= ((off >> 7) & ((ROWB == 128) ? 7u : 3u)) << 4;
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(s_hi + off), "r"(0u) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(s_hi + a_plane + off), "r"(0u) : "memory");
+      }
+      if (t_lo < t_hi && !(dbg & 1))  // (dbg & 1: timing experiment without the activation)
+        aa_strip_to_stage<(int)ROWB, TB>(d.in + (int64_t)b * d.in_bs + 2 * cp, d.in_ld, L, t_lo, t_hi, row0, s_hi, a_plane, cp,
+                                     e, gd, a2, inv_alpha);
+      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy operand reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(fullA(st));
     }
   }
   tc_fence_before();
@@ -1846,6 +2152,64 @@ void conv1d_umma_c32_launch(const pttspp_conv1d_desc& d_in, cudaStream_t s) {
 #undef PT_WRES
 }
 
+// fused AA-Snake -> conv: the weight-resident geometries, fp32 pre-activation input
+bool aa_conv1d_ok(const pttspp_conv1d_desc& d) {
+  if (!((d.Cin == 32 && d.Cout == 32 && d.K <= US_MAXK) || (d.Cin == 64 && d.Cout == 64 && d.K <= 7))) return false;
+  const int C = d.Cin, rowb = C * 2;
+  const int rowsA = UM_BM + round_up((d.K - 1) * d.dil, 8);
+  const size_t w_bytes = round_up(2 * d.K * C * rowb, 1024), a_stage = round_up(2 * rowsA * rowb, 1024);
+  if (w_bytes + 2 * a_stage + 4096 > 227 * 1024) return false;
+  return d.K >= 1 && d.in && (reinterpret_cast<uintptr_t>(d.in) & 7) == 0 && d.in_ld % 2 == 0 && d.in_bs % 2 == 0 &&
+         d.w_hi && d.w_lo && d.in_stride == 1 && !d.in_len && !d.in_add && aligned16(d.w_hi) && aligned16(d.w_lo) &&
+         d.w_scale_inv > 0.f && rowsA <= 256 && d.act != PTTSPP_ACT_GATE && epilogue_rl_ok(d);
+}
+
+template <int C, int EW, int G, int NG, int TB>
+void aa_conv1d_launch_t(const pttspp_conv1d_desc& d, const CUtensorMap& mBh, const CUtensorMap& mBl, const float* log_alpha,
+                        const float* up_f, const float* down_f, int rowsA, int nst, size_t smem, int num_sms,
+                        cudaStream_t s) {
+  auto kern = aa_conv_wres_kernel<C, EW, G, NG, TB>;
+  ensure_smem_optin((const void*)kern, 227 * 1024);
+  const int n_mt = ceil_div(d.M, UM_BM);
+  const long long n_tiles = (long long)n_mt * d.B;
+  PT_CHECK(n_tiles < (1ll << 30), "conv1d: too many tiles");
+  const int grid = (int)std::min<long long>(n_tiles, num_sms);
+  static const int dbg = [] { const char* e = getenv("PTTSPP_AAF_DBG"); return e ? atoi(e) : 0; }();  // timing experiments
+  kern<<<grid, (EW + 1 + G * NG) * 32, smem, s>>>(mBh, mBl, d, log_alpha, up_f, down_f, n_mt, (int)n_tiles, rowsA, nst, dbg);
+  PT_LAUNCHED();
+}
+
+void aa_conv1d_launch(const pttspp_conv1d_desc& d_in, const float* log_alpha, const float* up_f, const float* down_f,
+                      cudaStream_t s) {
+  pttspp_conv1d_desc d = d_in;
+  d.acc_scale = d_in.acc_scale * d_in.w_scale_inv;
+  const int num_sms = device_num_sms();
+  const int C = d.Cin;
+  const int rowb = C * 2;
+  const CUtensorMapSwizzle swz = (C == 32) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const int rowsA = UM_BM + round_up((d.K - 1) * d.dil, 8);
+  const uint64_t wdims[2] = {(uint64_t)C, (uint64_t)d.K * C};
+  const uint64_t wstr[1] = {(uint64_t)C * 2};
+  const uint32_t wbox[2] = {(uint32_t)C, (uint32_t)C};
+  const CUtensorMap mBh = make_map(d.w_hi, 2, wdims, wstr, wbox, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, swz);
+  const CUtensorMap mBl = make_map(d.w_lo, 2, wdims, wstr, wbox, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, swz);
+  const size_t w_bytes = round_up(2 * d.K * C * rowb, 1024);
+  const size_t a_stage = round_up(2 * rowsA * rowb, 1024);
+  const size_t misc = (1 + 2 * 6 + 2 * US_MAX_NBUF) * 8 + 16 + 1024;
+  const size_t cap = 227 * 1024;
+  PT_CHECK(w_bytes + 2 * a_stage + misc <= cap, "aa_conv1d: shared memory budget exceeded");
+  const int nst = (int)std::min<size_t>(4, (cap - w_bytes - misc) / a_stage);
+  const size_t smem = w_bytes + (size_t)nst * a_stage + misc;
+  static const int cfg = [] { const char* e = getenv("PTTSPP_AAF_CFG"); return e ? atoi(e) : 0; }();  // experiments
+  if (cfg == 1) {
+    if (C == 32) aa_conv1d_launch_t<32, 8, 7, 2, 4>(d, mBh, mBl, log_alpha, up_f, down_f, rowsA, nst, smem, num_sms, s);
+    else aa_conv1d_launch_t<64, 8, 7, 2, 4>(d, mBh, mBl, log_alpha, up_f, down_f, rowsA, nst, smem, num_sms, s);
+  } else {
+    if (C == 32) aa_conv1d_launch_t<32, 4, 4, 2, 8>(d, mBh, mBl, log_alpha, up_f, down_f, rowsA, nst, smem, num_sms, s);
+    else aa_conv1d_launch_t<64, 8, 7, 1, 8>(d, mBh, mBl, log_alpha, up_f, down_f, rowsA, nst, smem, num_sms, s);
+  }
+}
+
 }  // namespace
 
 bool conv1d_umma_supported(const pttspp_conv1d_desc& d) {
@@ -1970,12 +2334,17 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
   const int accumulations = d.K * d.Cin / 16;
   const bool narrow = !d2_in && (total_cout <= 64 || accumulations > 64);
   if (narrow) {
-    constexpr int BN = 64, ST = 4, NA = 4;
+    constexpr int BN = 64, ST = 4;
     const uint32_t wbox64[2] = {UM_BK, BN};
     const CUtensorMap mBh64 = make_map(d.w_hi, 2, wdims, wstr, wbox64);
     const CUtensorMap mBl64 = make_map(d.w_lo, 2, wdims, wstr, wbox64);
     const size_t smem = (size_t)ST * UmmaSmem<BN>::STAGE_BYTES + 256 + UM_EPI_WARPS * 2048 + 1024;
-    auto kern = (tma_out & 4) ? conv1d_umma_kernel<BN, ST, NA, 1, false> : conv1d_umma_kernel<BN, ST, NA, 0, false>;
+    // one main accumulator + the stacked [W_hi | W_lo] issue (two MMAs per k step) by default: the 64-column tile is
+    // bound by the operand fetch, and <= 64 truncating accumulations stay far inside the parity bars (measured);
+    // PTTSPP_UMMA_NARROW_NACC=4 restores three round-robin main accumulators (three MMAs per k step)
+    static const bool rr = [] { const char* e = getenv("PTTSPP_UMMA_NARROW_NACC"); return e && e[0] == '4'; }();
+    auto kern = rr ? ((tma_out & 4) ? conv1d_umma_kernel<BN, ST, 4, 1, false> : conv1d_umma_kernel<BN, ST, 4, 0, false>)
+                   : ((tma_out & 4) ? conv1d_umma_kernel<BN, ST, 2, 1, false> : conv1d_umma_kernel<BN, ST, 2, 0, false>);
     ensure_smem_optin((const void*)kern, (int)smem);
     const int nnt = ceil_div(total_cout, BN);
     const long long n_tiles = (long long)n_mt * nnt * d.B;
@@ -2004,6 +2373,19 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
 void conv1d_umma_cl(const pttspp_conv1d_desc& d, cudaStream_t s) {
   if (conv1d_umma_c32_ok(d)) conv1d_umma_c32_launch(d, s);
   else conv1d_umma_launch(d, nullptr, s);
+}
+
+bool aa_conv1d_supported(const pttspp_conv1d_desc& d) { return aa_conv1d_ok(d); }
+
+void aa_conv1d_cl(const pttspp_conv1d_desc& d, const float* log_alpha, const float* up_f, const float* down_f,
+                  cudaStream_t s) {
+  PT_CHECK(log_alpha && up_f && down_f, "aa_conv1d: null activation parameter");
+  PT_CHECK(aa_conv1d_ok(d), "aa_conv1d: unsupported descriptor (32 channels with <= 11 taps or 64 channels with <= 7 taps, "
+                            "fp32 input rows, split-fp16 weights, 32-byte aligned epilogue tensors)");
+  const double rows = (double)d.B * d.M;
+  // the activation's algorithmic traffic is gone; account the conv's flops and the fused pass's bytes (read x + write out)
+  ProfScope prof(PROF_CONV_UMMA, s, 2.0 * rows * d.Cout * (double)d.Cin * d.K, 4.0 * rows * (d.Cin + d.Cout));
+  aa_conv1d_launch(d, log_alpha, up_f, down_f, s);
 }
 
 void conv1d_umma_dual_cl(const pttspp_conv1d_desc& d1, const pttspp_conv1d_desc& d2, cudaStream_t s) {
@@ -2042,3 +2424,10 @@ extern "C" int pttspp_umma_probe(const void* a_half, int rows, const void* b_hal
   PT_API_END
 }
 
+extern "C" int pttspp_aa_conv1d_cl(const pttspp_conv1d_desc* d, const float* log_alpha, const float* up_filter,
+                                   const float* down_filter, pttspp_stream_t stream) {
+  PT_API_BEGIN
+  PT_CHECK(d, "null descriptor");
+  pttspp::aa_conv1d_cl(*d, log_alpha, up_filter, down_filter, (cudaStream_t)stream);
+  PT_API_END
+}

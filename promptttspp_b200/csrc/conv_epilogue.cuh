@@ -22,8 +22,8 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 }
 
 __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
-  hi = __float2half_rn(v);
-  lo = __float2half_rn(v - __half2float(hi));
+  hi = pt_f2h_sat(v);
+  lo = pt_f2h_sat(v - __half2float(hi));
 }
 
 // Four consecutive pre-activation columns col..col+3 (col % 4 == 0) of output row `row` of batch `b`.

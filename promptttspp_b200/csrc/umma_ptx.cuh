@@ -49,6 +49,31 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
   if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
   __syncwarp();
 }
+// the same wait for warps that are NOT on the critical path of a kernel whose other warps are issue bound (the fused
+// activation -> conv kernel: every failed poll of the epilogue / MMA warps took an issue slot from the producer warps)
+__device__ __forceinline__ void mbar_wait_warp_sleep(uint32_t bar, uint32_t parity, unsigned ns) {
+  if ((threadIdx.x & 31) == 0) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.b32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(parity)
+          : "memory");
+      if (done) break;
+      __nanosleep(ns);
+      if ((spin & 0xFFFu) == 0xFFFu) {
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000ll) __trap();
+      }
+    }
+  }
+  __syncwarp();
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -207,9 +232,9 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 
 // split two fp32 values into packed (hi, hi) and (lo, lo) half pairs: 2 F2FP + 2 conversions back + 2 FADD
 __device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(a, b);
+  const __half2 h = pt_f2h2_sat(a, b);
   const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  const __half2 l = pt_f2h2_sat(a - hf.x, b - hf.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }

@@ -210,6 +210,21 @@ def conv1d_umma_cl(x_planes, w_split, Cout, bias=None, K=1, dil=1, pad=0, act=AC
     return out, planes
 
 
+def aa_conv1d_cl(x, log_alpha, up_filter, down_filter, w_split, bias=None, K=1, dil=1, pad=0, res=None, beta=0.0,
+                 out=None, out_div=0.0):
+    """AA-Snake fused into the consuming conv (pttspp_aa_conv1d_cl): x [B, T, C] fp32 pre-activation, C in {32, 64}."""
+    _abi.require_cuda(x, "aa_conv1d_cl")
+    B, T, Cc = x.shape
+    d, out, _, keep = conv1d_umma_cl((x, x), w_split, Cc, bias=bias, K=K, dil=dil, pad=pad, res=res, beta=beta, out=out,
+                                     out_div=out_div, _desc_only=True)
+    d.in_hi = None; d.in_lo = None
+    d.in_ = x.data_ptr()
+    d.in_bs = x.stride(0); d.in_ld = x.stride(1)
+    _abi.check(_abi.lib().pttspp_aa_conv1d_cl(C.byref(d), _abi.ptr(log_alpha), _abi.ptr(up_filter), _abi.ptr(down_filter),
+                                              _abi.stream_ptr(x.device)))
+    return out
+
+
 def conv1d_umma_dual_cl(x_planes, w_split, cout1, kw1, kw2):
     """One tcgen05 launch, two epilogues: columns [0, cout1) use kw1, the rest kw2 (kwargs of conv1d_umma_cl).
     w_split packs all Cout rows; returns ((out1, planes1), (out2, planes2))."""

@@ -36,6 +36,20 @@ def test_split_planes_reconstruct(ops):
     assert float(((rec - ref).abs() - 4e-7 * ref.abs()).max()) < 4e-8
 
 
+def test_split_planes_saturate_instead_of_overflowing(ops):
+    """|v| beyond fp16's range: the hi plane saturates at 65504 (no inf), the lo plane carries the rest up to 2 x 65504;
+    nothing downstream can become inf - inf = NaN (activations had no saturation)."""
+    x = torch.tensor([[1.0e5, -1.0e5, 3.0e5, -7.0e8, 65504.0, 65519.9, 65520.0, 1.0]] * 2).view(1, 2, 8)
+    x = torch.cat([x, torch.zeros(1, 2, 8)], dim=2).contiguous()  # 16 channels
+    hi, lo = ops.split_f16(x.cuda())
+    hi, lo = hi.float().cpu(), lo.float().cpu()
+    assert torch.isfinite(hi).all() and torch.isfinite(lo).all()
+    rec = (hi + lo)[0, 0, :8]
+    assert rec[0] == 1.0e5 and rec[1] == -1.0e5          # exact through the lo plane
+    assert rec[2] == 2 * 65504.0 and rec[3] == -2 * 65504.0  # clipped, finite
+    assert rec[4] == 65504.0 and abs(float(rec[5]) - 65519.9) < 0.01 and rec[6] == 65520.0 and rec[7] == 1.0
+
+
 UMMA_CASES = [
     # Cin, Cout, K, dil, B, T
     (64, 128, 1, 1, 1, 128),      # single stage, single tile
@@ -286,3 +300,50 @@ def test_conv1d_umma_chunked_accumulation_is_fp32_class(ops, Cin, Cout):
     rec = pl3[0].float() + pl3[1].float()
     assert float((rec - out3).abs().max()) < 1e-6          # the emitted operand planes carry the same values
     assert float(_bct(out3)[1, :, 131:].abs().max()) == 0  # rows past the utterance are zero (out_len mask)
+
+
+AA_CONV_CASES = [
+    # C, K, dil, B, T: the BigVGAN geometries of the 32 / 64-channel stages; T not a multiple of the 128-row tile,
+    # utterances shorter than one tile, halos up to 50 rows crossing both utterance ends
+    (32, 3, 1, 2, 1000), (32, 3, 5, 2, 3001), (32, 7, 3, 1, 5000), (32, 11, 1, 3, 2999), (32, 11, 5, 2, 40000),
+    (32, 11, 5, 3, 77), (32, 7, 1, 2, 5),
+    (64, 3, 1, 2, 1000), (64, 3, 5, 2, 3001), (64, 7, 5, 2, 20000), (64, 7, 3, 3, 2999), (64, 7, 1, 2, 131),
+]
+
+
+@pytest.mark.parametrize("C,K,dil,B,T", AA_CONV_CASES)
+def test_aa_conv_fused_is_bit_identical_to_two_launches(ops, C, K, dil, B, T):
+    """AA-Snake fused into the conv's producer warps (pttspp_aa_conv1d_cl) == activation launch + conv launch, bit for
+    bit, with residual / running-sum / division epilogue as BigVGAN's conv2 uses them; and against fp32 torch."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    from oracle import oracle
+    from promptttspp_b200.layers.activations import AntiAliasActivation
+
+    g = torch.Generator().manual_seed(C * 7 + K + dil)
+    x = torch.randn(B, C, T, generator=g) * 2
+    w = torch.randn(C, C, K, generator=g) / math.sqrt(C * K)
+    b = torch.randn(C, generator=g)
+    res = torch.randn(B, C, T, generator=g)
+    prev = torch.randn(B, C, T, generator=g)
+    act = AntiAliasActivation(C)
+    alpha = torch.rand(C, generator=g) - 0.5
+    up, down = act.up.filter.view(-1).cuda(), act.down.lowpass.filter.view(-1).cuda()
+    pad = (K * dil - dil) // 2
+    wsp = ops.pack_conv_weight_split(w, device="cuda")
+    xc = _cl(x)
+    # two launches: activation -> operand planes -> conv
+    y = ops.aa_snake_cl(xc, alpha.cuda(), up, down, pair=True)
+    out2, _ = ops.conv1d_umma_cl(ops.split_f16(y), wsp, C, bias=b.cuda(), K=K, dil=dil, pad=pad, res=_cl(res), beta=1.0,
+                                 out=_cl(prev).clone(), out_div=3.0)
+    out1 = ops.aa_conv1d_cl(xc, alpha.cuda(), up, down, wsp, bias=b.cuda(), K=K, dil=dil, pad=pad, res=_cl(res), beta=1.0,
+                            out=_cl(prev).clone(), out_div=3.0)
+    torch.cuda.synchronize()
+    assert torch.equal(out1, out2), float((out1 - out2).abs().max())
+    a = oracle.aa_activation(x, alpha.view(1, -1, 1), act.up.filter, act.down.lowpass.filter)
+    ref = (res + F.conv1d(a, w, b, padding=pad, dilation=dil) + prev) / 3.0
+    err = float((_bct(out1) - ref).abs().max())
+    print(f"aa+conv {C} k{K} d{dil} T{T}: max-abs err vs fp32 torch {err:.3e}")
+    assert err < 2e-5 + 6e-9 * K * C, err
