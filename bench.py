@@ -136,10 +136,18 @@ def prof_report(lib):
     return [dict(kernel=TAGS[i], ms=ms[i], flops=fl[i], bytes=by[i], calls=calls[i]) for i in range(n)]
 
 
-def ncu_traffic(kernel, rows):
+def ncu_traffic(kernel, rows, leg="acoustic"):
     """DRAM bytes per launch of `kernel`'s family from the committed ncu --set full capture (profiles/), scaled from
     the capture's row count to this run's; None when no capture covers the family."""
     p2 = ROOT / "profiles" / "r02_ncu_traffic.json"
+    if leg == "bigvgan" and p2.exists():
+        fam = json.loads(p2.read_text()).get("bigvgan_families", {}).get(kernel)
+        if fam:
+            return fam["dram_bytes_per_launch"], (
+                f"profiles/r02_ncu_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over the {fam['launches']} "
+                f"launches of this family in one cfg3 forward, mean per launch; algorithmic bytes per launch "
+                f"{fam.get('algorithmic_bytes_per_launch')})")
+        return None, None
     if kernel == TAGS[6] and p2.exists() and rows:
         t = json.loads(p2.read_text())["diffnet_layers_kernel"]
         return t["dram_bytes_per_launch"] * rows / t["rows"], (
@@ -158,12 +166,12 @@ def ncu_traffic(kernel, rows):
     return None, None
 
 
-def roofline_from(report, pk, in_long_step, rows=None):
+def roofline_from(report, pk, in_long_step, rows=None, leg="acoustic"):
     """Dominant kernel family of one profiled step -> the `roofline` object."""
     top = max(report, key=lambda r: r["ms"])
     if top["ms"] <= 0 or top["calls"] == 0:
         return None
-    traffic, traffic_src = ncu_traffic(top["kernel"], rows)
+    traffic, traffic_src = ncu_traffic(top["kernel"], rows, leg)
     if top["flops"] > 0:
         peak = pk["tf_sustained"] if in_long_step else pk["tf_burst"]
         ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
@@ -466,7 +474,7 @@ def run_native(args, rank, local_rank, world):
 
             extra["cfg1"]["cpu_baseline"] = reference_arm.cfg1_sample(2, 1)
         roof_ac = roofline_from(rep_ac, pk, in_long_step=True, rows=float(padded) / world)
-        roof_voc = roofline_from(rep_voc, pk, in_long_step=True)
+        roof_voc = roofline_from(rep_voc, pk, in_long_step=True, leg="bigvgan")
         frames_s = float(valid) / (ms_dev * 1e-3)
         line = {
             "metric": METRIC, "value": frames_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,

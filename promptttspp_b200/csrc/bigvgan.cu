@@ -45,6 +45,7 @@ struct pttspp_bigvgan {
   // profiles/r02_aa_conv_fusion_experiment.txt), so it stays opt-in.
   bool fuse_aa = false;
   pttspp::PackedConv conv_pre, conv_post;
+  pttspp::PackedConv conv_pre_tc;  // tensor-core copy of conv_pre, mel axis zero-padded to a multiple of 64 (80 -> 128)
   std::vector<pttspp::UpsampleW> ups;
   std::vector<std::vector<std::vector<pttspp::AMPLayerW>>> mrfs;  // [stage][kernel][layer]
   pttspp::AAParams act_post;
@@ -335,6 +336,26 @@ extern "C" int pttspp_bigvgan_finalize(pttspp_bigvgan_t* h, pttspp_stream_t) {
     h->fuse_aa = (f && f[0] == '1');
   }
   h->conv_pre = load_conv1d(h->store, h->dev, "conv_pre", C0, c.in_channel, 7, 1, 3);
+  h->conv_pre_tc = PackedConv();
+  if (h->use_umma && C0 % 64 == 0) {
+    // conv_pre on the tensor cores (it was the last fp32 CUDA-core conv of the forward: 0.35 ms at cfg3): the mel axis is
+    // zero-padded to a multiple of 64, which leaves the weight-norm over (Cin, K) unchanged
+    const int Cp = round_up(c.in_channel, 64);
+    const int64_t n = (int64_t)C0 * c.in_channel * 7;
+    const bool wn = !h->store.has("conv_pre.weight");
+    const auto& v = h->store.get(wn ? "conv_pre.weight_v" : "conv_pre.weight", n).data;  // [C0][in][7]
+    std::vector<float> vp((size_t)C0 * Cp * 7, 0.f);
+    for (int co = 0; co < C0; ++co)
+      for (int ci = 0; ci < c.in_channel; ++ci)
+        for (int k = 0; k < 7; ++k) vp[((size_t)co * Cp + ci) * 7 + k] = v[((size_t)co * c.in_channel + ci) * 7 + k];
+    std::vector<uint16_t> hi(vp.size()), lo(vp.size());
+    h->conv_pre_tc = h->conv_pre;
+    h->conv_pre_tc.Cin = Cp;
+    pack_conv_weight_split(vp.data(), wn ? h->store.get("conv_pre.weight_g", C0).data.data() : nullptr, C0, Cp, 7, hi.data(),
+                           lo.data(), 0, &h->conv_pre_tc.w_scale_inv);
+    h->conv_pre_tc.w_hi = h->dev.upload_bytes(hi.data(), hi.size() * 2);
+    h->conv_pre_tc.w_lo = h->dev.upload_bytes(lo.data(), lo.size() * 2);
+  }
   for (int i = 0; i < c.num_upsamples; ++i) {
     UpsampleW u;
     u.Cin = C0 >> i;
@@ -466,6 +487,15 @@ static void bigvgan_forward_impl(pttspp_bigvgan_t* h, const float* mel, const fl
   };
   {
     auto d = conv_desc(h->conv_pre, t1, B, T, bxs);
+    if (h->conv_pre_tc.w_hi) {  // padded operand planes of the mel rows in the (still unused) bA region
+      const int Cp = h->conv_pre_tc.Cin;
+      uint16_t* mh = reinterpret_cast<uint16_t*>(bA);
+      uint16_t* ml = mh + (size_t)B * T * Cp;
+      split_f16_pad(t1, (int64_t)B * T, c.in_channel, Cp, mh, ml, s);
+      d.Cin = Cp; d.in_ld = Cp; d.in_bs = (int64_t)T * Cp;
+      d.in_hi = mh; d.in_lo = ml; d.w_hi = h->conv_pre_tc.w_hi; d.w_lo = h->conv_pre_tc.w_lo;
+      d.w_scale_inv = h->conv_pre_tc.w_scale_inv; d.impl = 2;
+    }
     if (!h->ups[0].w_hi.empty()) {
       uint16_t *ph, *pl;
       stage_planes((int64_t)B * T * h->conv_pre.Cout, ph, pl);
