@@ -107,7 +107,9 @@ typedef struct {
   int32_t B;
   int32_t impl; /* 0 = auto, 1 = force SIMT fp32, 2 = force tcgen05 split-fp16, 3 = tcgen05 split-fp16 with chunked
                  * near-fp32 accumulation (<= 16 tensor-core accumulations per accumulator, chunk sums added in
-                 * round-to-nearest fp32 registers): the text side, whose outputs decide integer durations */
+                 * round-to-nearest fp32 registers): the text side, whose outputs decide integer durations;
+                 * 4 = tcgen05 split-fp16 without chunking: contractions of up to 256 accumulations per accumulator and
+                 * single-N-tile convs may take the CTA-pair kernel (the vocoder, whose bar is 1e-4 RMS on the waveform) */
   /* ---- split-fp16 operands (tcgen05 path) -------------------------------------------------
    * An fp32 value v travels as two fp16 planes hi = fp16(v), lo = fp16(v - hi); the tensor cores
    * compute hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM (~2^-22 relative, fp32 class).

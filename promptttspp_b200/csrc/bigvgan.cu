@@ -44,6 +44,7 @@ struct pttspp_bigvgan {
   // resident warps of an SM, the 7-8 producer warps of the fused kernel take 2.8x the stand-alone kernel's time --
   // profiles/r02_aa_conv_fusion_experiment.txt), so it stays opt-in.
   bool fuse_aa = false;
+  int conv_impl = 4;  // 4: long contractions on the CTA-pair kernel, no chunked accumulation; PTTSPP_BIGVGAN_IMPL=2: round-2b choice
   pttspp::PackedConv conv_pre, conv_post;
   pttspp::PackedConv conv_pre_tc;  // tensor-core copy of conv_pre, mel axis zero-padded to a multiple of 64 (80 -> 128)
   std::vector<pttspp::UpsampleW> ups;
@@ -334,6 +335,8 @@ extern "C" int pttspp_bigvgan_finalize(pttspp_bigvgan_t* h, pttspp_stream_t) {
     h->use_umma = !(e && e[0] == '1');
     const char* f = getenv("PTTSPP_AA_FUSE");
     h->fuse_aa = (f && f[0] == '1');
+    const char* ci = getenv("PTTSPP_BIGVGAN_IMPL");
+    h->conv_impl = (ci && ci[0] == '2') ? 2 : 4;
   }
   h->conv_pre = load_conv1d(h->store, h->dev, "conv_pre", C0, c.in_channel, 7, 1, 3);
   h->conv_pre_tc = PackedConv();
@@ -494,7 +497,7 @@ static void bigvgan_forward_impl(pttspp_bigvgan_t* h, const float* mel, const fl
       split_f16_pad(t1, (int64_t)B * T, c.in_channel, Cp, mh, ml, s);
       d.Cin = Cp; d.in_ld = Cp; d.in_bs = (int64_t)T * Cp;
       d.in_hi = mh; d.in_lo = ml; d.w_hi = h->conv_pre_tc.w_hi; d.w_lo = h->conv_pre_tc.w_lo;
-      d.w_scale_inv = h->conv_pre_tc.w_scale_inv; d.impl = 2;
+      d.w_scale_inv = h->conv_pre_tc.w_scale_inv; d.impl = h->conv_impl;
     }
     if (!h->ups[0].w_hi.empty()) {
       uint16_t *ph, *pl;
@@ -534,7 +537,7 @@ static void bigvgan_forward_impl(pttspp_bigvgan_t* h, const float* mel, const fl
       if (!u.w_hi.empty()) {
         uint16_t *ph, *pl;
         stage_planes((int64_t)B * L * u.Cin, ph, pl);
-        d.in_hi = ph; d.in_lo = pl; d.w_hi = u.w_hi[r]; d.w_lo = u.w_lo[r]; d.w_scale_inv = u.w_scale_inv[r]; d.impl = 2;
+        d.in_hi = ph; d.in_lo = pl; d.w_hi = u.w_hi[r]; d.w_lo = u.w_lo[r]; d.w_scale_inv = u.w_scale_inv[r]; d.impl = h->conv_impl;
       }
       conv1d_cl(d, s);
     }
@@ -550,13 +553,13 @@ static void bigvgan_forward_impl(pttspp_bigvgan_t* h, const float* mel, const fl
         uint16_t* ph = reinterpret_cast<uint16_t*>(t1);
         uint16_t* pl = ph + (size_t)B * L * C;
         auto use_planes = [&](pttspp_conv1d_desc& q, const PackedConv& pc) {
-          q.in_hi = ph; q.in_lo = pl; q.w_hi = pc.w_hi; q.w_lo = pc.w_lo; q.w_scale_inv = pc.w_scale_inv; q.impl = 2;
+          q.in_hi = ph; q.in_lo = pl; q.w_hi = pc.w_hi; q.w_lo = pc.w_lo; q.w_scale_inv = pc.w_scale_inv; q.impl = h->conv_impl;
         };
         // narrow stages (32 / 64 channels): the activation runs inside the conv kernel's producer warps, the activated
         // tensor never exists in HBM (conv1d_umma.cu: aa_conv_wres_kernel); bit-identical to the two-launch path
         auto fused_desc = [&](const PackedConv& pc, const float* in, float* out) {
           auto q = conv_desc(pc, in, B, L, out);
-          q.w_hi = pc.w_hi; q.w_lo = pc.w_lo; q.w_scale_inv = pc.w_scale_inv; q.impl = 2;
+          q.w_hi = pc.w_hi; q.w_lo = pc.w_lo; q.w_scale_inv = pc.w_scale_inv; q.impl = h->conv_impl;
           return q;
         };
         bool fuse1 = false, fuse2 = false;

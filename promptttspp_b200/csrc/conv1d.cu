@@ -148,7 +148,7 @@ bool conv1d_umma_supported(const pttspp_conv1d_desc& d);
 void conv1d_cl(const pttspp_conv1d_desc& d, cudaStream_t s) {
   PT_CHECK(d.out || d.out_hi, "conv1d: no output (out and out_hi are NULL)");
   PT_CHECK(!d.out_hi || d.out_lo, "conv1d: out_hi without out_lo");
-  PT_CHECK(!d.res_hi || (d.res_lo && !d.res && (d.impl == 2 || d.impl == 3 || (d.impl == 0 && conv1d_umma_supported(d)))),
+  PT_CHECK(!d.res_hi || (d.res_lo && !d.res && (d.impl == 2 || d.impl == 3 || d.impl == 4 || (d.impl == 0 && conv1d_umma_supported(d)))),
            "conv1d: res_hi needs res_lo, no fp32 res, and the tcgen05 path");
   PT_CHECK(d.Cin > 0 && d.Cin % BK == 0, "conv1d: Cin=%d must be a positive multiple of %d", d.Cin, BK);
   PT_CHECK(!d.in_add || aligned16(d.in_add), "conv1d: in_add must be 16-byte aligned");
@@ -157,9 +157,9 @@ void conv1d_cl(const pttspp_conv1d_desc& d, cudaStream_t s) {
   PT_CHECK(d.B >= 1 && d.B <= 65535, "conv1d: batch %d out of range", d.B);
   if (d.M <= 0 || d.Cout <= 0) return;
   const double flops = 2.0 * d.B * (double)d.M * d.Cout * (double)d.Cin * d.K;
-  const bool umma = (d.impl == 2) || (d.impl == 3) || (d.impl == 0 && conv1d_umma_supported(d));
+  const bool umma = (d.impl == 2) || (d.impl == 3) || (d.impl == 4) || (d.impl == 0 && conv1d_umma_supported(d));
   ProfScope prof(umma ? PROF_CONV_UMMA : PROF_CONV_SIMT, s, flops, 0.0);
-  if (d.impl == 2 || d.impl == 3) {
+  if (d.impl == 2 || d.impl == 3 || d.impl == 4) {
     PT_CHECK(conv1d_umma_supported(d), "conv1d: tcgen05 path requested for an unsupported shape");
     conv1d_umma_cl(d, s);
     return;

@@ -815,7 +815,7 @@ conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_co
                       const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                       const pttspp_conv1d_desc d, const pttspp_conv1d_desc d2, const int cout1, const int cout_total,
                       const int vec_ok, const int n_mt, const int n_nt, const int n_units, const int rowsA,
-                      const int nbst) {
+                      const int nbst, const int nabuf) {
   constexpr uint32_t TMEM_COLS = 2 * UM_NACC * BN;
   constexpr int B_BYTES = BN * 128;        // one plane of one weight tile
   constexpr int BST_BYTES = 2 * B_BYTES;   // hi + lo
@@ -824,22 +824,27 @@ conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_co
   const int nslab = d.Cin / UM_BK;
   const uint32_t a_plane = (uint32_t)rowsA * 128u;          // bytes of one (slab, plane) tile; rowsA % 8 == 0
   const uint32_t a_bytes = (uint32_t)nslab * 2u * a_plane;  // whole activation block
-  const uint32_t ring = base + a_bytes;
-  const uint32_t bars = ring + (uint32_t)nbst * BST_BYTES;  // fullA, emptyA, fullB[nbst], emptyB[nbst], tfull[2], tempty[2]
-  const int nbars = 2 + 2 * nbst + 4;
+  // nabuf = 2: the next unit's activation block streams in while this unit's MMAs run (a must when a unit is a single
+  // N tile, e.g. BigVGAN's 64-channel k = 11 convs: otherwise block load and MMAs alternate)
+  const uint32_t ring = base + (uint32_t)nabuf * a_bytes;
+  const uint32_t bars = ring + (uint32_t)nbst * BST_BYTES;  // fullA[2], emptyA[2], fullB[nbst], emptyB[nbst], tfull[2], tempty[2]
+  const int nbars = 4 + 2 * nbst + 4;
   const uint32_t tmem_slot = bars + nbars * 8;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + a_bytes + nbst * BST_BYTES + nbars * 8);
-  const uint32_t fullA = bars, emptyA = bars + 8;
-  auto fullB = [&](int s) { return bars + (2 + s) * 8; };
-  auto emptyB = [&](int s) { return bars + (2 + nbst + s) * 8; };
-  auto tfull_bar = [&](int u) { return bars + (2 + 2 * nbst + u) * 8; };
-  auto tempty_bar = [&](int u) { return bars + (2 + 2 * nbst + 2 + u) * 8; };
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + nabuf * a_bytes + nbst * BST_BYTES + nbars * 8);
+  auto fullA = [&](int q) { return bars + q * 8; };
+  auto emptyA = [&](int q) { return bars + (2 + q) * 8; };
+  auto fullB = [&](int s) { return bars + (4 + s) * 8; };
+  auto emptyB = [&](int s) { return bars + (4 + nbst + s) * 8; };
+  auto tfull_bar = [&](int u) { return bars + (4 + 2 * nbst + u) * 8; };
+  auto tempty_bar = [&](int u) { return bars + (4 + 2 * nbst + 2 + u) * 8; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(fullA, 1);
-    mbar_init(emptyA, 1);
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(fullA(q), 1);
+      mbar_init(emptyA(q), 1);
+    }
     for (int s = 0; s < nbst; ++s) {
       mbar_init(fullB(s), 1);
       mbar_init(emptyB(s), 1);
@@ -874,11 +879,13 @@ conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_co
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++j) {
         const int mt = unit % n_mt, b = unit / n_mt;
         const int row0 = d.m_begin + mt * UM_BM - d.pad;  // first input row of the halo block (may be negative)
-        mbar_wait(emptyA, ((uint32_t)j & 1u) ^ 1u);        // previous unit's MMAs have retired
-        mbar_expect_tx(fullA, a_bytes);
+        const int q = j % nabuf;
+        const uint32_t ablk = base + (uint32_t)q * a_bytes;
+        mbar_wait(emptyA(q), (((uint32_t)(j / nabuf)) & 1u) ^ 1u);  // the MMAs of the unit that used this buffer have retired
+        mbar_expect_tx(fullA(q), a_bytes);
         for (int slab = 0; slab < nslab; ++slab) {
-          tma_load_3d(base + (uint32_t)(2 * slab) * a_plane, &mapAh, fullA, slab * UM_BK, row0, b);
-          tma_load_3d(base + (uint32_t)(2 * slab + 1) * a_plane, &mapAl, fullA, slab * UM_BK, row0, b);
+          tma_load_3d(ablk + (uint32_t)(2 * slab) * a_plane, &mapAh, fullA(q), slab * UM_BK, row0, b);
+          tma_load_3d(ablk + (uint32_t)(2 * slab + 1) * a_plane, &mapAl, fullA(q), slab * UM_BK, row0, b);
         }
         for (int nt = 0; nt < n_nt; ++nt)
           for (int slab = 0; slab < nslab; ++slab)
@@ -897,10 +904,13 @@ conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_co
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(UM_BM, BN);
+      constexpr uint32_t idesc2 = umma_idesc_f16(UM_BM, 2 * BN);  // [W_hi | W_lo] stacked along N (main | cross)
       uint32_t g = 0;
       int j = 0, i = 0;
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++j) {
-        mbar_wait(fullA, (uint32_t)j & 1u);
+        const int q = j % nabuf;
+        const uint32_t ablk = base + (uint32_t)q * a_bytes;
+        mbar_wait(fullA(q), ((uint32_t)(j / nabuf)) & 1u);
         tc_fence_after();
         for (int nt = 0; nt < n_nt; ++nt, ++i) {
           const int u = i & 1;
@@ -916,24 +926,23 @@ conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_co
               mbar_wait(fullB(s), ph);
               tc_fence_after();
               const uint32_t a_off = (uint32_t)(tap * d.dil) * 128u;  // taps share the halo tile
-              const uint64_t dAh = umma_desc_k_sw128(base + (uint32_t)(2 * slab) * a_plane + a_off);
-              const uint64_t dAl = umma_desc_k_sw128(base + (uint32_t)(2 * slab + 1) * a_plane + a_off);
+              const uint64_t dAh = umma_desc_k_sw128(ablk + (uint32_t)(2 * slab) * a_plane + a_off);
+              const uint64_t dAl = umma_desc_k_sw128(ablk + (uint32_t)(2 * slab + 1) * a_plane + a_off);
               const uint32_t st = ring + (uint32_t)s * BST_BYTES;
               const uint64_t dBh = umma_desc_k_sw128(st);
-              const uint64_t dBl = umma_desc_k_sw128(st + B_BYTES);
 #pragma unroll
               for (int kk = 0; kk < UM_BK / 16; ++kk) {
                 const uint64_t adv = (uint64_t)(kk * 32 >> 4);
-                umma_f16(acc_cross, dAl + adv, dBh + adv, idesc, first);
-                umma_f16(acc_cross, dAh + adv, dBl + adv, idesc, 1u);
-                umma_f16(acc_main, dAh + adv, dBh + adv, idesc, first);
+                // the streaming kernel's stacked issue, same order: the two kernels give the same bits
+                umma_f16(acc_main, dAh + adv, dBh + adv, idesc2, first);
+                umma_f16(acc_cross, dAl + adv, dBh + adv, idesc, 1u);
                 first = 1u;
               }
               umma_commit(emptyB(s));
             }
           umma_commit(tfull_bar(u));
         }
-        umma_commit(emptyA);  // the activation block may be overwritten once everything issued so far has retired
+        umma_commit(emptyA(q));  // the activation block may be overwritten once everything issued so far has retired
       }
     }
   } else {
@@ -2014,7 +2023,12 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
   if (env_pair == '0' && !needs_pair) return false;
   if (!epilogue_co_ok(d) || (dual && !epilogue_co_ok(d2))) return false;
   if (total_cout % UP_BN != 0 || d.Cin % UM_BK != 0 || d.Cin / UM_BK > UP_MAX_SLAB) return false;
-  if (d.K * d.Cin / 16 > 64) return false;  // long contractions keep the multi-accumulator streaming kernel
+  // impl 4 (the vocoder: 1e-4 RMS waveform bar, measured 8e-6): contractions of up to 256 accumulations per accumulator
+  // and single-N-tile convs take this kernel too -- it loads the activation block once per 256-row unit and each CTA
+  // only half of every weight tile, where the streaming kernels are bound by the L2 -> SM fill (ncu: 5.4-10 TB/s of
+  // re-streamed weight / activation tiles); everything else keeps the chunked streaming kernel for long contractions
+  const bool longk = d.impl == 4;
+  if (d.K * d.Cin / 16 > (longk ? 256 : 64)) return false;
   if (flatten_batch_ok(d) && (!dual || flatten_batch_ok(d2))) {
     flatten_batch(d);
     if (dual) flatten_batch(d2);
@@ -2037,7 +2051,7 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
   if (n_tiles >= (1ll << 30)) return false;
   // worth it only when every pair gets at least a couple of tiles (the activation block is loaded per unit)
   // and when the activation block is reused by at least two N tiles (otherwise the streaming kernel is faster)
-  if (env_pair != '2' && !needs_pair && (n_tiles < num_sms || n_nt < 2)) return false;
+  if (env_pair != '2' && !needs_pair && (n_tiles < num_sms || (n_nt < 2 && !(longk && d.K >= 5)))) return false;
 
   const uint64_t wdims[2] = {(uint64_t)d.Cin, (uint64_t)d.K * total_cout};
   const uint64_t wstr[1] = {(uint64_t)d.Cin * 2};
@@ -2270,16 +2284,42 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
   // is left with two weight stages in flight and becomes latency bound), so the latter is opt-in.
   const bool a_stationary = umma_env().a_stationary;
   if (a_stationary && rowsA <= 256 && a_bytes + 2 * bst <= cap && n_units * 2 >= num_sms) {
-    const int nbst = (int)std::min<size_t>(6, (cap - a_bytes) / bst);
+    const int nabuf = (2 * a_bytes + 3 * bst <= cap) ? 2 : 1;
+    const int nbst = (int)std::min<size_t>(6, (cap - nabuf * a_bytes) / bst);
     const uint32_t abox[3] = {UM_BK, (uint32_t)rowsA, 1};
     const CUtensorMap mAh = make_map(d.in_hi, 3, adims, astr, abox);
     const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox);
-    const size_t smem = a_bytes + nbst * bst + 512 + 1024;
+    const size_t smem = nabuf * a_bytes + nbst * bst + 512 + 1024;
     auto kern = conv1d_umma_as_kernel<UM_BN>;
     ensure_smem_optin((const void*)kern, 227 * 1024);
     const int grid = (int)std::min<long long>(n_units, num_sms);
     kern<<<grid, UM_THREADS, smem, s>>>(mAh, mAl, mBh, mBl, d, d2, d2_in ? cout1 : total_cout, total_cout, vec ? 1 : 0,
-                                        n_mt, n_nt, (int)n_units, rowsA, nbst);
+                                        n_mt, n_nt, (int)n_units, rowsA, nbst, nabuf);
+    PT_LAUNCHED();
+    return;
+  }
+  // Narrow outputs (<= 64 columns) with many taps -- BigVGAN's 64-channel k = 11 convs, whose weights do not fit the
+  // weight-resident kernel: the streaming kernel re-loads the 32 KB activation tile for every tap (L2 -> SM fill: 528 KB
+  // per 128-row tile at k = 11), the A-stationary kernel loads one halo block (47 KB, double buffered) and streams only
+  // the 16 KB weight tiles (223 KB per tile).  Same MMA order as the streaming kernel's 64-column tile: same bits.
+  // PTTSPP_UMMA_NO_AS64=1 keeps the streaming kernel (A/B measurements).
+  static const bool no_as64 = getenv("PTTSPP_UMMA_NO_AS64") != nullptr;
+  const size_t bst64 = 2 * (size_t)64 * 128;
+  if (!no_as64 && !d2_in && total_cout <= 64 && total_cout % 16 == 0 && d.K >= 5 && d.K * d.Cin / 16 <= 64 &&
+      rowsA <= 256 && 2 * a_bytes + 3 * bst64 <= cap && n_units * 2 >= num_sms && d_in.impl != 3) {
+    const int nbst = (int)std::min<size_t>(6, (cap - 2 * a_bytes) / bst64);
+    const uint32_t abox[3] = {UM_BK, (uint32_t)rowsA, 1};
+    const CUtensorMap mAh = make_map(d.in_hi, 3, adims, astr, abox);
+    const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox);
+    const uint32_t wbox64[2] = {UM_BK, 64};
+    const CUtensorMap mBh64 = make_map(d.w_hi, 2, wdims, wstr, wbox64);
+    const CUtensorMap mBl64 = make_map(d.w_lo, 2, wdims, wstr, wbox64);
+    const size_t smem = 2 * a_bytes + nbst * bst64 + 512 + 1024;
+    auto kern = conv1d_umma_as_kernel<64>;
+    ensure_smem_optin((const void*)kern, 227 * 1024);
+    const int grid = (int)std::min<long long>(n_units, num_sms);
+    kern<<<grid, UM_THREADS, smem, s>>>(mAh, mAl, mBh64, mBl64, d, d2, total_cout, total_cout, vec ? 1 : 0, n_mt, 1,
+                                        (int)n_units, rowsA, nbst, 2);
     PT_LAUNCHED();
     return;
   }
@@ -2289,7 +2329,8 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
   // Long contractions (> 64 tensor-core accumulations per accumulator) with >= 128 output columns also take the chunked
   // kernel: 128-column tiles (half the activation re-reads of the 64-column round-robin variant below) and a bounded
   // truncation bias.  PTTSPP_UMMA_LONGK=narrow keeps the old choice (A/B measurements).
-  const bool long_k_chunked = !d2_in && total_cout >= 128 && d.K * d.Cin / 16 > 64 && vec && !umma_env().longk_narrow;
+  // (impl 4 never chunks: a conv must give the same bits whichever kernel its batch size selects)
+  const bool long_k_chunked = !d2_in && total_cout >= 128 && d.K * d.Cin / 16 > 64 && vec && !umma_env().longk_narrow && d_in.impl != 4;
   if (d_in.impl == 3 || long_k_chunked) {
     // near-fp32 chunked accumulation (see the kernel comment): 4 (slab, tap) iterations = 16 accumulations per chunk
     PT_CHECK(!d2_in, "conv1d: the chunked tcgen05 mode has no dual-epilogue form");

@@ -347,3 +347,32 @@ def test_aa_conv_fused_is_bit_identical_to_two_launches(ops, C, K, dil, B, T):
     err = float((_bct(out1) - ref).abs().max())
     print(f"aa+conv {C} k{K} d{dil} T{T}: max-abs err vs fp32 torch {err:.3e}")
     assert err < 2e-5 + 6e-9 * K * C, err
+
+
+@pytest.mark.parametrize("Cin,Cout,K,dil,B,T", [(128, 128, 11, 5, 2, 20000), (128, 128, 7, 1, 2, 20000),
+                                                (256, 256, 11, 3, 2, 10000), (256, 256, 7, 5, 2, 10000)])
+def test_conv1d_umma_impl4_pair_equals_streaming(ops, monkeypatch, Cin, Cout, K, dil, B, T):
+    """impl 4 (the vocoder's convs): long contractions take the CTA-pair kernel when the batch fills the machine and the
+    un-chunked streaming kernel otherwise -- same bits either way (an utterance synthesised alone equals the same
+    utterance inside a batch), fp32 class against torch."""
+    from promptttspp_b200 import _abi
+
+    g = torch.Generator().manual_seed(Cin + K + dil)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cout, Cin, K, generator=g) / math.sqrt(Cin * K)
+    b = torch.randn(Cout, generator=g)
+    pad = (K * dil - dil) // 2
+    planes = ops.split_f16(_cl(x))
+    wsp = ops.pack_conv_weight_split(w, device="cuda")
+    n0 = _abi.lib().pttspp_launch_count()
+    out_pair, _ = ops.conv1d_umma_cl(planes, wsp, Cout, bias=b.cuda(), K=K, dil=dil, pad=pad, impl=4)
+    monkeypatch.setenv("PTTSPP_UMMA_PAIR", "0")
+    _abi.lib().pttspp_debug_reload_env()
+    out_stream, _ = ops.conv1d_umma_cl(planes, wsp, Cout, bias=b.cuda(), K=K, dil=dil, pad=pad, impl=4)
+    torch.cuda.synchronize()
+    assert _abi.lib().pttspp_launch_count() - n0 == 2
+    assert torch.equal(out_pair, out_stream), float((out_pair - out_stream).abs().max())
+    ref = F.conv1d(x, w, b, padding=pad, dilation=dil)
+    err = float((_bct(out_pair) - ref).abs().max())
+    print(f"impl4 {Cin}->{Cout} k{K} d{dil}: max-abs err {err:.3e}")
+    assert err < 1e-5 + 1.2e-8 * K * Cin, err
