@@ -809,14 +809,17 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
 // slabs, 128 + halo rows -- and walks all N tiles and taps over them, streaming only weights through the ring.
 // Taps share the halo tile: the UMMA descriptor start is simply advanced by tap*dil rows (the swizzle XOR is taken
 // from absolute shared-memory address bits, so any row offset is legal -- verified on B200 by tools/probe_desc.py).
-template <int BN>
+// NSUB = 2: a unit is 256 rows = two 128-row MMA tiles that share every weight stage (the weight tiles are what all SMs
+// re-stream from the same L2 lines: ncu of the 64-column k = 11 conv showed 5.4 TB/s of L2 -> SM fill at 36 % tensor pipe).
+template <int BN, int NSUB>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                       const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                       const pttspp_conv1d_desc d, const pttspp_conv1d_desc d2, const int cout1, const int cout_total,
                       const int vec_ok, const int n_mt, const int n_nt, const int n_units, const int rowsA,
                       const int nbst, const int nabuf) {
-  constexpr uint32_t TMEM_COLS = 2 * UM_NACC * BN;
+  constexpr uint32_t TMEM_COLS = 2 * NSUB * UM_NACC * BN;
+  static_assert(TMEM_COLS <= 512, "TMEM budget");
   constexpr int B_BYTES = BN * 128;        // one plane of one weight tile
   constexpr int BST_BYTES = 2 * B_BYTES;   // hi + lo
   extern __shared__ uint8_t smem_raw[];
@@ -877,16 +880,19 @@ conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_co
       uint32_t g = 0;
       int j = 0;
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++j) {
-        const int mt = unit % n_mt, b = unit / n_mt;
-        const int row0 = d.m_begin + mt * UM_BM - d.pad;  // first input row of the halo block (may be negative)
+        const int mt = unit % n_mt, b = unit / n_mt;  // n_mt counts units (NSUB x 128 rows) per utterance
+        const int row0 = d.m_begin + mt * (NSUB * UM_BM) - d.pad;  // first input row of the halo block (may be negative)
+        const int nbox = (rowsA > 256) ? 2 : 1, box_rows = rowsA / nbox;  // a TMA box holds at most 256 rows
         const int q = j % nabuf;
         const uint32_t ablk = base + (uint32_t)q * a_bytes;
         mbar_wait(emptyA(q), (((uint32_t)(j / nabuf)) & 1u) ^ 1u);  // the MMAs of the unit that used this buffer have retired
         mbar_expect_tx(fullA(q), a_bytes);
-        for (int slab = 0; slab < nslab; ++slab) {
-          tma_load_3d(ablk + (uint32_t)(2 * slab) * a_plane, &mapAh, fullA(q), slab * UM_BK, row0, b);
-          tma_load_3d(ablk + (uint32_t)(2 * slab + 1) * a_plane, &mapAl, fullA(q), slab * UM_BK, row0, b);
-        }
+        for (int slab = 0; slab < nslab; ++slab)
+          for (int bx = 0; bx < nbox; ++bx) {
+            const uint32_t boff = (uint32_t)(bx * box_rows) * 128u;
+            tma_load_3d(ablk + (uint32_t)(2 * slab) * a_plane + boff, &mapAh, fullA(q), slab * UM_BK, row0 + bx * box_rows, b);
+            tma_load_3d(ablk + (uint32_t)(2 * slab + 1) * a_plane + boff, &mapAl, fullA(q), slab * UM_BK, row0 + bx * box_rows, b);
+          }
         for (int nt = 0; nt < n_nt; ++nt)
           for (int slab = 0; slab < nslab; ++slab)
             for (int tap = 0; tap < d.K; ++tap, ++g) {
@@ -916,8 +922,7 @@ conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_co
           const int u = i & 1;
           mbar_wait(tempty_bar(u), (((uint32_t)i >> 1) & 1u) ^ 1u);
           tc_fence_after();
-          const uint32_t acc_main = tmem_base + (uint32_t)(u * UM_NACC * BN);
-          const uint32_t acc_cross = acc_main + (uint32_t)BN;
+          const uint32_t acc_u = tmem_base + (uint32_t)(u * NSUB * UM_NACC * BN);  // sub-tile s: + s * NACC * BN (main | cross)
           uint32_t first = 0;
           for (int slab = 0; slab < nslab; ++slab)
             for (int tap = 0; tap < d.K; ++tap, ++g) {
@@ -931,13 +936,19 @@ conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_co
               const uint32_t st = ring + (uint32_t)s * BST_BYTES;
               const uint64_t dBh = umma_desc_k_sw128(st);
 #pragma unroll
-              for (int kk = 0; kk < UM_BK / 16; ++kk) {
-                const uint64_t adv = (uint64_t)(kk * 32 >> 4);
-                // the streaming kernel's stacked issue, same order: the two kernels give the same bits
-                umma_f16(acc_main, dAh + adv, dBh + adv, idesc2, first);
-                umma_f16(acc_cross, dAl + adv, dBh + adv, idesc, 1u);
-                first = 1u;
+              for (int sub = 0; sub < NSUB; ++sub) {
+                const uint64_t soff = (uint64_t)((uint32_t)(sub * UM_BM) * 128u >> 4);  // the sub-tile's rows of the block
+                const uint32_t acc_main = acc_u + (uint32_t)(sub * UM_NACC * BN), acc_cross = acc_main + (uint32_t)BN;
+#pragma unroll
+                for (int kk = 0; kk < UM_BK / 16; ++kk) {
+                  const uint64_t adv = (uint64_t)(kk * 32 >> 4) + soff;
+                  const uint64_t advb = (uint64_t)(kk * 32 >> 4);
+                  // the streaming kernel's stacked issue, same order: the two kernels give the same bits
+                  umma_f16(acc_main, dAh + adv, dBh + advb, idesc2, (kk != 0) ? 1u : first);
+                  umma_f16(acc_cross, dAl + adv, dBh + advb, idesc, 1u);
+                }
               }
+              first = 1u;
               umma_commit(emptyB(s));
             }
           umma_commit(tfull_bar(u));
@@ -951,12 +962,18 @@ conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_co
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
       const int mt = unit % n_mt, b = unit / n_mt;
       for (int nt = 0; nt < n_nt; ++nt, ++i) {
-        if (nt * BN >= cout1)
-          umma_tile_epilogue<BN, UM_NACC>(d2, nt * BN - cout1, vec_ok, mt, b, i, warp, lane, tmem_base, tfull_bar(i & 1), 1,
-                                          nullptr, false, nullptr, 0u);
-        else
-          umma_tile_epilogue<BN, UM_NACC>(d, nt * BN, vec_ok, mt, b, i, warp, lane, tmem_base, tfull_bar(i & 1), 1,
-                                          nullptr, false, nullptr, 0u);
+#pragma unroll
+        for (int sub = 0; sub < NSUB; ++sub) {
+          // buffer (i & 1), sub-tile `sub`: the epilogue addresses buffer (its i) & 1 and waits with parity (its i >> 1) & 1
+          const uint32_t tb = tmem_base + (uint32_t)(((i & 1) * NSUB + sub) * UM_NACC * BN);
+          const int i2 = i & ~1;
+          if (nt * BN >= cout1)
+            umma_tile_epilogue<BN, UM_NACC>(d2, nt * BN - cout1, vec_ok, mt * NSUB + sub, b, i2, warp, lane, tb,
+                                            tfull_bar(i & 1), 1, nullptr, false, nullptr, 0u);
+          else
+            umma_tile_epilogue<BN, UM_NACC>(d, nt * BN, vec_ok, mt * NSUB + sub, b, i2, warp, lane, tb, tfull_bar(i & 1), 1,
+                                            nullptr, false, nullptr, 0u);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(i & 1));
@@ -2051,7 +2068,7 @@ bool conv1d_umma_pair_launch(pttspp_conv1d_desc d, pttspp_conv1d_desc d2, bool d
   if (n_tiles >= (1ll << 30)) return false;
   // worth it only when every pair gets at least a couple of tiles (the activation block is loaded per unit)
   // and when the activation block is reused by at least two N tiles (otherwise the streaming kernel is faster)
-  if (env_pair != '2' && !needs_pair && (n_tiles < num_sms || (n_nt < 2 && !(longk && d.K >= 5)))) return false;
+  if (env_pair != '2' && !needs_pair && (n_tiles < num_sms || (n_nt < 2 && !(longk && d.K >= 3)))) return false;
 
   const uint64_t wdims[2] = {(uint64_t)d.Cin, (uint64_t)d.K * total_cout};
   const uint64_t wstr[1] = {(uint64_t)d.Cin * 2};
@@ -2290,7 +2307,7 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
     const CUtensorMap mAh = make_map(d.in_hi, 3, adims, astr, abox);
     const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox);
     const size_t smem = nabuf * a_bytes + nbst * bst + 512 + 1024;
-    auto kern = conv1d_umma_as_kernel<UM_BN>;
+    auto kern = conv1d_umma_as_kernel<UM_BN, 1>;
     ensure_smem_optin((const void*)kern, 227 * 1024);
     const int grid = (int)std::min<long long>(n_units, num_sms);
     kern<<<grid, UM_THREADS, smem, s>>>(mAh, mAl, mBh, mBl, d, d2, d2_in ? cout1 : total_cout, total_cout, vec ? 1 : 0,
@@ -2304,9 +2321,32 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
   // the 16 KB weight tiles (223 KB per tile).  Same MMA order as the streaming kernel's 64-column tile: same bits.
   // PTTSPP_UMMA_NO_AS64=1 keeps the streaming kernel (A/B measurements).
   static const bool no_as64 = getenv("PTTSPP_UMMA_NO_AS64") != nullptr;
+  static const bool as64_single = getenv("PTTSPP_UMMA_AS64_NSUB1") != nullptr;  // A/B: 128-row units
   const size_t bst64 = 2 * (size_t)64 * 128;
-  if (!no_as64 && !d2_in && total_cout <= 64 && total_cout % 16 == 0 && d.K >= 5 && d.K * d.Cin / 16 <= 64 &&
-      rowsA <= 256 && 2 * a_bytes + 3 * bst64 <= cap && n_units * 2 >= num_sms && d_in.impl != 3) {
+  const int rowsA2 = 2 * UM_BM + round_up((d.K - 1) * d.dil, 16);  // 256-row units; two TMA boxes of rowsA2 / 2 rows
+  const size_t a_bytes2 = (size_t)nslab * 2 * rowsA2 * 128;
+  const bool as64 = !no_as64 && !d2_in && total_cout <= 64 && total_cout % 16 == 0 && d.K >= 5 && d.K * d.Cin / 16 <= 64 &&
+                    d_in.impl != 3 && n_units * 2 >= num_sms;
+  if (as64 && !as64_single && 2 * a_bytes2 + 3 * bst64 <= cap && n_units >= 2 * num_sms) {
+    const int nbst = (int)std::min<size_t>(6, (cap - 2 * a_bytes2) / bst64);
+    const uint32_t abox[3] = {UM_BK, (uint32_t)(rowsA2 / 2), 1};
+    const CUtensorMap mAh = make_map(d.in_hi, 3, adims, astr, abox);
+    const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox);
+    const uint32_t wbox64[2] = {UM_BK, 64};
+    const CUtensorMap mBh64 = make_map(d.w_hi, 2, wdims, wstr, wbox64);
+    const CUtensorMap mBl64 = make_map(d.w_lo, 2, wdims, wstr, wbox64);
+    const size_t smem = 2 * a_bytes2 + nbst * bst64 + 512 + 1024;
+    auto kern = conv1d_umma_as_kernel<64, 2>;
+    ensure_smem_optin((const void*)kern, 227 * 1024);
+    const int n_mt2 = ceil_div(n_mt, 2);
+    const long long n_units2 = (long long)n_mt2 * d.B;
+    const int grid = (int)std::min<long long>(n_units2, num_sms);
+    kern<<<grid, UM_THREADS, smem, s>>>(mAh, mAl, mBh64, mBl64, d, d2, total_cout, total_cout, vec ? 1 : 0, n_mt2, 1,
+                                        (int)n_units2, rowsA2, nbst, 2);
+    PT_LAUNCHED();
+    return;
+  }
+  if (as64 && rowsA <= 256 && 2 * a_bytes + 3 * bst64 <= cap) {
     const int nbst = (int)std::min<size_t>(6, (cap - 2 * a_bytes) / bst64);
     const uint32_t abox[3] = {UM_BK, (uint32_t)rowsA, 1};
     const CUtensorMap mAh = make_map(d.in_hi, 3, adims, astr, abox);
@@ -2315,7 +2355,7 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
     const CUtensorMap mBh64 = make_map(d.w_hi, 2, wdims, wstr, wbox64);
     const CUtensorMap mBl64 = make_map(d.w_lo, 2, wdims, wstr, wbox64);
     const size_t smem = 2 * a_bytes + nbst * bst64 + 512 + 1024;
-    auto kern = conv1d_umma_as_kernel<64>;
+    auto kern = conv1d_umma_as_kernel<64, 1>;
     ensure_smem_optin((const void*)kern, 227 * 1024);
     const int grid = (int)std::min<long long>(n_units, num_sms);
     kern<<<grid, UM_THREADS, smem, s>>>(mAh, mAl, mBh64, mBl64, d, d2, total_cout, total_cout, vec ? 1 : 0, n_mt, 1,

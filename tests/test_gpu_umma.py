@@ -70,6 +70,10 @@ UMMA_CASES = [
     (128, 128, 7, 1, 2, 6000),
     (128, 128, 11, 5, 2, 6000),
     (64, 64, 11, 5, 1, 12000),
+    # >= 2 units per SM: the A-stationary 64-column kernel with 256-row units (two MMA tiles share every weight stage);
+    # odd number of 128-row tiles per utterance
+    (64, 64, 11, 5, 4, 12100),
+    (64, 64, 11, 1, 4, 12100),
     (256, 256, 17, 1, 4, 2500),   # frame-prior shape: halo of 16 rows
     (256, 256, 5, 1, 4, 2500),
     # 32 channels: weight-resident SWIZZLE_64B kernel (BigVGAN's last stage)
