@@ -127,75 +127,93 @@ __global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__
 // amplification).  Needs exactly symmetric filters, f[k] == f[11-k] (true for the reference's Kaiser sinc: checked on the
 // host where the filters are loaded): 6 + 6 packed coefficients stay in registers.  With symmetric filters every
 // channel's result is bit-identical to the strip kernel's (same operation order).
-constexpr int AP_STRIP = 64;        // outputs per thread; AP_TB outputs per block (template), AP_STRIP / AP_TB blocks
-template <bool EDGE, int AP_TB>
-__device__ __forceinline__ void aa_pair_block(const float* __restrict__ xb, float* __restrict__ y, __half* __restrict__ y_hi,
-                                              __half* __restrict__ y_lo, int64_t ob, int tb, int L, int C,
-                                              f32x2 (&sv)[2 * AP_TB + 10], f32x2 (&xw)[AP_TB + 5], f32x2 (&xn)[AP_TB],
-                                              bool more, const f32x2 (&e)[6], const f32x2 (&g)[6], f32x2 a2,
-                                              f32x2 inv_alpha) {
-  // new inputs x[tb + 5 .. tb + TB + 4]: requested one block earlier (ncu: the kernel stalled on these loads --
-  // long-scoreboard was the largest stall reason at 4 warps per scheduler); now request the next block's
-#pragma unroll
-  for (int i = 0; i < AP_TB; ++i) xw[5 + i] = xn[i];
-  if (more) {
-#pragma unroll
-    for (int i = 0; i < AP_TB; ++i) {
-      int l = tb + AP_TB + 5 + i;
-      l = l > L - 1 ? L - 1 : l;
-      xn[i] = *reinterpret_cast<const f32x2*>(xb + (int64_t)l * C);
-    }
-  }
-  // new up-sampled values: sv[i] <-> index 2*tb - 5 + i, i = 10 .. 2*TB + 9
+constexpr int AP_STRIP = 64;  // outputs per thread
+constexpr int AP_TB = 8;      // outputs per block; a strip is AP_STRIP / AP_TB = 8 blocks
+
+// The kernel is ISSUE bound (timing experiments in profiles/r02c_aa_experiments.txt: removing the sine, the stores or the
+// down-sampling taps each shortens it in proportion to the removed instructions; an FFMA2 holds the issue port for two
+// cycles, so 37 packed + 37 other instructions per output pair are 111 of the 129 measured cycles).  What can go is the
+// "other" half: the rolling windows therefore live in RING buffers with compile-time slot numbers -- 32 slots for the
+// up-sampled values (window 26, advance 16 per block), 16 for the inputs (window 13, advance 8): after two blocks every
+// value is back in its slot, so the loop body is two blocks and the 15 packed register moves per block that carried the
+// halo are gone -- and the output mode (fp32 / operand planes) is a template parameter instead of a branch per store.
+// P = block parity.  S(i): ring slot of window entry i (entry i <-> up-sampled index 2*tb - 5 + i); X(i): slot of input
+// window entry i (entry i <-> x[tb - 5 + i] ... the five carried inputs are entries 0..4, the block's new ones 5..12).
+template <bool EDGE, int P, int OM>
+__device__ __forceinline__ void aa_ring_block(const float* __restrict__ xb, float* __restrict__ y, __half* __restrict__ y_hi,
+                                              __half* __restrict__ y_lo, const int64_t ob, const int tb, const int L,
+                                              const int ldc, f32x2 (&sv)[32], f32x2 (&xw)[16], const bool more,
+                                              const f32x2 (&e)[6], const f32x2 (&g)[6], const f32x2 a2,
+                                              const f32x2 inv_alpha) {
+#define AA_S(i) ((16 * P + (i)) & 31)
+#define AA_X(i) ((8 * P + (i)) & 15)
+  // new up-sampled values: entries 10 .. 25
 #pragma unroll
   for (int i = 10; i < 2 * AP_TB + 10; ++i) {
     f32x2 u = pk2(0.f, 0.f);
     if ((i & 1) == 0) {
 #pragma unroll
-      for (int dd = 0; dd < 6; ++dd) u = fma2(xw[i / 2 + dd - 5], e[dd], u);          // f2[10 - 2d]
+      for (int dd = 0; dd < 6; ++dd) u = fma2(xw[AA_X(i / 2 + dd - 5)], e[dd], u);          // f2[10 - 2d]
     } else {
 #pragma unroll
-      for (int dd = 0; dd < 6; ++dd) u = fma2(xw[(i - 1) / 2 + dd - 5], e[5 - dd], u);  // f2[11 - 2d] == f2[2d]
+      for (int dd = 0; dd < 6; ++dd) u = fma2(xw[AA_X((i - 1) / 2 + dd - 5)], e[5 - dd], u);  // f2[11 - 2d] == f2[2d]
     }
-    sv[i] = snake2(u, a2, inv_alpha);
+    sv[AA_S(i)] = snake2(u, a2, inv_alpha);
+  }
+  // the next block's inputs x[tb + 13 .. tb + 20] go into the slots of input entries 0..7 of this block, which the
+  // up-sampling above has finished with (entries 8..12 are the next block's carried inputs); they have the whole
+  // down-sampling phase to arrive
+  if (more) {
+    if (tb + 2 * AP_TB + 4 <= L - 1) {  // rows inside the utterance: one pointer, compile-time multiples of the row stride
+      const float* xp = xb + (int64_t)(tb + AP_TB + 5) * ldc;
+#pragma unroll
+      for (int i = 0; i < AP_TB; ++i) xw[AA_X(13 + i)] = *reinterpret_cast<const f32x2*>(xp + i * ldc);
+    } else {
+#pragma unroll
+      for (int i = 0; i < AP_TB; ++i) {
+        int l = tb + AP_TB + 5 + i;
+        l = l > L - 1 ? L - 1 : l;
+        xw[AA_X(13 + i)] = *reinterpret_cast<const f32x2*>(xb + (int64_t)l * ldc);
+      }
+    }
   }
   if (EDGE) {
-    const int imax = 2 * (L - tb) + 4;  // strip index of up-sampled sample 2L-1: later ones repeat it
+    const int imax = 2 * (L - tb) + 4;  // entry of up-sampled sample 2L-1: later ones repeat it
 #pragma unroll
     for (int i = 10; i < 2 * AP_TB + 10; ++i)
-      if (i > imax) sv[i] = sv[i - 1];
+      if (i > imax) sv[AA_S(i)] = sv[AA_S(i - 1)];
   }
+  float* const yb = (OM & 1) ? y + ob : nullptr;  // block bases: every store is base + (compile-time t) * row stride
+  __half* const hb = (OM & 2) ? y_hi + ob : nullptr;
+  __half* const lb = (OM & 2) ? y_lo + ob : nullptr;
 #pragma unroll
   for (int t = 0; t < AP_TB; ++t) {
     if (!EDGE || tb + t < L) {
       f32x2 acc = pk2(0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < 12; ++k) acc = fma2(sv[2 * t + k], g[k < 6 ? k : 11 - k], acc);
+      for (int k = 0; k < 12; ++k) acc = fma2(sv[AA_S(2 * t + k)], g[k < 6 ? k : 11 - k], acc);
       float a0, a1;
       upk2(acc, a0, a1);
-      const int64_t o = ob + (int64_t)t * C;
-      if (y) *reinterpret_cast<float2*>(y + o) = make_float2(a0, a1);
-      if (y_hi) {
+      if (OM & 1) *reinterpret_cast<float2*>(yb + t * ldc) = make_float2(a0, a1);
+      if (OM & 2) {
         const __half2 h = pt_f2h2_sat(a0, a1);
         const float2 hf = __half22float2(h);
-        *reinterpret_cast<__half2*>(y_hi + o) = h;
-        *reinterpret_cast<__half2*>(y_lo + o) = pt_f2h2_sat(a0 - hf.x, a1 - hf.y);
+        *reinterpret_cast<__half2*>(hb + t * ldc) = h;
+        *reinterpret_cast<__half2*>(lb + t * ldc) = pt_f2h2_sat(a0 - hf.x, a1 - hf.y);
       }
     }
   }
-  // carry the shared halo into the next block
-#pragma unroll
-  for (int i = 0; i < 10; ++i) sv[i] = sv[2 * AP_TB + i];
-#pragma unroll
-  for (int i = 0; i < 5; ++i) xw[i] = xw[AP_TB + i];
+#undef AA_S
+#undef AA_X
 }
 
-template <int AP_TB, int MINB>
-__global__ void __launch_bounds__(256, MINB) aa_snake_pair_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                            __half* __restrict__ y_hi, __half* __restrict__ y_lo, int L,
-                                                            int C, int n_strips, const float* __restrict__ log_alpha,
-                                                            const float* __restrict__ up_f,
-                                                            const float* __restrict__ down_f) {
+template <int OM>
+__global__ void __launch_bounds__(256, 2) aa_snake_pair_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                               __half* __restrict__ y_hi, __half* __restrict__ y_lo,
+                                                               int L, int C, int n_strips,
+                                                               const float* __restrict__ log_alpha,
+                                                               const float* __restrict__ up_f,
+                                                               const float* __restrict__ down_f) {
   const int half_c = C >> 1;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cp = (int)(gid % half_c);
@@ -204,6 +222,7 @@ __global__ void __launch_bounds__(256, MINB) aa_snake_pair_kernel(const float* _
   const int strip = (int)strip_ll;
   const int c = 2 * cp;
   const int t0 = strip * AP_STRIP;
+  const int ldc = C;
   f32x2 e[6], g[6];
 #pragma unroll
   for (int d = 0; d < 6; ++d) {
@@ -215,15 +234,22 @@ __global__ void __launch_bounds__(256, MINB) aa_snake_pair_kernel(const float* _
   const f32x2 inv_alpha = pk2(1.f / (al0 + 1e-9f), 1.f / (al1 + 1e-9f));
   const f32x2 a2 = pk2(al0, al1);
   const float* xb = x + (int64_t)blockIdx.y * L * C + c;
-  f32x2 sv[2 * AP_TB + 10], xw[AP_TB + 5];
+  f32x2 sv[32], xw[16];
   // prologue: the 10 up-sampled values in front of the strip (indices 2*t0 - 5 .. 2*t0 + 4) from x[t0 - 5 .. t0 + 4]
+  // -> ring entries 0..9 of block parity 0; inputs x[t0 .. t0 + 4] -> input entries 0..4, x[t0 + 5 .. t0 + 12] -> 5..12
   {
     f32x2 xs[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
       int l = t0 - 5 + i;
       l = l < 0 ? 0 : (l > L - 1 ? L - 1 : l);
-      xs[i] = *reinterpret_cast<const f32x2*>(xb + (int64_t)l * C);
+      xs[i] = *reinterpret_cast<const f32x2*>(xb + (int64_t)l * ldc);
+    }
+#pragma unroll
+    for (int i = 0; i < AP_TB; ++i) {
+      int l = t0 + 5 + i;
+      l = l > L - 1 ? L - 1 : l;
+      xw[5 + i] = *reinterpret_cast<const f32x2*>(xb + (int64_t)l * ldc);
     }
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
@@ -248,23 +274,26 @@ __global__ void __launch_bounds__(256, MINB) aa_snake_pair_kernel(const float* _
 #pragma unroll
     for (int i = 0; i < 5; ++i) xw[i] = xs[5 + i];
   }
-  f32x2 xn[AP_TB];  // inputs of the next block, in flight while the current one is computed
-#pragma unroll
-  for (int i = 0; i < AP_TB; ++i) {
-    int l = t0 + 5 + i;
-    l = l > L - 1 ? L - 1 : l;
-    xn[i] = *reinterpret_cast<const f32x2*>(xb + (int64_t)l * C);
-  }
   const int64_t ob0 = (int64_t)blockIdx.y * L * C + c;
-#pragma unroll 1
   constexpr int AP_NB = AP_STRIP / AP_TB;
-  for (int blk = 0; blk < AP_NB; ++blk) {
-    const int tb = t0 + blk * AP_TB;
-    if (tb >= L) break;
-    const int64_t ob = ob0 + (int64_t)tb * C;
-    const bool more = (blk + 1 < AP_NB) && (tb + AP_TB < L);
-    if (tb + AP_TB + 4 <= L - 1) aa_pair_block<false, AP_TB>(xb, y, y_hi, y_lo, ob, tb, L, C, sv, xw, xn, more, e, g, a2, inv_alpha);
-    else aa_pair_block<true, AP_TB>(xb, y, y_hi, y_lo, ob, tb, L, C, sv, xw, xn, more, e, g, a2, inv_alpha);
+#pragma unroll 1
+  for (int blk = 0; blk < AP_NB; blk += 2) {
+    {
+      const int tb = t0 + blk * AP_TB;
+      if (tb >= L) break;
+      const int64_t ob = ob0 + (int64_t)tb * ldc;
+      const bool more = tb + AP_TB < L;  // (blk + 1 < AP_NB always: blk is even)
+      if (tb + AP_TB + 4 <= L - 1) aa_ring_block<false, 0, OM>(xb, y, y_hi, y_lo, ob, tb, L, ldc, sv, xw, more, e, g, a2, inv_alpha);
+      else aa_ring_block<true, 0, OM>(xb, y, y_hi, y_lo, ob, tb, L, ldc, sv, xw, more, e, g, a2, inv_alpha);
+    }
+    {
+      const int tb = t0 + (blk + 1) * AP_TB;
+      if (tb >= L) break;
+      const int64_t ob = ob0 + (int64_t)tb * ldc;
+      const bool more = (blk + 2 < AP_NB) && (tb + AP_TB < L);
+      if (tb + AP_TB + 4 <= L - 1) aa_ring_block<false, 1, OM>(xb, y, y_hi, y_lo, ob, tb, L, ldc, sv, xw, more, e, g, a2, inv_alpha);
+      else aa_ring_block<true, 1, OM>(xb, y, y_hi, y_lo, ob, tb, L, ldc, sv, xw, more, e, g, a2, inv_alpha);
+    }
   }
 }
 
@@ -282,14 +311,12 @@ void aa_snake_cl(const float* x, float* y, int B, int L, int C, const float* log
     const int n_strips = ceil_div(L, AP_STRIP);
     const long long threads = (long long)(C / 2) * n_strips;
     dim3 grid((unsigned)ceil_div64(threads, 256), B);
-    // PTTSPP_AA_TB (experiments): outputs per rolling block; 8 -> 101 registers, 2 CTAs per SM; 4 -> 80 registers, 3 CTAs
-    static const int tb = [] { const char* e = getenv("PTTSPP_AA_TB"); return e ? atoi(e) : 8; }();
-    if (tb == 4)
-      aa_snake_pair_kernel<4, 3><<<grid, 256, 0, s>>>(x, y, (__half*)y_hi, (__half*)y_lo, L, C, n_strips, log_alpha, up_f, down_f);
-    else if (tb == 2)
-      aa_snake_pair_kernel<2, 4><<<grid, 256, 0, s>>>(x, y, (__half*)y_hi, (__half*)y_lo, L, C, n_strips, log_alpha, up_f, down_f);
+    if (y && y_hi)
+      aa_snake_pair_kernel<3><<<grid, 256, 0, s>>>(x, y, (__half*)y_hi, (__half*)y_lo, L, C, n_strips, log_alpha, up_f, down_f);
+    else if (y_hi)
+      aa_snake_pair_kernel<2><<<grid, 256, 0, s>>>(x, y, (__half*)y_hi, (__half*)y_lo, L, C, n_strips, log_alpha, up_f, down_f);
     else
-      aa_snake_pair_kernel<8, 2><<<grid, 256, 0, s>>>(x, y, (__half*)y_hi, (__half*)y_lo, L, C, n_strips, log_alpha, up_f, down_f);
+      aa_snake_pair_kernel<1><<<grid, 256, 0, s>>>(x, y, (__half*)y_hi, (__half*)y_lo, L, C, n_strips, log_alpha, up_f, down_f);
     PT_LAUNCHED();
     return;
   }
