@@ -811,7 +811,7 @@ conv1d_umma_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
 // from absolute shared-memory address bits, so any row offset is legal -- verified on B200 by tools/probe_desc.py).
 // NSUB = 2: a unit is 256 rows = two 128-row MMA tiles that share every weight stage (the weight tiles are what all SMs
 // re-stream from the same L2 lines: ncu of the 64-column k = 11 conv showed 5.4 TB/s of L2 -> SM fill at 36 % tensor pipe).
-template <int BN, int NSUB>
+template <int BN, int NSUB, bool RL>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                       const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
@@ -875,17 +875,17 @@ conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_co
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == UM_EPI_WARPS) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      uint32_t g = 0;
-      int j = 0;
-      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++j) {
-        const int mt = unit % n_mt, b = unit / n_mt;  // n_mt counts units (NSUB x 128 rows) per utterance
-        const int row0 = d.m_begin + mt * (NSUB * UM_BM) - d.pad;  // first input row of the halo block (may be negative)
-        const int nbox = (rowsA > 256) ? 2 : 1, box_rows = rowsA / nbox;  // a TMA box holds at most 256 rows
-        const int q = j % nabuf;
-        const uint32_t ablk = base + (uint32_t)q * a_bytes;
-        mbar_wait(emptyA(q), (((uint32_t)(j / nabuf)) & 1u) ^ 1u);  // the MMAs of the unit that used this buffer have retired
+    // ================= TMA producer (warp-uniform loop, one elected lane issues) =================
+    uint32_t g = 0;
+    int j = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++j) {
+      const int mt = unit % n_mt, b = unit / n_mt;  // n_mt counts units (NSUB x 128 rows) per utterance
+      const int row0 = d.m_begin + mt * (NSUB * UM_BM) - d.pad;  // first input row of the halo block (may be negative)
+      const int nbox = (rowsA > 256) ? 2 : 1, box_rows = rowsA / nbox;  // a TMA box holds at most 256 rows
+      const int q = j % nabuf;
+      const uint32_t ablk = base + (uint32_t)q * a_bytes;
+      mbar_wait_warp(emptyA(q), (((uint32_t)(j / nabuf)) & 1u) ^ 1u);  // the MMAs of the unit that used this buffer have retired
+      if (elect_one()) {
         mbar_expect_tx(fullA(q), a_bytes);
         for (int slab = 0; slab < nslab; ++slab)
           for (int bx = 0; bx < nbox; ++bx) {
@@ -893,48 +893,54 @@ conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_co
             tma_load_3d(ablk + (uint32_t)(2 * slab) * a_plane + boff, &mapAh, fullA(q), slab * UM_BK, row0 + bx * box_rows, b);
             tma_load_3d(ablk + (uint32_t)(2 * slab + 1) * a_plane + boff, &mapAl, fullA(q), slab * UM_BK, row0 + bx * box_rows, b);
           }
-        for (int nt = 0; nt < n_nt; ++nt)
-          for (int slab = 0; slab < nslab; ++slab)
-            for (int tap = 0; tap < d.K; ++tap, ++g) {
-              const int s = g % nbst;
-              const uint32_t ph = (g / nbst) & 1u;
-              mbar_wait(emptyB(s), ph ^ 1u);
+      }
+      __syncwarp();
+      for (int nt = 0; nt < n_nt; ++nt)
+        for (int slab = 0; slab < nslab; ++slab)
+          for (int tap = 0; tap < d.K; ++tap, ++g) {
+            const int s = g % nbst;
+            const uint32_t ph = (g / nbst) & 1u;
+            mbar_wait_warp(emptyB(s), ph ^ 1u);
+            if (elect_one()) {
               mbar_expect_tx(fullB(s), BST_BYTES);
               const uint32_t st = ring + (uint32_t)s * BST_BYTES;
               tma_load_2d(st, &mapBh, fullB(s), slab * UM_BK, tap * cout_total + nt * BN);
               tma_load_2d(st + B_BYTES, &mapBl, fullB(s), slab * UM_BK, tap * cout_total + nt * BN);
             }
-      }
+            __syncwarp();
+          }
     }
   } else if (warp == UM_EPI_WARPS + 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(UM_BM, BN);
-      constexpr uint32_t idesc2 = umma_idesc_f16(UM_BM, 2 * BN);  // [W_hi | W_lo] stacked along N (main | cross)
-      uint32_t g = 0;
-      int j = 0, i = 0;
-      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++j) {
-        const int q = j % nabuf;
-        const uint32_t ablk = base + (uint32_t)q * a_bytes;
-        mbar_wait(fullA(q), ((uint32_t)(j / nabuf)) & 1u);
+    // ================= MMA issuer (warp-uniform loop, one elected lane issues: barrier addresses and descriptors stay in
+    // uniform registers; the single-lane form of this loop issued one instruction every few cycles and was the
+    // kernel's bottleneck -- ncu: no barrier retries in this warp at 36 % tensor pipe) =================
+    constexpr uint32_t idesc = umma_idesc_f16(UM_BM, BN);
+    constexpr uint32_t idesc2 = umma_idesc_f16(UM_BM, 2 * BN);  // [W_hi | W_lo] stacked along N (main | cross)
+    const uint64_t desc0 = umma_desc_k_sw128(base);  // descriptors differ only in the 14-bit start-address field
+    uint32_t g = 0;
+    int j = 0, i = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++j) {
+      const int q = j % nabuf;
+      const uint32_t ablk_off = (uint32_t)q * a_bytes;
+      mbar_wait_warp(fullA(q), ((uint32_t)(j / nabuf)) & 1u);
+      tc_fence_after();
+      for (int nt = 0; nt < n_nt; ++nt, ++i) {
+        const int u = i & 1;
+        mbar_wait_warp(tempty_bar(u), (((uint32_t)i >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        for (int nt = 0; nt < n_nt; ++nt, ++i) {
-          const int u = i & 1;
-          mbar_wait(tempty_bar(u), (((uint32_t)i >> 1) & 1u) ^ 1u);
-          tc_fence_after();
-          const uint32_t acc_u = tmem_base + (uint32_t)(u * NSUB * UM_NACC * BN);  // sub-tile s: + s * NACC * BN (main | cross)
-          uint32_t first = 0;
-          for (int slab = 0; slab < nslab; ++slab)
-            for (int tap = 0; tap < d.K; ++tap, ++g) {
-              const int s = g % nbst;
-              const uint32_t ph = (g / nbst) & 1u;
-              mbar_wait(fullB(s), ph);
-              tc_fence_after();
-              const uint32_t a_off = (uint32_t)(tap * d.dil) * 128u;  // taps share the halo tile
-              const uint64_t dAh = umma_desc_k_sw128(ablk + (uint32_t)(2 * slab) * a_plane + a_off);
-              const uint64_t dAl = umma_desc_k_sw128(ablk + (uint32_t)(2 * slab + 1) * a_plane + a_off);
-              const uint32_t st = ring + (uint32_t)s * BST_BYTES;
-              const uint64_t dBh = umma_desc_k_sw128(st);
+        const uint32_t acc_u = tmem_base + (uint32_t)(u * NSUB * UM_NACC * BN);  // sub-tile s: + s * NACC * BN (main | cross)
+        uint32_t first = 0;
+        for (int slab = 0; slab < nslab; ++slab)
+          for (int tap = 0; tap < d.K; ++tap, ++g) {
+            const int s = g % nbst;
+            const uint32_t ph = (g / nbst) & 1u;
+            mbar_wait_warp(fullB(s), ph);
+            tc_fence_after();
+            const uint32_t a_off = ablk_off + (uint32_t)(2 * slab) * a_plane + (uint32_t)(tap * d.dil) * 128u;  // taps share the halo tile
+            const uint64_t dAh = desc0 + (uint64_t)(a_off >> 4);
+            const uint64_t dAl = dAh + (uint64_t)(a_plane >> 4);
+            const uint64_t dBh = desc0 + (uint64_t)(((uint32_t)nabuf * a_bytes + (uint32_t)s * BST_BYTES) >> 4);
+            if (elect_one()) {
 #pragma unroll
               for (int sub = 0; sub < NSUB; ++sub) {
                 const uint64_t soff = (uint64_t)((uint32_t)(sub * UM_BM) * 128u >> 4);  // the sub-tile's rows of the block
@@ -948,13 +954,16 @@ conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_co
                   umma_f16(acc_cross, dAl + adv, dBh + advb, idesc, 1u);
                 }
               }
-              first = 1u;
               umma_commit(emptyB(s));
             }
-          umma_commit(tfull_bar(u));
-        }
-        umma_commit(emptyA(q));  // the activation block may be overwritten once everything issued so far has retired
+            __syncwarp();
+            first = 1u;
+          }
+        if (elect_one()) umma_commit(tfull_bar(u));
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(emptyA(q));  // the activation block may be overwritten once everything issued so far has retired
+      __syncwarp();
     }
   } else {
     // ================= epilogue: warps 0-15 =================
@@ -967,7 +976,14 @@ conv1d_umma_as_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_co
           // buffer (i & 1), sub-tile `sub`: the epilogue addresses buffer (its i) & 1 and waits with parity (its i >> 1) & 1
           const uint32_t tb = tmem_base + (uint32_t)(((i & 1) * NSUB + sub) * UM_NACC * BN);
           const int i2 = i & ~1;
-          if (nt * BN >= cout1)
+          if constexpr (RL) {  // row-per-lane 256-bit epilogue (host: epilogue_rl_ok): half the instructions of the generic one
+            if (nt * BN >= cout1)
+              umma_tile_epilogue_rl<BN, UM_NACC, UM_EPI_WARPS>(d2, nt * BN - cout1, mt * NSUB + sub, b, 0, ((uint32_t)i >> 1) & 1u,
+                                                               warp, lane, tb, tfull_bar(i & 1), 1, 0);
+            else
+              umma_tile_epilogue_rl<BN, UM_NACC, UM_EPI_WARPS>(d, nt * BN, mt * NSUB + sub, b, 0, ((uint32_t)i >> 1) & 1u, warp,
+                                                               lane, tb, tfull_bar(i & 1), 1, 0);
+          } else if (nt * BN >= cout1)
             umma_tile_epilogue<BN, UM_NACC>(d2, nt * BN - cout1, vec_ok, mt * NSUB + sub, b, i2, warp, lane, tb,
                                             tfull_bar(i & 1), 1, nullptr, false, nullptr, 0u);
           else
@@ -2307,7 +2323,7 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
     const CUtensorMap mAh = make_map(d.in_hi, 3, adims, astr, abox);
     const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox);
     const size_t smem = nabuf * a_bytes + nbst * bst + 512 + 1024;
-    auto kern = conv1d_umma_as_kernel<UM_BN, 1>;
+    auto kern = conv1d_umma_as_kernel<UM_BN, 1, false>;
     ensure_smem_optin((const void*)kern, 227 * 1024);
     const int grid = (int)std::min<long long>(n_units, num_sms);
     kern<<<grid, UM_THREADS, smem, s>>>(mAh, mAl, mBh, mBl, d, d2, d2_in ? cout1 : total_cout, total_cout, vec ? 1 : 0,
@@ -2336,7 +2352,9 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
     const CUtensorMap mBh64 = make_map(d.w_hi, 2, wdims, wstr, wbox64);
     const CUtensorMap mBl64 = make_map(d.w_lo, 2, wdims, wstr, wbox64);
     const size_t smem = 2 * a_bytes2 + nbst * bst64 + 512 + 1024;
-    auto kern = conv1d_umma_as_kernel<64, 2>;
+    // (measured: the row-per-lane epilogue wins only when the tile also leaves as operand planes -- 811 -> 639 us -- and
+    // loses 7 % on plain / residual epilogues)
+    auto kern = (d.out_hi && epilogue_rl_ok(d)) ? conv1d_umma_as_kernel<64, 2, true> : conv1d_umma_as_kernel<64, 2, false>;
     ensure_smem_optin((const void*)kern, 227 * 1024);
     const int n_mt2 = ceil_div(n_mt, 2);
     const long long n_units2 = (long long)n_mt2 * d.B;
@@ -2355,7 +2373,7 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
     const CUtensorMap mBh64 = make_map(d.w_hi, 2, wdims, wstr, wbox64);
     const CUtensorMap mBl64 = make_map(d.w_lo, 2, wdims, wstr, wbox64);
     const size_t smem = 2 * a_bytes + nbst * bst64 + 512 + 1024;
-    auto kern = conv1d_umma_as_kernel<64, 1>;
+    auto kern = (d.out_hi && epilogue_rl_ok(d)) ? conv1d_umma_as_kernel<64, 1, true> : conv1d_umma_as_kernel<64, 1, false>;
     ensure_smem_optin((const void*)kern, 227 * 1024);
     const int grid = (int)std::min<long long>(n_units, num_sms);
     kern<<<grid, UM_THREADS, smem, s>>>(mAh, mAl, mBh64, mBl64, d, d2, total_cout, total_cout, vec ? 1 : 0, n_mt, 1,
