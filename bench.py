@@ -290,9 +290,12 @@ def leg_cfg4(model, voc, voc_f0, device, n=32):
 
     phonemes, emb = var_len_requests(n, seed=41)
     res = {"workload": f"cfg4: end-to-end text+style-prompt -> 24 kHz waveform, {n} variable-length requests "
-                       "(32..256 phonemes) through serving.BatchedSynthesizer (max_tokens 8192)"}
+                       "(32..256 phonemes) through serving.BatchedSynthesizer (max_tokens 8192, batch boundaries "
+                       "minimising the padded work: serving.cost_buckets)"}
     for name, v in (("bigvgan", voc), ("bigvgan_f0", voc_f0)):
         srv = BatchedSynthesizer(model, v, MelStats(mean=-5.0, std=2.0), max_tokens=8192, max_sentences=32)
+        res["batches"] = [len(b) for b in __import__("promptttspp_b200.serving", fromlist=["cost_buckets"]).cost_buckets(
+            [int(p.numel()) for p in phonemes], 8192, 32)]
 
         def run():
             torch.manual_seed(11)

@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from promptttspp_b200.serving import token_buckets
+from promptttspp_b200.serving import cost_buckets, token_buckets
 
 
 def test_token_buckets_cover_budget_and_order():
@@ -27,6 +27,37 @@ def test_token_buckets_cover_budget_and_order():
         token_buckets([1], 0)
     # a rank's shard only
     assert sorted(i for b in token_buckets(lengths, 1024, 8, indices=[3, 5, 7]) for i in b) == [3, 5, 7]
+
+
+def test_cost_buckets_minimise_padded_work():
+    import random
+
+    def cost(batches, lengths, min_tokens=2048, overhead=256):
+        return sum(max(len(b) * max(lengths[i] for i in b), min_tokens) + overhead for b in batches)
+
+    rng = random.Random(3)
+    for trial in range(20):
+        n = rng.randint(1, 70)
+        lengths = [rng.randint(1, 300) for _ in range(n)]
+        for max_tokens, cap in ((8192, 32), (1024, 8), (200, None)):
+            cb = cost_buckets(lengths, max_tokens, cap)
+            tb = token_buckets(lengths, max_tokens, cap)
+            assert sorted(i for b in cb for i in b) == list(range(n))             # every request exactly once
+            for b in cb:
+                longest = max(lengths[i] for i in b)
+                assert len(b) == 1 or len(b) * longest <= max_tokens                # same budget rule as the greedy cutter
+                assert cap is None or len(b) <= cap
+                assert all(lengths[b[0]] >= lengths[i] for i in b)                  # length-sorted, longest first
+            assert cost(cb, lengths) <= cost(tb, lengths)                           # never worse than budget filling
+            assert cb == cost_buckets(lengths, max_tokens, cap)                     # deterministic
+    # cfg4's shape: 32 requests of 32..256 phonemes -- one budget-filling batch pads to 8192 tokens, the optimum does not
+    lengths = [32 + 7 * i for i in range(32)]
+    assert len(token_buckets(lengths, 8192, 32)) == 1
+    cb = cost_buckets(lengths, 8192, 32)
+    assert len(cb) >= 2 and sum(len(b) * max(lengths[i] for i in b) for b in cb) < 0.85 * 32 * max(lengths)
+    assert cost_buckets([300, 10], max_tokens=128) == [[0], [1]]
+    assert cost_buckets([], 64) == []
+    assert sorted(i for b in cost_buckets(lengths, 1024, 8, indices=[3, 5, 7]) for i in b) == [3, 5, 7]
 
 
 @pytest.mark.gpu
