@@ -222,14 +222,15 @@ class WavWriter:
 class BatchedSynthesizer:
     def __init__(self, model, vocoder, stats: MelStats = MelStats(), max_tokens: int = 4096,
                  max_sentences: Optional[int] = 32, use_lowpass: bool = True, noise_scale: float = 0.5,
-                 frame_rate: int = 100, seed: Optional[int] = None, bucketing: str = "cost"):
+                 frame_rate: int = 100, seed: Optional[int] = None, bucketing: str = "cost",
+                 min_tokens: int = 2048, overhead_tokens: int = 256):
         """bucketing: "cost" (default) = `cost_buckets`, batch boundaries minimising the padded work; "greedy" =
         `token_buckets`, the trainer's budget-filling rule."""
         if bucketing not in ("cost", "greedy"):
             raise ValueError(f"bucketing must be 'cost' or 'greedy', got {bucketing!r}")
         self.model, self.vocoder, self.stats = model, vocoder, stats
         self.max_tokens, self.max_sentences = max_tokens, max_sentences
-        self.bucketing = bucketing
+        self.bucketing, self.min_tokens, self.overhead_tokens = bucketing, min_tokens, overhead_tokens
         self.use_lowpass, self.noise_scale, self.frame_rate = use_lowpass, noise_scale, frame_rate
         self.f0_aware = hasattr(vocoder, "m_source")
         # seed: every batch draws its noise from torch.manual_seed(seed + first request index of the batch), so a
@@ -248,8 +249,11 @@ class BatchedSynthesizer:
         hop = getattr(self.vocoder, "hop", 240)
         out: Dict[int, torch.Tensor] = {}
         # batches are cut from ALL requests and then dealt to the ranks: their composition does not depend on world_size
-        cutter = cost_buckets if self.bucketing == "cost" else token_buckets
-        buckets = cutter(lengths, self.max_tokens, self.max_sentences)
+        if self.bucketing == "cost":
+            buckets = cost_buckets(lengths, self.max_tokens, self.max_sentences, min_tokens=self.min_tokens,
+                                   overhead_tokens=self.overhead_tokens)
+        else:
+            buckets = token_buckets(lengths, self.max_tokens, self.max_sentences)
         for batch in shard_batches(buckets, lengths, world_size, rank):
             if self.seed is not None:
                 torch.manual_seed(self.seed + batch[0])
