@@ -1455,6 +1455,166 @@ conv1d_umma_c32_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_c
   }
 }
 
+// ---- weight-resident kernel, CTA-pair form ---------------------------------------------------------------------------
+// The weight-resident kernel above is bound by the tensor core's operand fetch from shared memory (ncu: 70 % of the
+// wavefront peak at 38 % tensor pipe).  As a cta_group::2 pair one instruction covers 256 rows (128 per CTA) and each
+// CTA supplies only HALF of the B operand: per k step and CTA  x_hi (4 KB) + half of [W_hi | W_lo]  and  x_lo (4 KB) +
+// half of W_hi  = 11 -> 9.5 KB at 32 channels, 14 -> 11 KB at 64, with half the MMA instructions per row.  The weights
+// stay resident: per tap slot 1 = the CTA's half of the stacked operand (rank 0: the C rows of W_hi, rank 1: the C rows
+// of W_lo) and slot 2 = its half of W_hi (C/2 rows) -- 1.5 C rows per tap and CTA, so 64 channels x 11 taps (135 KB) fit
+// next to two activation stages, which the single-CTA form (180 KB) cannot hold.  Same MMA order per output element as
+// every other kernel of the vocoder's convs: same bits.
+template <int US_C>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(US_THREADS, 1)
+conv1d_umma_wres_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                             const __grid_constant__ CUtensorMap mapBhF, const __grid_constant__ CUtensorMap mapBlF,
+                             const __grid_constant__ CUtensorMap mapBhH, const pttspp_conv1d_desc d, const int n_mt,
+                             const int n_units, const int rowsA, const int nst) {
+  constexpr int NBUF = 512 / (2 * US_C);
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t ROWB = US_C * 2;
+  constexpr uint32_t TAPB = (US_C + US_C / 2) * ROWB;  // slot 1 (C rows) + slot 2 (C/2 rows)
+  constexpr int MAX_NST = 6;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t w_bytes = (uint32_t)d.K * TAPB;
+  const uint32_t a_plane = (uint32_t)rowsA * ROWB;
+  const uint32_t a_stage = ((2u * a_plane) + 1023u) & ~1023u;
+  const uint32_t ring = base + ((w_bytes + 1023u) & ~1023u);
+  const uint32_t bars_off = ((w_bytes + 1023u) & ~1023u) + (uint32_t)nst * a_stage;
+  const uint32_t bars = base + bars_off;
+  constexpr int NBARS = 1 + 2 * MAX_NST + 2 * NBUF;
+  const uint32_t fullW = bars;
+  auto fullA = [&](int st) { return bars + (1 + st) * 8; };
+  auto emptyA = [&](int st) { return bars + (1 + MAX_NST + st) * 8; };
+  auto tfull_bar = [&](int u) { return bars + (1 + 2 * MAX_NST + u) * 8; };
+  auto tempty_bar = [&](int u) { return bars + (1 + 2 * MAX_NST + NBUF + u) * 8; };
+  const uint32_t tmem_slot = bars + NBARS * 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + bars_off + NBARS * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  constexpr int W_PROD = US_GROUPS * US_EW, W_MMA = W_PROD + 1;
+  if (threadIdx.x == 0) {
+    mbar_init(fullW, 1);
+    for (int st = 0; st < MAX_NST; ++st) {
+      mbar_init(fullA(st), 1);
+      mbar_init(emptyA(st), 1);
+    }
+    for (int u = 0; u < NBUF; ++u) {
+      mbar_init(tfull_bar(u), 1);
+      mbar_init(tempty_bar(u), 2 * US_EW);  // one epilogue group of each CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == W_PROD && lane == 0) {
+    tma_prefetch_desc(&mapAh);
+    tma_prefetch_desc(&mapAl);
+    tma_prefetch_desc(&mapBhF);
+    tma_prefetch_desc(&mapBlF);
+    tma_prefetch_desc(&mapBhH);
+  }
+  if (warp == W_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int n_blocks = d.B * n_mt;  // flat (utterance, 128-row block) list; unit u = blocks 2u (rank 0), 2u + 1 (rank 1)
+
+  if (warp == W_PROD) {
+    // ================= TMA producer (both CTAs): own weight halves once, own activation block per unit =================
+    if (elect_one()) {
+      if (rank == 0) mbar_expect_tx(fullW, 2u * w_bytes);
+      for (int tap = 0; tap < d.K; ++tap) {
+        tma_load_2d_pair(base + (uint32_t)tap * TAPB, rank == 0 ? &mapBhF : &mapBlF, fullW, 0, tap * US_C);
+        tma_load_2d_pair(base + (uint32_t)tap * TAPB + US_C * ROWB, &mapBhH, fullW, 0, tap * US_C + (int)rank * (US_C / 2));
+      }
+    }
+    __syncwarp();
+    uint32_t g = 0;
+    for (int unit = cluster_id; unit < n_units; unit += n_clusters, ++g) {
+      const int q = 2 * unit + (int)rank;
+      const int b = min(q / n_mt, d.B - 1), mt = (q < n_blocks) ? q - (q / n_mt) * n_mt : n_mt;  // past the end: no rows
+      const int st = (int)(g % (uint32_t)nst);
+      mbar_wait_warp(emptyA(st), ((g / (uint32_t)nst) & 1u) ^ 1u);
+      const int row0 = d.m_begin + mt * UM_BM - d.pad;
+      if (elect_one()) {
+        if (rank == 0) mbar_expect_tx(fullA(st), 4u * a_plane);
+        tma_load_3d_pair(ring + (uint32_t)st * a_stage, &mapAh, fullA(st), 0, row0, b);
+        tma_load_3d_pair(ring + (uint32_t)st * a_stage + a_plane, &mapAl, fullA(st), 0, row0, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == W_MMA) {
+    // ================= MMA issuer (leader CTA) =================
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(2 * UM_BM, US_C);
+      constexpr uint32_t idesc2 = umma_idesc_f16(2 * UM_BM, 2 * US_C);
+      const uint64_t descW = (US_C == 32) ? umma_desc_k_sw64(base) : umma_desc_k_sw128(base);
+      mbar_wait_warp(fullW, 0);
+      tc_fence_after();
+      uint32_t g = 0;
+      for (int unit = cluster_id; unit < n_units; unit += n_clusters, ++g) {
+        const int st = (int)(g % (uint32_t)nst), u = g % NBUF;
+        mbar_wait_warp(tempty_bar(u), ((g / NBUF) & 1u) ^ 1u);  // both CTAs' epilogue groups have drained buffer u
+        mbar_wait_warp(fullA(st), (g / (uint32_t)nst) & 1u);
+        tc_fence_after();
+        const uint32_t acc_main = tmem_base + (uint32_t)(u * 2 * US_C);
+        const uint32_t acc_cross = acc_main + (uint32_t)US_C;
+        const uint64_t descA = (US_C == 32) ? umma_desc_k_sw64(ring + (uint32_t)st * a_stage)
+                                            : umma_desc_k_sw128(ring + (uint32_t)st * a_stage);
+        if (elect_one()) {
+          for (int tap = 0; tap < d.K; ++tap) {
+            const uint64_t dAh = descA + (uint64_t)(((uint32_t)(tap * d.dil) * ROWB) >> 4);
+            const uint64_t dAl = dAh + (uint64_t)(a_plane >> 4);
+            const uint64_t dB1 = descW + (uint64_t)(((uint32_t)tap * TAPB) >> 4);
+            const uint64_t dB2 = dB1 + (uint64_t)((US_C * ROWB) >> 4);
+#pragma unroll
+            for (int kk = 0; kk < US_C / 16; ++kk) {
+              const uint64_t adv = (uint64_t)(kk * 2);
+              const uint32_t acc = (tap | kk) ? 1u : 0u;
+              umma_f16_pair(acc_main, dAh + adv, dB1 + adv, idesc2, acc);  // x_hi . [W_hi | W_lo] -> main | cross
+              umma_f16_pair(acc_cross, dAl + adv, dB2 + adv, idesc, 1u);   // x_lo . W_hi
+            }
+          }
+          umma_commit_pair(emptyA(st));
+          umma_commit_pair(tfull_bar(u));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================= epilogue (both CTAs): two groups of 8 warps alternate units, each CTA drains its own rows ======
+    const int grp = warp / US_EW, wl = warp % US_EW;
+    uint32_t g = 0;
+    for (int unit = cluster_id; unit < n_units; unit += n_clusters, ++g) {
+      if ((int)(g % US_GROUPS) != grp) continue;
+      const int q = 2 * unit + (int)rank;
+      const int b = min(q / n_mt, d.B - 1), mt = (q < n_blocks) ? q - (q / n_mt) * n_mt : n_mt;
+      const int u = g % NBUF;
+      umma_tile_epilogue_rl<US_C, 2, US_EW>(d, 0, mt, b, u, (g / NBUF) & 1u, wl, lane, tmem_base, tfull_bar(u), 1, 0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(tempty_bar(u));
+        else mbar_arrive_cluster(tempty_bar(u), 0);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still signal it
+  if (warp == W_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---- fused anti-aliased Snake -> weight-resident conv -------------------------------------------------------------
 // BigVGAN's AMP layer is  x -> AA-Snake -> conv1 -> AA-Snake -> conv2 (+x)  (vocoders/bigvgan.py:42-47,
 // layers/activations.py:22-138).  With the activation as its own launch the activated tensor makes a round trip through
@@ -2199,6 +2359,57 @@ void conv1d_umma_c32_launch(const pttspp_conv1d_desc& d_in, cudaStream_t s) {
 #undef PT_WRES
 }
 
+// CTA-pair form of the weight-resident kernel: impl 4 convs (the vocoder) with enough 128-row blocks to fill the machine
+bool conv1d_umma_wres_pair_try(const pttspp_conv1d_desc& d_in, cudaStream_t s) {
+  static const bool off = getenv("PTTSPP_UMMA_NO_WRES_PAIR") != nullptr;
+  const pttspp_conv1d_desc& q = d_in;
+  if (off || q.impl != 4) return false;
+  if (!((q.Cin == 32 && q.Cout == 32 && q.K <= US_MAXK) || (q.Cin == 64 && q.Cout == 64 && q.K <= US_MAXK))) return false;
+  if (!(q.K >= 1 && q.in_hi && q.in_lo && q.w_hi && q.w_lo && q.in_stride == 1 && !q.in_len && !q.in_add &&
+        q.in_ld % 8 == 0 && q.in_bs % 8 == 0 && aligned16(q.in_hi) && aligned16(q.in_lo) && aligned16(q.w_hi) &&
+        aligned16(q.w_lo) && q.w_scale_inv > 0.f && epilogue_rl_ok(q)))
+    return false;
+  const int C = q.Cin, rowb = C * 2;
+  const int rowsA = UM_BM + round_up((q.K - 1) * q.dil, 8);
+  if (rowsA > 256) return false;
+  const size_t w_bytes = round_up(q.K * (C + C / 2) * rowb, 1024);
+  const size_t a_stage = round_up(2 * rowsA * rowb, 1024);
+  const size_t misc = (1 + 2 * 6 + 2 * US_MAX_NBUF) * 8 + 16 + 1024;
+  const size_t cap = 227 * 1024;
+  if (w_bytes + 2 * a_stage + misc > cap) return false;
+  const int num_sms = device_num_sms();
+  const int n_mt = ceil_div(q.M, UM_BM);
+  const long long n_blocks = (long long)n_mt * q.B;
+  if (n_blocks < 2ll * num_sms || n_blocks >= (1ll << 30)) return false;  // every pair gets >= 2 units
+  pttspp_conv1d_desc d = d_in;
+  d.acc_scale = d_in.acc_scale * d_in.w_scale_inv;
+  const CUtensorMapSwizzle swz = (C == 32) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const uint64_t wdims[2] = {(uint64_t)C, (uint64_t)d.K * C};
+  const uint64_t wstr[1] = {(uint64_t)C * 2};
+  const uint32_t wboxF[2] = {(uint32_t)C, (uint32_t)C}, wboxH[2] = {(uint32_t)C, (uint32_t)(C / 2)};
+  const CUtensorMap mBhF = make_map(d.w_hi, 2, wdims, wstr, wboxF, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, swz);
+  const CUtensorMap mBlF = make_map(d.w_lo, 2, wdims, wstr, wboxF, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, swz);
+  const CUtensorMap mBhH = make_map(d.w_hi, 2, wdims, wstr, wboxH, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, swz);
+  const uint64_t adims[3] = {(uint64_t)C, (uint64_t)d.T_in, (uint64_t)d.B};
+  const uint64_t astr[2] = {(uint64_t)d.in_ld * 2, (uint64_t)d.in_bs * 2};
+  const uint32_t abox[3] = {(uint32_t)C, (uint32_t)rowsA, 1};
+  const CUtensorMap mAh = make_map(d.in_hi, 3, adims, astr, abox, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, swz);
+  const CUtensorMap mAl = make_map(d.in_lo, 3, adims, astr, abox, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, swz);
+  int nst = (int)std::min<size_t>(6, (cap - w_bytes - misc) / a_stage);
+  const size_t smem = w_bytes + (size_t)nst * a_stage + misc;
+  const int n_units = (int)ceil_div64(n_blocks, 2);
+  const int n_clusters = std::min(n_units, num_sms / 2);
+  int a_n_mt = n_mt, a_units = n_units, a_rowsA = rowsA, a_nst = nst;
+  void* args[] = {(void*)&mAh, (void*)&mAl, (void*)&mBhF, (void*)&mBlF, (void*)&mBhH, (void*)&d, &a_n_mt, &a_units, &a_rowsA,
+                  &a_nst};
+  const void* kern = (C == 32) ? (const void*)conv1d_umma_wres_pair_kernel<32> : (const void*)conv1d_umma_wres_pair_kernel<64>;
+  ensure_smem_optin(kern, 227 * 1024);
+  cudaGetLastError();
+  PT_CUDA(cudaLaunchKernel(kern, dim3(2 * n_clusters), dim3(US_THREADS), args, smem, s));
+  ++g_launch_count;
+  return true;
+}
+
 // fused AA-Snake -> conv: the weight-resident geometries, fp32 pre-activation input
 bool aa_conv1d_ok(const pttspp_conv1d_desc& d) {
   if (!((d.Cin == 32 && d.Cout == 32 && d.K <= US_MAXK) || (d.Cin == 64 && d.Cout == 64 && d.K <= 7))) return false;
@@ -2470,6 +2681,7 @@ void conv1d_umma_launch(const pttspp_conv1d_desc& d_in, const pttspp_conv1d_desc
 }
 
 void conv1d_umma_cl(const pttspp_conv1d_desc& d, cudaStream_t s) {
+  if (conv1d_umma_wres_pair_try(d, s)) return;
   if (conv1d_umma_c32_ok(d)) conv1d_umma_c32_launch(d, s);
   else conv1d_umma_launch(d, nullptr, s);
 }

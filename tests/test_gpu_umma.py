@@ -380,3 +380,33 @@ def test_conv1d_umma_impl4_pair_equals_streaming(ops, monkeypatch, Cin, Cout, K,
     err = float((_bct(out_pair) - ref).abs().max())
     print(f"impl4 {Cin}->{Cout} k{K} d{dil}: max-abs err {err:.3e}")
     assert err < 1e-5 + 1.2e-8 * K * Cin, err
+
+
+@pytest.mark.parametrize("C,K,dil,B,T", [(32, 11, 5, 2, 40000), (32, 3, 1, 3, 13000), (32, 7, 3, 2, 20001),
+                                         (64, 7, 5, 2, 20000), (64, 3, 1, 3, 13000), (64, 11, 5, 4, 12100),
+                                         (64, 11, 1, 3, 13001)])
+def test_conv1d_umma_wres_pair_equals_single_cta(ops, C, K, dil, B, T):
+    """impl 4 with >= 2 blocks per SM: the CTA-pair form of the weight-resident kernel (cta_group::2, each CTA holds half
+    of the stacked weight operand) == the single-CTA kernels (impl 2) bit for bit, incl. residual / running sum / division,
+    an odd number of 128-row blocks (the last unit is half empty) and the 64-channel k = 11 case only the pair form can
+    hold resident; fp32 class against torch."""
+    from promptttspp_b200 import _abi
+
+    g = torch.Generator().manual_seed(C + K + dil)
+    x = torch.randn(B, C, T, generator=g)
+    w = torch.randn(C, C, K, generator=g) / math.sqrt(C * K)
+    b = torch.randn(C, generator=g)
+    res = torch.randn(B, C, T, generator=g)
+    prev = torch.randn(B, C, T, generator=g)
+    pad = (K * dil - dil) // 2
+    planes = ops.split_f16(_cl(x))
+    wsp = ops.pack_conv_weight_split(w, device="cuda")
+    kw = dict(bias=b.cuda(), K=K, dil=dil, pad=pad, res=_cl(res), beta=1.0, out_div=3.0)
+    out4, _ = ops.conv1d_umma_cl(planes, wsp, C, out=_cl(prev).clone(), impl=4, **kw)
+    out2, _ = ops.conv1d_umma_cl(planes, wsp, C, out=_cl(prev).clone(), impl=2, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(out4, out2), float((out4 - out2).abs().max())
+    ref = (res + F.conv1d(x, w, b, padding=pad, dilation=dil) + prev) / 3.0
+    err = float((_bct(out4) - ref).abs().max())
+    print(f"wres pair {C} k{K} d{dil}: max-abs err {err:.3e}")
+    assert err < 1e-5 + 6e-9 * K * C, err
