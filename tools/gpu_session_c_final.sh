@@ -16,7 +16,7 @@ python tools/gap_profile.py > gpurun_out/r02c_gap_profile_final.txt 2>&1; tail -
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02c_launches_acoustic.csv python bench.py --leg acoustic --steps 1 --warmup 1 > gpurun_out/r02c_launch_ac.log 2>&1
 python tools/summarize_launches.py gpurun_out/r02c_launches_acoustic.csv > gpurun_out/r02c_launches_acoustic_summary.txt; head -12 gpurun_out/r02c_launches_acoustic_summary.txt
 # full captures: weight-resident kernel after the stacked issue, the pair kernel on a long contraction, the activation kernel
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:c32_kernel -s 24 -c 2 -f -o gpurun_out/r02c_c32_full python bench.py --leg bigvgan --steps 1 --warmup 1 > gpurun_out/r02c_ncu_c32.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:wres_pair_kernel -s 48 -c 2 -f -o gpurun_out/r02c_c32_full python bench.py --leg bigvgan --steps 1 --warmup 1 > gpurun_out/r02c_ncu_c32.log 2>&1
 ncu -i gpurun_out/r02c_c32_full.ncu-rep --page raw --csv > gpurun_out/r02c_c32_raw.csv 2>/dev/null; python tools/ncu_summary.py gpurun_out/r02c_c32_raw.csv > gpurun_out/r02c_ncu_c32.txt
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:umma_pair_kernel -s 20 -c 2 -f -o gpurun_out/r02c_pair_full python bench.py --leg bigvgan --steps 1 --warmup 1 > gpurun_out/r02c_ncu_pair.log 2>&1
 ncu -i gpurun_out/r02c_pair_full.ncu-rep --page raw --csv > gpurun_out/r02c_pair_raw.csv 2>/dev/null; python tools/ncu_summary.py gpurun_out/r02c_pair_raw.csv > gpurun_out/r02c_ncu_pair.txt
